@@ -1,0 +1,283 @@
+/* ncnn_cuda.h -- the thin C ABI between the host C++ runtime (ncnn_b200/csrc/host) and the
+ * hand-written sm_100a kernels (ncnn_b200/csrc/cuda).
+ *
+ * Everything here is `extern "C"`, POD arguments only, `cudaStream_t` travels as `void*`,
+ * no C++ types and no exceptions cross the boundary.  Return codes follow the reference's
+ * convention (SURVEY.md 8b "errors"): 0 ok, -1 invalid / unsupported argument, -100 out of
+ * memory or CUDA failure (reference: src/layer/convolution.cpp:64-71, src/net.cpp:641-642).
+ *
+ * What each group replaces in the reference (Tencent/ncnn @ a4d2ea1d):
+ *   device/memory/stream ... VulkanDevice + VkAllocator::fastMalloc/fastFree (src/allocator.h:267-296)
+ *                            and VkCompute::record_upload/record_download/submit_and_wait
+ *                            (src/command.h:22-88)
+ *   ncnn_cuda_tensor ........ VkMat (src/mat.h:387-555): a non-owning POD view of a device blob
+ *   conv2d/dwconv2d/...  .... the bodies of Layer::forward for the hot-path operators
+ *                            (src/layer/<op>.cpp, file:line cited per entry point)
+ *
+ * DEVICE LAYOUT (private to this backend; the host Mat layout of src/mat.h is converted at
+ * upload/download): a blob is [n][P][cpitch] "pixels x channels", channels innermost:
+ *     dims 1 (w)        : P = 1,     C = w
+ *     dims 2 (w,h)      : P = h,     C = w
+ *     dims 3 (w,h,c)    : P = h*w,   C = c      (NHWC)
+ *     dims 4 (w,h,d,c)  : P = d*h*w, C = c
+ * element (b, pixel p, channel q) lives at data[b*nstep + p*cpitch + q]; cpitch >= C
+ * (16-byte multiple for 16-bit types so that TMA can address rows), nstep >= P*cpitch.
+ * Lanes q in [C, cpitch) are padding: kernels never rely on their value.
+ */
+#ifndef NCNN_CUDA_H
+#define NCNN_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NCNN_CUDA_API __attribute__((visibility("default")))
+#else
+#define NCNN_CUDA_API
+#endif
+
+/* element types of device blobs */
+#define NCNN_CUDA_F32  0
+#define NCNN_CUDA_BF16 1
+#define NCNN_CUDA_F16  2
+
+typedef struct ncnn_cuda_tensor
+{
+    void* data;       /* device pointer */
+    int dims;         /* 1..4, as ncnn::Mat::dims */
+    int w, h, d, c;   /* logical ncnn shape */
+    int n;            /* batch (ncnn::Mat::n, src/mat.h:373-381) */
+    int elemtype;     /* NCNN_CUDA_F32 / BF16 / F16 */
+    int cpitch;       /* elements between consecutive pixels */
+    long long nstep;  /* elements between consecutive samples */
+} ncnn_cuda_tensor;
+
+/* host Mat view used by upload/download (reference layout, src/mat.cpp:299-861):
+ * planar, element (b,q,z,y,x) at data[b*nstep + q*cstep + (z*h+y)*w + x], fp32 */
+typedef struct ncnn_cuda_hostmat
+{
+    void* data;       /* host OR device pointer to fp32 planar data */
+    int dims;
+    int w, h, d, c, n;
+    long long cstep;  /* elements */
+    long long nstep;  /* elements */
+} ncnn_cuda_hostmat;
+
+/* ------------------------------------------------------------------ device / memory / stream */
+NCNN_CUDA_API int ncnn_cuda_device_count(void);
+NCNN_CUDA_API int ncnn_cuda_set_device(int index);
+NCNN_CUDA_API int ncnn_cuda_get_device(void);
+/* name: >= 256 bytes. Any out pointer may be NULL. */
+NCNN_CUDA_API int ncnn_cuda_device_info(int index, char* name, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+NCNN_CUDA_API const char* ncnn_cuda_last_error(void);
+
+NCNN_CUDA_API int ncnn_cuda_malloc(void** ptr, size_t size);
+NCNN_CUDA_API int ncnn_cuda_free(void* ptr);
+NCNN_CUDA_API int ncnn_cuda_malloc_host(void** ptr, size_t size); /* pinned */
+NCNN_CUDA_API int ncnn_cuda_free_host(void* ptr);
+NCNN_CUDA_API int ncnn_cuda_memcpy_h2d_async(void* dst, const void* src, size_t size, void* stream);
+NCNN_CUDA_API int ncnn_cuda_memcpy_d2h_async(void* dst, const void* src, size_t size, void* stream);
+NCNN_CUDA_API int ncnn_cuda_memcpy_d2d_async(void* dst, const void* src, size_t size, void* stream);
+NCNN_CUDA_API int ncnn_cuda_memset_async(void* dst, int value, size_t size, void* stream);
+
+NCNN_CUDA_API int ncnn_cuda_stream_create(void** stream);
+NCNN_CUDA_API int ncnn_cuda_stream_destroy(void* stream);
+NCNN_CUDA_API int ncnn_cuda_stream_sync(void* stream);
+NCNN_CUDA_API int ncnn_cuda_device_sync(void);
+
+NCNN_CUDA_API int ncnn_cuda_event_create(void** event);
+NCNN_CUDA_API int ncnn_cuda_event_destroy(void* event);
+NCNN_CUDA_API int ncnn_cuda_event_record(void* event, void* stream);
+NCNN_CUDA_API int ncnn_cuda_event_sync(void* event);
+NCNN_CUDA_API int ncnn_cuda_event_elapsed_ms(void* start, void* stop, float* ms);
+
+/* CUDA graph capture of one recorded forward walk (the analogue of re-submitting a recorded
+ * VkCompute command buffer, src/command.cpp:1834) */
+NCNN_CUDA_API int ncnn_cuda_graph_begin_capture(void* stream);
+NCNN_CUDA_API int ncnn_cuda_graph_end_capture(void* stream, void** graph_exec);
+NCNN_CUDA_API int ncnn_cuda_graph_launch(void* graph_exec, void* stream);
+NCNN_CUDA_API int ncnn_cuda_graph_destroy(void* graph_exec);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+NCNN_CUDA_API unsigned long long ncnn_cuda_launch_count(void);
+
+/* ------------------------------------------------------------------ layout conversion
+ * pack: planar fp32 (host layout, but `src->data` must be DEVICE memory: the caller has
+ * already copied the raw Mat bytes) -> device blob layout/dtype.  unpack: the inverse.
+ * Replaces VkCompute::record_upload/record_download + Packing/Cast (src/command.cpp:358,439). */
+NCNN_CUDA_API int ncnn_cuda_pack_from_planar(const ncnn_cuda_hostmat* src, const ncnn_cuda_tensor* dst, void* stream);
+NCNN_CUDA_API int ncnn_cuda_unpack_to_planar(const ncnn_cuda_tensor* src, const ncnn_cuda_hostmat* dst, void* stream);
+/* general re-layout: dst's logical element order (ncnn dense order n, c, d, h, w) is taken from
+ * src's logical order: covers Reshape / Flatten (src/layer/reshape.cpp, flatten.cpp), dtype casts
+ * and clone (VkCompute::record_clone). Total logical element counts per sample must match. */
+NCNN_CUDA_API int ncnn_cuda_reshape(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, void* stream);
+/* Permute (src/layer/permute.cpp:16-164): order_type as in the reference */
+NCNN_CUDA_API int ncnn_cuda_permute(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, int order_type, void* stream);
+
+/* ------------------------------------------------------------------ fused activation
+ * activation_type / params exactly as src/layer/fused_activation.h:10-64:
+ * 0 none, 1 relu, 2 leakyrelu(slope), 3 clip(min,max), 4 sigmoid, 5 mish, 6 hardswish(alpha,beta) */
+typedef struct ncnn_cuda_activation
+{
+    int type;
+    float p0, p1;
+} ncnn_cuda_activation;
+
+/* ------------------------------------------------------------------ Convolution
+ * src/layer/convolution.cpp:113-184 (+ make_padding :328-372).  Weights arrive in the
+ * reference order [outch][inch][kh][kw] fp32 (convolution.cpp:159) and are re-packed ONCE
+ * (the create_pipeline step, as convolution_x86.cpp:279-500 / convolution_vulkan.cpp do). */
+typedef struct ncnn_cuda_conv2d_desc
+{
+    int inch, outch;
+    int kernel_w, kernel_h, dilation_w, dilation_h, stride_w, stride_h;
+    int pad_left, pad_right, pad_top, pad_bottom; /* resolved, >= 0 (host resolves -233/-234 per input size) */
+    float pad_value;
+    int bias_term;
+    ncnn_cuda_activation act;
+    int elemtype; /* compute/storage type of the blobs this pipeline will see */
+} ncnn_cuda_conv2d_desc;
+
+typedef struct ncnn_cuda_conv2d* ncnn_cuda_conv2d_t;
+
+NCNN_CUDA_API int ncnn_cuda_conv2d_create(ncnn_cuda_conv2d_t* conv, const ncnn_cuda_conv2d_desc* desc, const float* weight_host, const float* bias_host, void* stream);
+NCNN_CUDA_API int ncnn_cuda_conv2d_destroy(ncnn_cuda_conv2d_t conv);
+/* pads may differ per call (SAME modes depend on the input size); pass desc pads for fixed padding.
+ * `residual` (may be NULL): fused `top = act(conv + bias + residual)`, the Eltwise-SUM(+ReLU) fold
+ * (tools/ncnnoptimize.cpp-style fusion done at load time). */
+NCNN_CUDA_API int ncnn_cuda_conv2d_forward(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top,
+                                           int pad_left, int pad_top, const ncnn_cuda_tensor* residual, const ncnn_cuda_activation* act_override,
+                                           void* workspace, size_t workspace_size, void* stream);
+/* bytes of scratch `forward` needs for this input shape (0 for the implicit-GEMM paths) */
+NCNN_CUDA_API size_t ncnn_cuda_conv2d_workspace_size(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top);
+/* which kernel family a call would use: 0 SIMT fp32, 1 tcgen05 GEMM (1x1), 2 tcgen05 implicit GEMM (TMA im2col), 3 tcgen05 + explicit im2col */
+NCNN_CUDA_API int ncnn_cuda_conv2d_algo(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom);
+
+/* ------------------------------------------------------------------ ConvolutionDepthWise
+ * src/layer/convolutiondepthwise.cpp:146-270.  group == channels == num_output is the
+ * depthwise branch (:181-214); other groupings run the grouped branch (:216-267).
+ * weights [group][outch_g][inch_g][kh][kw]. */
+typedef struct ncnn_cuda_dwconv2d_desc
+{
+    int inch, outch, group;
+    int kernel_w, kernel_h, dilation_w, dilation_h, stride_w, stride_h;
+    float pad_value;
+    int bias_term;
+    ncnn_cuda_activation act;
+    int elemtype;
+} ncnn_cuda_dwconv2d_desc;
+
+typedef struct ncnn_cuda_dwconv2d* ncnn_cuda_dwconv2d_t;
+
+NCNN_CUDA_API int ncnn_cuda_dwconv2d_create(ncnn_cuda_dwconv2d_t* conv, const ncnn_cuda_dwconv2d_desc* desc, const float* weight_host, const float* bias_host, void* stream);
+NCNN_CUDA_API int ncnn_cuda_dwconv2d_destroy(ncnn_cuda_dwconv2d_t conv);
+NCNN_CUDA_API int ncnn_cuda_dwconv2d_forward(ncnn_cuda_dwconv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top,
+                                             int pad_left, int pad_top, void* stream);
+
+/* ------------------------------------------------------------------ Pooling
+ * src/layer/pooling.cpp:39-348 (+ make_padding :350-412).  The host resolves pad_mode into
+ * pad_left/pad_top and the output size; the kernel treats everything outside the real input as
+ * padding (max: ignored; avg: excluded from the divisor unless count_include_pad, in which case
+ * the divisor is kernel_w*kernel_h exactly as :317-343). */
+typedef struct ncnn_cuda_pool2d_desc
+{
+    int pooling_type; /* 0 max, 1 avg */
+    int kernel_w, kernel_h, stride_w, stride_h;
+    int pad_left, pad_top;
+    int global_pooling;
+    int avgpool_count_include_pad;
+    int adaptive_pooling; /* output size taken from `top` */
+    /* count_include_pad only counts the explicit pads, not the pad_mode-0 tail (pooling.cpp:262-266):
+     * padded extent that counts = w + pad_left + pad_right_counted */
+    int pad_right, pad_bottom;
+} ncnn_cuda_pool2d_desc;
+
+NCNN_CUDA_API int ncnn_cuda_pool2d_forward(const ncnn_cuda_pool2d_desc* desc, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
+
+/* ------------------------------------------------------------------ InnerProduct / Gemm
+ * A dense layer over the "pixels x channels" view:  top[m][p] = act(bias[p] + sum_k bottom[m][k] * W[p][k]).
+ * InnerProduct (src/layer/innerproduct.cpp:84-165): weights [num_output][num_input] with num_input in the
+ * reference's flattened c-major order; `in_w,in_h,in_c` describe a 3-D bottom so create() can permute the
+ * columns into this backend's channel-innermost order (VGG16 fc6 sees a 7x7x512 blob).
+ * Implemented by the same kernels as a 1x1 convolution. */
+typedef struct ncnn_cuda_linear_desc
+{
+    int num_input, num_output;
+    int bias_term;
+    ncnn_cuda_activation act;
+    int elemtype;
+    int in_w, in_h, in_c; /* 0,0,0 = bottom rows are already dense K vectors */
+} ncnn_cuda_linear_desc;
+
+typedef struct ncnn_cuda_conv2d* ncnn_cuda_linear_t; /* same object as a 1x1 conv */
+
+NCNN_CUDA_API int ncnn_cuda_linear_create(ncnn_cuda_linear_t* fc, const ncnn_cuda_linear_desc* desc, const float* weight_host, const float* bias_host, void* stream);
+NCNN_CUDA_API int ncnn_cuda_linear_destroy(ncnn_cuda_linear_t fc);
+/* bottom: M x K view (rows = n * P), top: M x num_output */
+NCNN_CUDA_API int ncnn_cuda_linear_forward(ncnn_cuda_linear_t fc, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
+
+/* General matrix product for Gemm (src/layer/gemm.cpp:250-315) with runtime A and B:
+ * C[i][j] = alpha * sum_k A(i,k) * B(k,j) + beta * Cin(broadcast), strided fp32-accumulate SIMT kernel.
+ * A(i,k) = a[i*a_rs + k*a_cs] etc.; c_* strides may be 0 for broadcasting (gemm.cpp:274-293). */
+typedef struct ncnn_cuda_gemm_args
+{
+    int M, N, K, batch;
+    const void* a; long long a_rs, a_cs, a_bs;
+    const void* b; long long b_rs, b_cs, b_bs;
+    const void* c; long long c_rs, c_cs, c_bs; /* c may be NULL */
+    void* out; long long o_rs, o_cs, o_bs;
+    float alpha, beta;
+    int elemtype;   /* of a, b, out */
+    int c_elemtype; /* of c (bias constants are kept fp32) */
+} ncnn_cuda_gemm_args;
+
+NCNN_CUDA_API int ncnn_cuda_gemm_strided(const ncnn_cuda_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------ glue operators */
+/* unary, in place allowed (bottom == top).  op: see NCNN_CUDA_UNARY_*.
+ * ReLU src/layer/relu.cpp:16-50 (p0 = slope), Sigmoid sigmoid.cpp, Swish swish.cpp:14-35,
+ * plus the fused_activation codes so a standalone activation layer can reuse them. */
+#define NCNN_CUDA_UNARY_RELU      1 /* p0 = negative slope */
+#define NCNN_CUDA_UNARY_CLIP      3 /* p0 = min, p1 = max */
+#define NCNN_CUDA_UNARY_SIGMOID   4
+#define NCNN_CUDA_UNARY_MISH      5
+#define NCNN_CUDA_UNARY_HARDSWISH 6 /* p0 = alpha, p1 = beta */
+#define NCNN_CUDA_UNARY_SWISH     7
+#define NCNN_CUDA_UNARY_SCALE     8 /* x * p0 (Dropout with scale != 1, dropout.cpp:14-40) */
+#define NCNN_CUDA_UNARY_TANH      9
+#define NCNN_CUDA_UNARY_HARDSIGMOID 10 /* p0 = alpha, p1 = beta */
+NCNN_CUDA_API int ncnn_cuda_unary(int op, float p0, float p1, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
+
+/* Eltwise src/layer/eltwise.cpp:22-178: op 0 PROD, 1 SUM (optional coeffs), 2 MAX over `count` same-shape
+ * bottoms; `relu` fuses a following ReLU layer (graph-level fold). */
+NCNN_CUDA_API int ncnn_cuda_eltwise(int op, const ncnn_cuda_tensor* bottoms, int count, const float* coeffs, int relu, const ncnn_cuda_tensor* top, void* stream);
+
+/* BinaryOp src/layer/binaryop.cpp (op codes binaryop.h:24-45) with numpy-style broadcasting over the
+ * logical (w,h,d,c) dims (docs/developer-guide/binaryop-broadcasting.md); b may be NULL for the
+ * with_scalar form (then `scalar` is used). */
+NCNN_CUDA_API int ncnn_cuda_binaryop(int op, const ncnn_cuda_tensor* a, const ncnn_cuda_tensor* b, float scalar, const ncnn_cuda_tensor* top, void* stream);
+
+/* Concat src/layer/concat.cpp:14-292 / Slice src/layer/slice.cpp: `axis` is the reference's positive axis
+ * index for the blob rank (3-D: 0 = c, 1 = h, 2 = w).  One call copies one bottom into `top` at element
+ * offset `offset` along that axis (concat), or the range [offset, offset + extent(top)) of `bottom` (slice). */
+NCNN_CUDA_API int ncnn_cuda_copy_into_axis(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int axis, int offset, void* stream);
+NCNN_CUDA_API int ncnn_cuda_copy_from_axis(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int axis, int offset, void* stream);
+
+/* Interp src/layer/interp.cpp: resize_type 1 nearest (:606-625; hs/ws are the reference's float source steps,
+ * in_y = min((int)(y*hs), h-1)), 2 bilinear (linear_coeffs :56-90, align_corner 0/1; hs/ws unused) */
+NCNN_CUDA_API int ncnn_cuda_interp(int resize_type, int align_corner, float hs, float ws, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
+
+/* Softmax src/layer/softmax.cpp:32-250 along the reference's positive axis for the blob rank; in place allowed */
+NCNN_CUDA_API int ncnn_cuda_softmax(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int axis, void* stream);
+
+/* Padding src/layer/padding.cpp: constant (type 0), replicate (1), reflect (2) on w/h (and c via front/behind) */
+NCNN_CUDA_API int ncnn_cuda_padding(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int top_pad, int left_pad, int front_pad, int type, float value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NCNN_CUDA_H */

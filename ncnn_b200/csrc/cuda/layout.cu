@@ -1,0 +1,302 @@
+// layout.cu -- conversions between the reference's planar Mat layout (src/mat.cpp:299-861) and this
+// backend's channel-innermost device layout, plus Reshape / Flatten / Permute / cast / clone.
+#include "common.cuh"
+
+namespace ncnn_cuda {
+
+struct DShape
+{
+    int dims, w, h, d, c;
+    int cpitch;
+    long long nstep;
+
+    __host__ __device__ long long logical_count() const
+    {
+        if (dims == 1) return w;
+        if (dims == 2) return (long long)w * h;
+        if (dims == 3) return (long long)w * h * c;
+        return (long long)w * h * d * c;
+    }
+    // logical flat index (ncnn dense order: c, d, h, w) -> physical offset within a sample
+    __device__ long long phys_of_logical(long long i) const
+    {
+        if (dims == 1) return i;
+        if (dims == 2)
+        {
+            long long y = i / w;
+            int x = (int)(i - y * w);
+            return y * cpitch + x;
+        }
+        long long plane = (long long)w * h * (dims == 4 ? d : 1);
+        long long q = i / plane;
+        long long p = i - q * plane;
+        return p * cpitch + q;
+    }
+};
+
+static inline DShape dshape(const ncnn_cuda_tensor* t)
+{
+    DShape s;
+    s.dims = t->dims;
+    s.w = t->w;
+    s.h = t->dims >= 2 ? t->h : 1;
+    s.d = t->dims == 4 ? t->d : 1;
+    s.c = t->dims >= 3 ? t->c : 1;
+    s.cpitch = t->cpitch;
+    s.nstep = t->nstep;
+    return s;
+}
+
+// ---------------------------------------------------------------- planar <-> pixels x channels
+// Tiled transpose through shared memory so both sides are coalesced: tile = 32 pixels x 32 channels.
+template<typename TD, bool PACK>
+__global__ void planar_transpose_kernel(float* __restrict__ planar, long long cstep, long long pl_nstep,
+                                        TD* __restrict__ dev, int cpitch, long long dv_nstep, int P, int C)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32;
+    const int q0 = blockIdx.y * 32;
+    float* pl = planar + (long long)b * pl_nstep;
+    TD* dv = dev + (long long)b * dv_nstep;
+    if (PACK)
+    {
+        // read planar: threads along pixels
+        for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        {
+            int q = q0 + j, p = p0 + threadIdx.x;
+            if (q < C && p < P) tile[j][threadIdx.x] = pl[(long long)q * cstep + p];
+        }
+        __syncthreads();
+        // write device: threads along channels
+        for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        {
+            int p = p0 + j, q = q0 + threadIdx.x;
+            if (p < P && q < cpitch) dv[(long long)p * cpitch + q] = from_f32<TD>(q < C ? tile[threadIdx.x][j] : 0.f);
+        }
+    }
+    else
+    {
+        for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        {
+            int p = p0 + j, q = q0 + threadIdx.x;
+            if (p < P && q < C) tile[j][threadIdx.x] = to_f32(dv[(long long)p * cpitch + q]);
+        }
+        __syncthreads();
+        for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        {
+            int q = q0 + j, p = p0 + threadIdx.x;
+            if (q < C && p < P) pl[(long long)q * cstep + p] = tile[threadIdx.x][j];
+        }
+    }
+}
+
+// dims 1/2: both sides are row-major [P][C]; only pitch and dtype differ
+template<typename TD, bool PACK>
+__global__ void planar_rows_kernel(float* __restrict__ planar, long long pl_nstep, TD* __restrict__ dev, int cpitch,
+                                   long long dv_nstep, int P, int C, int n)
+{
+    long long total = (long long)n * P * cpitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        int q = (int)(i % cpitch);
+        long long r = i / cpitch;
+        int p = (int)(r % P);
+        int b = (int)(r / P);
+        float* pl = planar + (long long)b * pl_nstep + (long long)p * C;
+        TD* dv = dev + (long long)b * dv_nstep + (long long)p * cpitch;
+        if (PACK)
+            dv[q] = from_f32<TD>(q < C ? pl[q] : 0.f);
+        else if (q < C)
+            pl[q] = to_f32(dv[q]);
+    }
+}
+
+template<typename TD, bool PACK>
+static int planar_convert(const ncnn_cuda_hostmat* hm, const ncnn_cuda_tensor* t, cudaStream_t stream)
+{
+    TView v = make_view(t);
+    NC_REQUIRE(hm->dims == t->dims && hm->w == t->w && (t->dims < 2 || hm->h == t->h) && (t->dims < 3 || hm->c == t->c) && (t->dims < 4 || hm->d == t->d),
+               "pack/unpack: host and device shapes differ");
+    int n = v.n;
+    if (t->dims <= 2)
+    {
+        long long total = (long long)n * v.P * v.cpitch;
+        planar_rows_kernel<TD, PACK><<<grid_for(total, 256), 256, 0, stream>>>((float*)hm->data, hm->nstep, (TD*)t->data, v.cpitch, v.nstep, v.P, v.C, n);
+        NC_LAUNCH_CHECK();
+        return 0;
+    }
+    dim3 block(32, 8);
+    int cspan = PACK ? v.cpitch : v.C;
+    dim3 grid(ceil_div(v.P, 32), ceil_div(cspan, 32), n);
+    planar_transpose_kernel<TD, PACK><<<grid, block, 0, stream>>>((float*)hm->data, hm->cstep, hm->nstep, (TD*)t->data, v.cpitch, v.nstep, v.P, v.C);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------- generic gather (reshape / permute / cast)
+struct PermuteMap
+{
+    int src_of[4]; // for out logical dim i (0=w,1=h,2=d,3=c): which src logical dim supplies it
+};
+
+template<typename TS, typename TD, bool PERMUTE>
+__global__ void gather_kernel(const TS* __restrict__ src, DShape ss, TD* __restrict__ dst, DShape ds, int n, PermuteMap pm)
+{
+    const int dP = ds.dims == 1 ? 1 : (ds.dims == 2 ? ds.h : ds.w * ds.h * ds.d);
+    const int dC = ds.dims == 1 ? ds.w : (ds.dims == 2 ? ds.w : ds.c);
+    long long total = (long long)n * dP * dC;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        int q = (int)(i % dC);
+        long long r = i / dC;
+        int p = (int)(r % dP);
+        int b = (int)(r / dP);
+        // out logical coords
+        int ox, oy, oz, oc;
+        if (ds.dims == 1)
+        {
+            ox = q; oy = 0; oz = 0; oc = 0;
+        }
+        else if (ds.dims == 2)
+        {
+            ox = q; oy = p; oz = 0; oc = 0;
+        }
+        else
+        {
+            ox = p % ds.w;
+            int t = p / ds.w;
+            oy = t % ds.h;
+            oz = t / ds.h;
+            oc = q;
+        }
+        long long sphys;
+        if (PERMUTE)
+        {
+            int oc4[4] = {ox, oy, oz, oc};
+            int sc[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 4; k++) sc[pm.src_of[k]] = oc4[k];
+            // src logical coords (x,y,z,ch)
+            if (ss.dims == 1)
+                sphys = sc[0];
+            else if (ss.dims == 2)
+                sphys = (long long)sc[1] * ss.cpitch + sc[0];
+            else
+                sphys = ((long long)(sc[2] * ss.h + sc[1]) * ss.w + sc[0]) * ss.cpitch + sc[3];
+        }
+        else
+        {
+            long long flat = (((long long)oc * ds.d + oz) * ds.h + oy) * ds.w + ox;
+            sphys = ss.phys_of_logical(flat);
+        }
+        long long dphys = ds.dims == 1 ? q : (long long)p * ds.cpitch + q;
+        dst[(long long)b * ds.nstep + dphys] = from_f32<TD>(to_f32(src[(long long)b * ss.nstep + sphys]));
+    }
+}
+
+template<typename TS, typename TD>
+static int launch_gather(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, bool permute, const PermuteMap& pm, cudaStream_t stream)
+{
+    DShape ss = dshape(src), ds = dshape(dst);
+    int n = dst->n < 1 ? 1 : dst->n;
+    long long total = (long long)n * ds.logical_count();
+    if (total == 0) return 0;
+    if (permute)
+        gather_kernel<TS, TD, true><<<grid_for(total, 256), 256, 0, stream>>>((const TS*)src->data, ss, (TD*)dst->data, ds, n, pm);
+    else
+        gather_kernel<TS, TD, false><<<grid_for(total, 256), 256, 0, stream>>>((const TS*)src->data, ss, (TD*)dst->data, ds, n, pm);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+static int dispatch_gather(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, bool permute, const PermuteMap& pm, cudaStream_t stream)
+{
+#define NC_G(TS, TD) return launch_gather<TS, TD>(src, dst, permute, pm, stream)
+    int s = src->elemtype, d = dst->elemtype;
+    if (s == NCNN_CUDA_F32 && d == NCNN_CUDA_F32) NC_G(float, float);
+    if (s == NCNN_CUDA_F32 && d == NCNN_CUDA_BF16) NC_G(float, __nv_bfloat16);
+    if (s == NCNN_CUDA_F32 && d == NCNN_CUDA_F16) NC_G(float, __half);
+    if (s == NCNN_CUDA_BF16 && d == NCNN_CUDA_F32) NC_G(__nv_bfloat16, float);
+    if (s == NCNN_CUDA_BF16 && d == NCNN_CUDA_BF16) NC_G(__nv_bfloat16, __nv_bfloat16);
+    if (s == NCNN_CUDA_F16 && d == NCNN_CUDA_F32) NC_G(__half, float);
+    if (s == NCNN_CUDA_F16 && d == NCNN_CUDA_F16) NC_G(__half, __half);
+#undef NC_G
+    set_last_error_msg("reshape/permute: unsupported element type pair");
+    return -1;
+}
+
+} // namespace ncnn_cuda
+
+using namespace ncnn_cuda;
+
+extern "C" {
+
+int ncnn_cuda_pack_from_planar(const ncnn_cuda_hostmat* src, const ncnn_cuda_tensor* dst, void* stream)
+{
+    switch (dst->elemtype)
+    {
+    case NCNN_CUDA_F32: return planar_convert<float, true>(src, dst, as_stream(stream));
+    case NCNN_CUDA_BF16: return planar_convert<__nv_bfloat16, true>(src, dst, as_stream(stream));
+    case NCNN_CUDA_F16: return planar_convert<__half, true>(src, dst, as_stream(stream));
+    }
+    return -1;
+}
+
+int ncnn_cuda_unpack_to_planar(const ncnn_cuda_tensor* src, const ncnn_cuda_hostmat* dst, void* stream)
+{
+    switch (src->elemtype)
+    {
+    case NCNN_CUDA_F32: return planar_convert<float, false>(dst, src, as_stream(stream));
+    case NCNN_CUDA_BF16: return planar_convert<__nv_bfloat16, false>(dst, src, as_stream(stream));
+    case NCNN_CUDA_F16: return planar_convert<__half, false>(dst, src, as_stream(stream));
+    }
+    return -1;
+}
+
+int ncnn_cuda_reshape(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, void* stream)
+{
+    DShape ss = dshape(src), ds = dshape(dst);
+    NC_REQUIRE(ss.logical_count() == ds.logical_count(), "reshape: element counts differ");
+    NC_REQUIRE((src->n < 1 ? 1 : src->n) == (dst->n < 1 ? 1 : dst->n), "reshape: batch differs");
+    PermuteMap pm = {{0, 1, 2, 3}};
+    return dispatch_gather(src, dst, false, pm, as_stream(stream));
+}
+
+int ncnn_cuda_permute(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, int order_type, void* stream)
+{
+    // tables: new (w,h,[d,]c) named in terms of the old dims, src/layer/permute.cpp:38-41, 66-73, 188-212
+    // encoded as src_of[new dim] with 0=w 1=h 2=d 3=c
+    static const int t2[2][2] = {{0, 1}, {1, 0}};
+    static const int t3[6][3] = {{0, 1, 3}, {1, 0, 3}, {0, 3, 1}, {3, 0, 1}, {1, 3, 0}, {3, 1, 0}};
+    static const int t4[24][4] = {
+        {0, 1, 2, 3}, {1, 0, 2, 3}, {0, 2, 1, 3}, {2, 0, 1, 3}, {1, 2, 0, 3}, {2, 1, 0, 3},
+        {0, 1, 3, 2}, {1, 0, 3, 2}, {0, 3, 1, 2}, {3, 0, 1, 2}, {1, 3, 0, 2}, {3, 1, 0, 2},
+        {0, 2, 3, 1}, {2, 0, 3, 1}, {0, 3, 2, 1}, {3, 0, 2, 1}, {2, 3, 0, 1}, {3, 2, 0, 1},
+        {1, 2, 3, 0}, {2, 1, 3, 0}, {1, 3, 2, 0}, {3, 1, 2, 0}, {2, 3, 1, 0}, {3, 2, 1, 0}};
+    PermuteMap pm = {{0, 1, 2, 3}};
+    NC_REQUIRE(src->dims == dst->dims, "permute: rank differs");
+    if (src->dims == 2)
+    {
+        NC_REQUIRE(order_type >= 0 && order_type < 2, "permute: bad order_type");
+        pm.src_of[0] = t2[order_type][0];
+        pm.src_of[1] = t2[order_type][1];
+    }
+    else if (src->dims == 3)
+    {
+        NC_REQUIRE(order_type >= 0 && order_type < 6, "permute: bad order_type");
+        // 3-D blobs have no d: (w,h,c) -> logical slots 0,1,3
+        pm.src_of[0] = t3[order_type][0];
+        pm.src_of[1] = t3[order_type][1];
+        pm.src_of[2] = 2;
+        pm.src_of[3] = t3[order_type][2];
+    }
+    else if (src->dims == 4)
+    {
+        NC_REQUIRE(order_type >= 0 && order_type < 24, "permute: bad order_type");
+        for (int i = 0; i < 4; i++) pm.src_of[i] = t4[order_type][i];
+    }
+    return dispatch_gather(src, dst, true, pm, as_stream(stream));
+}
+
+} // extern "C"

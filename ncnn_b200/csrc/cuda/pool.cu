@@ -1,0 +1,183 @@
+// pool.cu -- Pooling (src/layer/pooling.cpp:39-348, padding rules :350-412 of the reference).
+// Bandwidth-bound: one thread owns a 16-byte channel vector of one output pixel; consecutive threads walk
+// channels then pixels, so every tap is a fully coalesced row segment of the channel-innermost blob.
+// No padded copy is materialised (the reference's copy_make_border sweep disappears): out-of-image taps are
+// skipped for max, and contribute 0 / are excluded from the divisor for avg exactly as :255-343.
+#include "common.cuh"
+
+using namespace ncnn_cuda;
+
+namespace {
+
+struct PoolGeom
+{
+    int C, inw, inh, outw, outh, n;
+    int kw, kh, sw, sh, pad_left, pad_top, pad_right, pad_bottom;
+    int type, global, include_pad, adaptive;
+    int in_cpitch, out_cpitch;
+    long long in_nstep, out_nstep;
+};
+
+template<typename T, int VEC>
+__global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* __restrict__ out, PoolGeom g)
+{
+    const int CV = (g.C + VEC - 1) / VEC;
+    const long long total = (long long)g.n * g.outh * g.outw * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        const int cv = (int)(idx % CV);
+        long long r = idx / CV;
+        const int ox = (int)(r % g.outw);
+        r /= g.outw;
+        const int oy = (int)(r % g.outh);
+        const int b = (int)(r / g.outh);
+        const int c0 = cv * VEC;
+        const T* inb = in + (long long)b * g.in_nstep + c0;
+
+        int y0, y1, x0, x1; // window in input coordinates, [y0,y1) x [x0,x1), may stick out of the image
+        if (g.global)
+        {
+            y0 = 0; y1 = g.inh; x0 = 0; x1 = g.inw;
+        }
+        else if (g.adaptive)
+        {
+            y0 = g.inh * oy / g.outh;
+            y1 = (g.inh * (oy + 1) + g.outh - 1) / g.outh;
+            x0 = g.inw * ox / g.outw;
+            x1 = (g.inw * (ox + 1) + g.outw - 1) / g.outw;
+        }
+        else
+        {
+            y0 = oy * g.sh - g.pad_top;
+            y1 = y0 + g.kh;
+            x0 = ox * g.sw - g.pad_left;
+            x1 = x0 + g.kw;
+        }
+        float acc[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] = g.type == 0 ? -FLT_MAX : 0.f;
+        int area = 0;
+        for (int iy = y0; iy < y1; iy++)
+        {
+            if (iy < 0 || iy >= g.inh) continue;
+            for (int ix = x0; ix < x1; ix++)
+            {
+                if (ix < 0 || ix >= g.inw) continue;
+                float xv[VEC];
+                load_vec_f32<T, VEC>(inb + ((long long)iy * g.inw + ix) * g.in_cpitch, xv);
+                if (g.type == 0)
+                {
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[v] = fmaxf(acc[v], xv[v]);
+                }
+                else
+                {
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) acc[v] += xv[v];
+                }
+                area++;
+            }
+        }
+        if (g.type == 1)
+        {
+            if (g.global)
+            {
+                const float size = (float)(g.inw * g.inh);
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] = acc[v] / size;
+            }
+            else if (g.adaptive)
+            {
+                const float hk = (float)(y1 - y0), wk = (float)(x1 - x0);
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] = acc[v] / hk / wk;
+            }
+            else if (g.include_pad)
+            {
+                const float maxk = (float)(g.kw * g.kh);
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] = acc[v] / maxk;
+            }
+            else
+            {
+                const float a = (float)area; // 0 -> 0/0 = NaN, as the reference's `sum / area`
+#pragma unroll
+                for (int v = 0; v < VEC; v++) acc[v] = acc[v] / a;
+            }
+        }
+        T* o = out + (long long)b * g.out_nstep + ((long long)oy * g.outw + ox) * g.out_cpitch + c0;
+        store_vec_f32<T, VEC>(o, acc);
+    }
+}
+
+template<typename T>
+static int run_pool(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const PoolGeom& g, cudaStream_t stream)
+{
+    constexpr int VEC = 16 / sizeof(T);
+    const int cround = ((g.C + VEC - 1) / VEC) * VEC;
+    const bool vec_ok = (g.in_cpitch % VEC == 0) && (g.out_cpitch % VEC == 0) && (g.in_nstep % VEC == 0) && (g.out_nstep % VEC == 0)
+                        && (((uintptr_t)bottom->data & 15) == 0) && (((uintptr_t)top->data & 15) == 0) && cround <= g.in_cpitch && cround <= g.out_cpitch;
+    if (vec_ok)
+    {
+        long long total = (long long)g.n * g.outh * g.outw * (cround / VEC);
+        pool_kernel<T, VEC><<<grid_for(total, 256, 16), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, g);
+    }
+    else
+    {
+        long long total = (long long)g.n * g.outh * g.outw * g.C;
+        pool_kernel<T, 1><<<grid_for(total, 256, 16), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, g);
+    }
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace
+
+extern "C" int ncnn_cuda_pool2d_forward(const ncnn_cuda_pool2d_desc* d, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream_)
+{
+    cudaStream_t stream = as_stream(stream_);
+    NC_REQUIRE(d && bottom && top && bottom->dims == 3, "pool2d_forward: a 3-D bottom blob is required");
+    NC_REQUIRE(bottom->elemtype == top->elemtype, "pool2d_forward: element types differ");
+    TView bv = make_view(bottom), tv = make_view(top);
+    NC_REQUIRE(bv.n == tv.n && tv.C == bottom->c, "pool2d_forward: batch/channel mismatch");
+    PoolGeom g;
+    g.C = bottom->c;
+    g.inw = bottom->w;
+    g.inh = bottom->h;
+    g.n = bv.n;
+    g.global = d->global_pooling;
+    if (g.global)
+    {
+        g.outw = 1;
+        g.outh = 1;
+    }
+    else
+    {
+        NC_REQUIRE(top->dims == 3, "pool2d_forward: a 3-D top blob is required");
+        g.outw = top->w;
+        g.outh = top->h;
+    }
+    g.kw = d->kernel_w;
+    g.kh = d->kernel_h;
+    g.sw = d->stride_w;
+    g.sh = d->stride_h;
+    g.pad_left = d->pad_left;
+    g.pad_top = d->pad_top;
+    g.pad_right = d->pad_right;
+    g.pad_bottom = d->pad_bottom;
+    g.type = d->pooling_type;
+    g.include_pad = d->avgpool_count_include_pad;
+    g.adaptive = d->adaptive_pooling;
+    g.in_cpitch = bottom->cpitch;
+    g.out_cpitch = top->cpitch;
+    g.in_nstep = bottom->nstep;
+    g.out_nstep = top->nstep;
+    NC_REQUIRE(g.type == 0 || g.type == 1, "pool2d_forward: pooling_type must be 0 (max) or 1 (avg)");
+    switch (bottom->elemtype)
+    {
+    case NCNN_CUDA_F32: return run_pool<float>(bottom, top, g, stream);
+    case NCNN_CUDA_BF16: return run_pool<__nv_bfloat16>(bottom, top, g, stream);
+    case NCNN_CUDA_F16: return run_pool<__half>(bottom, top, g, stream);
+    }
+    return -1;
+}
