@@ -190,9 +190,11 @@ typedef struct ncnn_cuda_pool2d_desc
     int global_pooling;
     int avgpool_count_include_pad;
     int adaptive_pooling; /* output size taken from `top` */
-    /* count_include_pad only counts the explicit pads, not the pad_mode-0 tail (pooling.cpp:262-266):
-     * padded extent that counts = w + pad_left + pad_right_counted */
-    int pad_right, pad_bottom;
+    /* avg without count_include_pad divides by the number of window taps inside [area_x0, area_x1) x [area_y0, area_y1)
+     * (input coordinates; taps there but outside the image add 0).  For pad_mode 0/1 that is the image itself
+     * (0, w, 0, h); for the SAME modes the reference counts its SAME padding because it tests the explicit
+     * pad members only (pooling.cpp:283-300), so the host passes (pad_left_member - pad_left_applied, ...). */
+    int area_x0, area_x1, area_y0, area_y1;
 } ncnn_cuda_pool2d_desc;
 
 NCNN_CUDA_API int ncnn_cuda_pool2d_forward(const ncnn_cuda_pool2d_desc* desc, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);

@@ -12,7 +12,8 @@ namespace {
 struct PoolGeom
 {
     int C, inw, inh, outw, outh, n;
-    int kw, kh, sw, sh, pad_left, pad_top, pad_right, pad_bottom;
+    int kw, kh, sw, sh, pad_left, pad_top;
+    int ax0, ax1, ay0, ay1;
     int type, global, include_pad, adaptive;
     int in_cpitch, out_cpitch;
     long long in_nstep, out_nstep;
@@ -59,10 +60,16 @@ __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* 
         int area = 0;
         for (int iy = y0; iy < y1; iy++)
         {
-            if (iy < 0 || iy >= g.inh) continue;
+            if (iy < g.ay0 || iy >= g.ay1) continue;
+            const bool yin = iy >= 0 && iy < g.inh;
             for (int ix = x0; ix < x1; ix++)
             {
-                if (ix < 0 || ix >= g.inw) continue;
+                if (ix < g.ax0 || ix >= g.ax1) continue;
+                if (!yin || ix < 0 || ix >= g.inw)
+                {
+                    area++; // a counted padding tap (SAME modes, avg only): contributes 0
+                    continue;
+                }
                 float xv[VEC];
                 load_vec_f32<T, VEC>(inb + ((long long)iy * g.inw + ix) * g.in_cpitch, xv);
                 if (g.type == 0)
@@ -163,8 +170,14 @@ extern "C" int ncnn_cuda_pool2d_forward(const ncnn_cuda_pool2d_desc* d, const nc
     g.sh = d->stride_h;
     g.pad_left = d->pad_left;
     g.pad_top = d->pad_top;
-    g.pad_right = d->pad_right;
-    g.pad_bottom = d->pad_bottom;
+    if (d->pooling_type == 1 && !d->global_pooling && !d->adaptive_pooling && !d->avgpool_count_include_pad)
+    {
+        g.ax0 = d->area_x0; g.ax1 = d->area_x1; g.ay0 = d->area_y0; g.ay1 = d->area_y1;
+    }
+    else
+    {
+        g.ax0 = 0; g.ax1 = bottom->w; g.ay0 = 0; g.ay1 = bottom->h;
+    }
     g.type = d->pooling_type;
     g.include_pad = d->avgpool_count_include_pad;
     g.adaptive = d->adaptive_pooling;

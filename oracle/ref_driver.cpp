@@ -11,10 +11,12 @@
 #include "c_api.h"
 #include "cpu.h"
 #include "layer.h"
+#include "modelbin.h"
 #include "net.h"
 #include "option.h"
 
 #include <stdlib.h>
+#include <vector>
 
 extern "C" {
 
@@ -41,6 +43,17 @@ ncnn_layer_t ref_layer_create_naive(const char* type)
 ncnn_layer_t ref_layer_create_cpu(const char* type)
 {
     return wrap_as(type, ncnn::create_layer_cpu(type));
+}
+
+// load_model from an array of Mats, the way tests/testutil.cpp:1331 feeds ModelBinFromMatArray.
+// (The reference's own ncnn_modelbin_create_from_mat_array keeps a pointer into a vector that dies when it
+// returns -- src/c_api.cpp:1115-1128 -- so the oracle goes to the C++ class directly.)
+int ref_layer_load_model_from_mats(ncnn_layer_t layer, const ncnn_mat_t* weights, int n)
+{
+    std::vector<ncnn::Mat> mats(n > 0 ? n : 1);
+    for (int i = 0; i < n; i++) mats[i] = *(const ncnn::Mat*)weights[i];
+    ncnn::ModelBinFromMatArray mb(&mats[0]);
+    return ((ncnn::Layer*)layer->pthis)->load_model(mb);
 }
 
 int ref_layer_get_support_batch(const ncnn_layer_t layer)

@@ -1,0 +1,318 @@
+"""Kernel-level parity: every compute entry point of include/ncnn_cuda.h against the reference's own naive layer
+(oracle/_ref, create_layer_naive -- the ground truth tests/testutil.cpp:1301 of the reference uses) on seeded inputs.
+
+Shape grids follow the reference's tests/test_convolution.cpp:98-163, test_convolutiondepthwise.cpp:69-79,
+test_pooling.cpp, test_innerproduct.cpp (reduced), with a batch axis added (the backend is natively batched; the
+reference loops per sample, src/net.cpp:654-705).
+
+Tolerances (BASELINE.json north_star), metric = max|a-b| / max|ref| per tensor:
+    fp32 CUDA-core path            <= 1e-5
+    bf16 / fp16 tensor-core path   <= 2e-3   (inputs and weights pre-rounded to the storage type on both sides)
+A 16-bit top blob additionally carries its own storage rounding (unit roundoff 2^-8 for bf16, 2^-11 for fp16, relative
+to each element); `nerr(..., elemtype)` discounts exactly that per-element amount before normalising, so the 2e-3 bound
+is on the arithmetic (fp32-accumulated tensor-core sums), not on the storage format.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cabi
+import geom
+from cabi import BF16, F16, F32
+
+pytestmark = pytest.mark.gpu
+
+TOL = {F32: 1e-5, BF16: 2e-3, F16: 2e-3}
+ROUNDOFF = {F32: 0.0, BF16: 2.0 ** -8, F16: 2.0 ** -11}
+
+
+def nerr(a, b, elemtype=F32):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    den = max(np.abs(b).max(), 1e-30)
+    d = np.abs(a - b) - ROUNDOFF[elemtype] * np.abs(b)
+    return max(d.max(), 0.0) / den
+
+
+def quant(a, elemtype):
+    """round to the storage type so that the oracle sees exactly the values the device blob holds"""
+    import torch
+    if elemtype == F32:
+        return np.asarray(a, np.float32)
+    return torch.from_numpy(np.asarray(a, np.float32)).to(cabi.torch_dtype(elemtype)).float().numpy()
+
+
+def rand(rng, shape, lo=-1.0, hi=1.0):
+    return rng.uniform(lo, hi, shape).astype(np.float32)
+
+
+def sync():
+    import torch
+    torch.cuda.synchronize()
+
+
+ACT_PARAMS = {0: [], 1: [], 2: [0.1], 3: [-0.5, 0.8], 4: [], 5: [], 6: [0.2, 0.5]}
+
+
+def act_of(t):
+    p = ACT_PARAMS[t] + [0.0, 0.0]
+    return cabi.act(t, p[0], p[1])
+
+
+# ------------------------------------------------------------------------------------------ Convolution
+def run_conv(ref, rng, elemtype, n, w, h, inch, outch, k, d, s, pad, bias, act_type, pad_value=0.0, kh=None, residual=False, expect_algo=None):
+    L = cabi.lib()
+    kw = k
+    kh = kh or k
+    x = quant(rand(rng, (n, inch, h, w)), elemtype)
+    wt = quant(rand(rng, (outch, inch, kh, kw)) * np.float32(np.sqrt(3.0 / (inch * kw * kh))), elemtype)
+    b = rand(rng, (outch,)) if bias else None
+    params = {0: outch, 1: kw, 11: kh, 2: d, 3: s, 4: pad, 5: int(bias), 6: wt.size, 9: act_type, 18: float(pad_value)}
+    if ACT_PARAMS[act_type]:
+        params[10] = np.asarray(ACT_PARAMS[act_type], np.float32)
+    if residual:
+        params[9] = 0
+    want = ref.layer_forward("Convolution", params, [wt] + ([b] if bias else []), [x], batched=True)[0]
+
+    pads = geom.conv_pads(w, h, kw, kh, d, d, s, s, pad, pad, pad, pad)
+    outw, outh = geom.conv_out(w, h, kw, kh, d, d, s, s, pads)
+    assert want.shape == (n, outch, outh, outw)
+    res_np = None
+    if residual:
+        res_np = quant(rand(rng, want.shape), elemtype)
+        want = want + res_np
+        if act_type == 1:
+            want = np.maximum(want, 0)
+
+    desc = cabi.ConvDesc(inch, outch, kw, kh, d, d, s, s, pads[0], pads[1], pads[2], pads[3], pad_value, int(bias), act_of(act_type), elemtype)
+    handle = C.c_void_p()
+    wa, wp = cabi.fptr(wt)
+    if bias:
+        ba, bp = cabi.fptr(b)
+    else:
+        bp = None
+    cabi.check(L.ncnn_cuda_conv2d_create(C.byref(handle), C.byref(desc), wp, bp, None), "conv2d_create")
+    bottom = cabi.Blob.from_numpy(x, elemtype)
+    top = cabi.Blob((outch, outh, outw), n, elemtype, fill=float("nan"))
+    bd, td = bottom.desc(), top.desc()
+    rd = None
+    if residual:
+        resb = cabi.Blob.from_numpy(res_np, elemtype)
+        rd = resb.desc()
+    if expect_algo is not None:
+        assert L.ncnn_cuda_conv2d_algo(handle, C.byref(bd)) == expect_algo
+    cabi.check(L.ncnn_cuda_conv2d_forward(handle, C.byref(bd), C.byref(td), pads[0], pads[2], C.byref(rd) if rd else None, None, None, C.c_size_t(0), None),
+               "conv2d_forward")
+    sync()
+    got = top.numpy()
+    L.ncnn_cuda_conv2d_destroy(handle)
+    e = nerr(got, want, elemtype)
+    assert np.isfinite(got).all(), "non-finite output"
+    assert e <= TOL[elemtype], "conv n%d %dx%dx%d->%d k%dx%d d%d s%d p%d act%d: err %.3g" % (n, w, h, inch, outch, kw, kh, d, s, pad, act_type, e)
+    return e
+
+
+CONV_GRID = [
+    # k, d, s, pad   (tests/test_convolution.cpp:100-117 of the reference)
+    (1, 1, 1, 0), (1, 1, 2, 0), (2, 1, 1, 1), (2, 1, 2, -233), (3, 1, 1, 1), (3, 1, 2, 1), (3, 2, 1, -234), (4, 1, 1, 2),
+    (4, 1, 2, -233), (4, 2, 1, -234), (5, 1, 1, -233), (5, 1, 2, 2), (5, 2, 2, 2), (7, 1, 1, 3), (7, 1, 2, 3), (7, 2, 1, -233),
+]
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_convolution_grid(ref, elemtype):
+    rng = np.random.default_rng(7767517)
+    chans = [(1, 1), (4, 13), (13, 4), (12, 12), (8, 12), (16, 24), (15, 15), (16, 16), (3, 64), (40, 72)]
+    i = 0
+    for (k, d, s, pad) in CONV_GRID:
+        for (ci, co) in chans[i % 3::3]:
+            run_conv(ref, rng, elemtype, n=1 + i % 3, w=9 + i % 5, h=7 + i % 4, inch=ci, outch=co, k=k, d=d, s=s, pad=pad, bias=i % 2 == 0, act_type=i % 7)
+            i += 1
+
+
+@pytest.mark.parametrize("elemtype", [BF16, F16])
+def test_convolution_tensor_core_shapes(ref, elemtype):
+    """shapes of the named models' layers (reduced spatial size / batch), all on the tcgen05 path"""
+    rng = np.random.default_rng(1)
+    cases = [
+        # w, h, cin, cout, k, s, pad, n
+        (56, 56, 64, 256, 1, 1, 0, 2),     # resnet50 1x1 (TILED)
+        (28, 28, 256, 64, 1, 1, 0, 3),     # M tail: 3*784 = 2352 = 18.4 tiles
+        (30, 30, 64, 64, 3, 1, 1, 2),      # 3x3 s1 p1 (IM2COL)
+        (56, 56, 256, 512, 1, 2, 0, 2),    # strided 1x1 projection (IM2COL)
+        (64, 64, 3, 64, 7, 2, 3, 2),       # stem
+        (33, 31, 3, 32, 3, 2, 1, 3),       # mobilenet / yolo stem, odd sizes
+        (14, 14, 512, 512, 3, 1, 1, 2),    # vgg-like, K = 4608
+        (13, 13, 512, 1000, 1, 1, 1, 2),   # squeezenet conv10: 1x1 with pad 1
+        (20, 20, 320, 96, 1, 1, 0, 2),     # non-multiple-of-64 channels
+        (17, 19, 24, 144, 3, 2, -233, 2),
+    ]
+    for (w, h, ci, co, k, s, pad, n) in cases:
+        run_conv(ref, rng, elemtype, n, w, h, ci, co, k, 1, s, pad, True, 1, expect_algo=2)
+
+
+def test_convolution_pad_value_and_kernel_wh(ref):
+    rng = np.random.default_rng(2)
+    run_conv(ref, rng, F32, 2, 11, 9, 5, 7, 3, 1, 1, 1, True, 0, pad_value=0.7)
+    run_conv(ref, rng, BF16, 2, 11, 9, 16, 16, 3, 1, 1, 1, True, 0, pad_value=0.5)  # non-zero pad value: falls back to the SIMT kernel
+    run_conv(ref, rng, F32, 2, 11, 9, 5, 7, 3, 1, 2, 1, True, 1, kh=5)
+    run_conv(ref, rng, BF16, 2, 12, 10, 32, 48, 5, 1, 1, 2, True, 1, kh=3)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16])
+def test_convolution_fused_residual(ref, elemtype):
+    rng = np.random.default_rng(3)
+    run_conv(ref, rng, elemtype, 2, 14, 14, 64, 256, 1, 1, 1, 0, True, 1, residual=True)
+    run_conv(ref, rng, elemtype, 3, 9, 9, 24, 40, 3, 1, 1, 1, True, 0, residual=True)
+
+
+# ------------------------------------------------------------------------------------------ ConvolutionDepthWise
+def run_dw(ref, rng, elemtype, n, w, h, ch, outch, group, k, d, s, pad, bias, act_type):
+    L = cabi.lib()
+    x = quant(rand(rng, (n, ch, h, w)), elemtype)
+    wt = rand(rng, (outch, ch // group, k, k)) * np.float32(0.5)
+    b = rand(rng, (outch,)) if bias else None
+    params = {0: outch, 1: k, 2: d, 3: s, 4: pad, 5: int(bias), 6: wt.size, 7: group, 9: act_type}
+    if ACT_PARAMS[act_type]:
+        params[10] = np.asarray(ACT_PARAMS[act_type], np.float32)
+    want = ref.layer_forward("ConvolutionDepthWise", params, [wt] + ([b] if bias else []), [x], batched=True)[0]
+    pads = geom.conv_pads(w, h, k, k, d, d, s, s, pad, pad, pad, pad)
+    outw, outh = geom.conv_out(w, h, k, k, d, d, s, s, pads)
+    desc = cabi.DwConvDesc(ch, outch, group, k, k, d, d, s, s, 0.0, int(bias), act_of(act_type), elemtype)
+    handle = C.c_void_p()
+    wa, wp = cabi.fptr(wt)
+    if bias:
+        ba, bp = cabi.fptr(b)
+    else:
+        bp = None
+    cabi.check(L.ncnn_cuda_dwconv2d_create(C.byref(handle), C.byref(desc), wp, bp, None), "dwconv2d_create")
+    bottom = cabi.Blob.from_numpy(x, elemtype, pad_fill=0.0)
+    top = cabi.Blob((outch, outh, outw), n, elemtype, fill=float("nan"))
+    bd, td = bottom.desc(), top.desc()
+    cabi.check(L.ncnn_cuda_dwconv2d_forward(handle, C.byref(bd), C.byref(td), pads[0], pads[2], None), "dwconv2d_forward")
+    sync()
+    got = top.numpy()
+    L.ncnn_cuda_dwconv2d_destroy(handle)
+    tol = 1e-5 if elemtype == F32 else 1e-4  # 16-bit: fp32 weights and accumulation, only the output store rounds
+    e = nerr(got, want, elemtype)
+    assert e <= tol, "dw n%d %dx%dx%d g%d k%d d%d s%d p%d: err %.3g" % (n, w, h, ch, group, k, d, s, pad, e)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_convolutiondepthwise_grid(ref, elemtype):
+    rng = np.random.default_rng(11)
+    i = 0
+    for (k, d, s, pad) in [(1, 1, 1, 0), (2, 1, 2, -233), (3, 1, 1, 1), (3, 1, 2, 1), (3, 2, 1, -234), (5, 1, 2, 2), (7, 2, 1, -233)]:
+        for (ch, outch, group) in [(1, 1, 1), (2, 2, 2), (3, 3, 3), (7, 7, 7), (8, 8, 8), (12, 12, 12), (15, 15, 15), (16, 16, 16), (32, 32, 32), (96, 96, 96),
+                                   (4, 2, 2), (6, 6, 2), (12, 24, 4)]:
+            if i % 2 == 0 or group != ch:
+                run_dw(ref, rng, elemtype, 1 + i % 3, 11 + i % 6, 9 + i % 3, ch, outch, group, k, d, s, pad, i % 2 == 0, i % 7)
+            i += 1
+
+
+def test_convolutiondepthwise_mobilenet_shapes(ref):
+    rng = np.random.default_rng(12)
+    for (w, c, s) in [(56, 32, 1), (56, 96, 2), (28, 144, 1), (14, 384, 1), (14, 576, 2), (7, 960, 1)]:
+        run_dw(ref, rng, F32, 2, w, w, c, c, c, 3, 1, s, 1, True, 1)
+
+
+# ------------------------------------------------------------------------------------------ Pooling
+def run_pool(ref, rng, elemtype, n, w, h, c, ptype, k, s, pad, pad_mode, global_pool=0, include_pad=0, adaptive=0, out_wh=(0, 0)):
+    L = cabi.lib()
+    x = quant(rand(rng, (n, c, h, w)), elemtype)
+    params = {0: ptype, 1: k, 2: s, 3: pad, 4: global_pool, 5: pad_mode, 6: include_pad, 7: adaptive, 8: out_wh[0], 18: out_wh[1]}
+    want = ref.layer_forward("Pooling", params, [], [x], batched=True)[0]
+    if global_pool:
+        g = dict(outw=1, outh=1, pad_left=0, pad_top=0, area=(0, w, 0, h))
+        top = cabi.Blob((c,), n, elemtype, fill=float("nan"))
+    elif adaptive:
+        g = dict(outw=out_wh[0], outh=out_wh[1], pad_left=0, pad_top=0, area=(0, w, 0, h))
+        top = cabi.Blob((c, g["outh"], g["outw"]), n, elemtype, fill=float("nan"))
+    else:
+        g = geom.pool_geometry(w, h, k, k, s, s, pad, pad, pad, pad, pad_mode)
+        top = cabi.Blob((c, g["outh"], g["outw"]), n, elemtype, fill=float("nan"))
+    desc = cabi.PoolDesc(ptype, k, k, s, s, g["pad_left"], g["pad_top"], global_pool, include_pad, adaptive, *g["area"])
+    bottom = cabi.Blob.from_numpy(x, elemtype, pad_fill=0.0)
+    bd, td = bottom.desc(), top.desc()
+    cabi.check(L.ncnn_cuda_pool2d_forward(C.byref(desc), C.byref(bd), C.byref(td), None), "pool2d_forward")
+    sync()
+    got = top.numpy()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    # degenerate windows that lie entirely in padding: the reference yields 0/0 = NaN (avg) or -FLT_MAX (max, which
+    # a 16-bit blob stores as -inf); both sides must agree on where they are, and they are left out of the error
+    deg = ~np.isfinite(want) | (np.abs(want) >= 3e38)
+    assert (deg == (~np.isfinite(got) | (np.abs(got) >= 3e38))).all()
+    got = np.where(deg, 0, got)
+    want = np.where(deg, 0, want)
+    tol = 1e-6 if (elemtype == F32) else 1e-5
+    if ptype == 0 and elemtype != F32:
+        tol = 0.0  # max of stored values is exact
+    e = nerr(got, want, elemtype if ptype == 1 else F32)
+    assert e <= tol, "pool n%d %dx%dx%d type%d k%d s%d p%d mode%d g%d inc%d ad%d: err %.3g" % (n, w, h, c, ptype, k, s, pad, pad_mode, global_pool, include_pad, adaptive, e)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16])
+def test_pooling_grid(ref, elemtype):
+    rng = np.random.default_rng(21)
+    i = 0
+    for ptype in (0, 1):
+        for (k, s, pad) in [(2, 1, 0), (2, 2, 1), (3, 1, 0), (3, 2, 1), (4, 2, 1), (5, 1, 2), (5, 2, 2), (7, 3, 1)]:
+            for pad_mode in (0, 1, 2, 3):
+                c = [1, 3, 4, 8, 12, 16, 31, 64][i % 8]
+                run_pool(ref, rng, elemtype, 1 + i % 3, 13 + i % 5, 11 + i % 4, c, ptype, k, s, pad if pad_mode < 2 else 0, pad_mode, include_pad=(i // 3) % 2)
+                i += 1
+    for ptype in (0, 1):
+        run_pool(ref, rng, elemtype, 2, 7, 7, 2048, ptype, 0, 1, 0, 0, global_pool=1)
+        run_pool(ref, rng, elemtype, 3, 13, 9, 10, ptype, 0, 1, 0, 0, global_pool=1)
+        run_pool(ref, rng, elemtype, 2, 13, 9, 12, ptype, 0, 1, 0, 0, adaptive=1, out_wh=(4, 3))
+    # the named models' windows: resnet 3x3 s2 pad_mode 0 (tail pad), avg 7x7 s1, vgg 2x2 s2, sppf 5x5 s1 p2 valid
+    run_pool(ref, rng, elemtype, 2, 112, 112, 64, 0, 3, 2, 0, 0)
+    run_pool(ref, rng, elemtype, 2, 7, 7, 256, 1, 7, 1, 0, 0)
+    run_pool(ref, rng, elemtype, 2, 28, 28, 32, 0, 2, 2, 0, 0)
+    run_pool(ref, rng, elemtype, 2, 20, 20, 256, 0, 5, 1, 2, 1)
+
+
+# ------------------------------------------------------------------------------------------ InnerProduct
+def run_fc(ref, rng, elemtype, n, in_shape, num_output, bias, act_type):
+    L = cabi.lib()
+    x = quant(rand(rng, (n,) + tuple(in_shape)), elemtype)
+    num_input = int(np.prod(in_shape)) if len(in_shape) != 2 else in_shape[1]
+    wt = quant(rand(rng, (num_output, num_input)) * np.float32(np.sqrt(3.0 / num_input)), elemtype)
+    b = rand(rng, (num_output,)) if bias else None
+    params = {0: num_output, 1: int(bias), 2: wt.size, 9: act_type}
+    if ACT_PARAMS[act_type]:
+        params[10] = np.asarray(ACT_PARAMS[act_type], np.float32)
+    want = ref.layer_forward("InnerProduct", params, [wt] + ([b] if bias else []), [x], batched=True)[0]
+    if len(in_shape) == 3:
+        desc = cabi.LinearDesc(num_input, num_output, int(bias), act_of(act_type), elemtype, in_shape[2], in_shape[1], in_shape[0])
+    else:
+        desc = cabi.LinearDesc(num_input, num_output, int(bias), act_of(act_type), elemtype, 0, 0, 0)
+    handle = C.c_void_p()
+    wa, wp = cabi.fptr(wt)
+    if bias:
+        ba, bp = cabi.fptr(b)
+    else:
+        bp = None
+    cabi.check(L.ncnn_cuda_linear_create(C.byref(handle), C.byref(desc), wp, bp, None), "linear_create")
+    bottom = cabi.Blob.from_numpy(x, elemtype)
+    top_shape = (num_output,) if len(in_shape) != 2 else (in_shape[0], num_output)
+    top = cabi.Blob(top_shape, n, elemtype, fill=float("nan"))
+    bd, td = bottom.desc(), top.desc()
+    cabi.check(L.ncnn_cuda_linear_forward(handle, C.byref(bd), C.byref(td), None), "linear_forward")
+    sync()
+    got = top.numpy()
+    L.ncnn_cuda_linear_destroy(handle)
+    e = nerr(got, want, elemtype)
+    assert e <= TOL[elemtype], "fc n%d %s->%d: err %.3g" % (n, in_shape, num_output, e)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_innerproduct(ref, elemtype):
+    rng = np.random.default_rng(31)
+    run_fc(ref, rng, elemtype, 3, (2048,), 1000, True, 0)
+    run_fc(ref, rng, elemtype, 2, (64, 7, 7), 96, True, 1)      # 3-D bottom: reference flattens c-major (innerproduct.cpp:141-162)
+    run_fc(ref, rng, elemtype, 2, (5, 24), 13, True, 4)         # 2-D bottom: row-wise gemm (innerproduct.cpp:102-134)
+    run_fc(ref, rng, elemtype, 1, (15,), 7, False, 2)
+    run_fc(ref, rng, elemtype, 130, (1280,), 1000, True, 0)
