@@ -78,6 +78,8 @@ NCNN_CUDA_API int ncnn_cuda_malloc(void** ptr, size_t size);
 NCNN_CUDA_API int ncnn_cuda_free(void* ptr);
 NCNN_CUDA_API int ncnn_cuda_malloc_host(void** ptr, size_t size); /* pinned */
 NCNN_CUDA_API int ncnn_cuda_free_host(void* ptr);
+/* 1 when `ptr` is page-locked host memory (cudaMallocHost / cudaHostRegister): async copies need no staging */
+NCNN_CUDA_API int ncnn_cuda_host_is_pinned(const void* ptr);
 NCNN_CUDA_API int ncnn_cuda_memcpy_h2d_async(void* dst, const void* src, size_t size, void* stream);
 NCNN_CUDA_API int ncnn_cuda_memcpy_d2h_async(void* dst, const void* src, size_t size, void* stream);
 NCNN_CUDA_API int ncnn_cuda_memcpy_d2d_async(void* dst, const void* src, size_t size, void* stream);
@@ -222,7 +224,7 @@ NCNN_CUDA_API int ncnn_cuda_linear_destroy(ncnn_cuda_linear_t fc);
 NCNN_CUDA_API int ncnn_cuda_linear_forward(ncnn_cuda_linear_t fc, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
 
 /* General matrix product for Gemm (src/layer/gemm.cpp:250-315) with runtime A and B:
- * C[i][j] = alpha * sum_k A(i,k) * B(k,j) + beta * Cin(broadcast), strided fp32-accumulate SIMT kernel.
+ * C[i][j] = alpha * (sum_k A(i,k) * B(k,j) + beta * Cin(broadcast))  (gemm.cpp:269-303), strided fp32-accumulate SIMT kernel.
  * A(i,k) = a[i*a_rs + k*a_cs] etc.; c_* strides may be 0 for broadcasting (gemm.cpp:274-293). */
 typedef struct ncnn_cuda_gemm_args
 {

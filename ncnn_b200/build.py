@@ -37,13 +37,13 @@ def _compile(src, obj, cmd):
 def build(jobs=None, force=False, verbose=True):
     os.makedirs(BUILD, exist_ok=True)
     cu = sorted(glob.glob(os.path.join(HERE, "csrc", "cuda", "*.cu")))
-    cpp = sorted(glob.glob(os.path.join(HERE, "csrc", "host", "*.cpp")))
+    cpp = sorted(glob.glob(os.path.join(HERE, "csrc", "host", "*.cpp")) + glob.glob(os.path.join(HERE, "csrc", "host", "layer", "*.cpp")))
     headers = glob.glob(os.path.join(HERE, "csrc", "**", "*.h"), recursive=True) + glob.glob(os.path.join(HERE, "csrc", "**", "*.cuh"), recursive=True) \
         + glob.glob(os.path.join(ROOT, "include", "*.h"))
     hdr_time = _newest(headers + [os.path.abspath(__file__)])
     tasks, objs = [], []
     for s in cu + cpp:
-        o = os.path.join(BUILD, os.path.basename(s) + ".o")
+        o = os.path.join(BUILD, os.path.relpath(s, os.path.join(HERE, "csrc")).replace(os.sep, "__") + ".o")
         objs.append(o)
         if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hdr_time):
             continue

@@ -49,8 +49,10 @@ __global__ void __launch_bounds__(256) gemm_strided_kernel(ncnn_cuda_gemm_args g
         int i = i0 + ty + 8 * r, j = j0 + tx;
         if (i < g.M && j < g.N)
         {
-            float v = g.alpha * acc[r];
+            // the reference's order (gemm.cpp:269-303): sum = beta * C; sum += A.B; sum *= alpha
+            float v = acc[r];
             if (c) v += g.beta * to_f32(c[(long long)i * g.c_rs + (long long)j * g.c_cs]);
+            v *= g.alpha;
             out[(long long)i * g.o_rs + (long long)j * g.o_cs] = from_f32<T>(v);
         }
     }

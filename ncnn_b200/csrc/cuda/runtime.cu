@@ -134,6 +134,17 @@ int ncnn_cuda_free_host(void* ptr)
     return 0;
 }
 
+int ncnn_cuda_host_is_pinned(const void* ptr)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return attr.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 int ncnn_cuda_memcpy_h2d_async(void* dst, const void* src, size_t size, void* stream)
 {
     NC_CHECK(cudaMemcpyAsync(dst, src, size, cudaMemcpyHostToDevice, as_stream(stream)));

@@ -1,0 +1,209 @@
+#include "command.h"
+
+#include <map>
+#include <mutex>
+
+namespace ncnn {
+
+CudaContext::CudaContext(int _device_index)
+    : device_index(_device_index), stream(0), blob_allocator(0), staging_allocator(0)
+{
+    ncnn_cuda_stream_create(&stream);
+    blob_allocator = new CudaBlobAllocator(_device_index);
+    staging_allocator = new CudaStagingAllocator;
+}
+
+CudaContext::~CudaContext()
+{
+    if (stream)
+    {
+        ncnn_cuda_stream_sync(stream);
+        ncnn_cuda_stream_destroy(stream);
+    }
+    delete blob_allocator;
+    delete staging_allocator;
+}
+
+namespace {
+struct ContextPool
+{
+    std::mutex lock;
+    std::map<int, std::vector<CudaContext*> > idle;
+    std::map<int, CudaWeightAllocator*> weights;
+    ~ContextPool()
+    {
+        // process teardown: the CUDA runtime may already be gone, leave device memory to the driver
+    }
+};
+static ContextPool& pool()
+{
+    static ContextPool* p = new ContextPool;
+    return *p;
+}
+} // namespace
+
+int get_cuda_device_count()
+{
+    return ncnn_cuda_device_count();
+}
+
+CudaContext* acquire_cuda_context(int device_index)
+{
+    if (device_index < 0) device_index = ncnn_cuda_get_device();
+    if (device_index < 0) return 0;
+    if (ncnn_cuda_set_device(device_index) != 0) return 0;
+    ContextPool& p = pool();
+    {
+        std::lock_guard<std::mutex> lk(p.lock);
+        std::vector<CudaContext*>& v = p.idle[device_index];
+        if (!v.empty())
+        {
+            CudaContext* c = v.back();
+            v.pop_back();
+            return c;
+        }
+    }
+    CudaContext* c = new CudaContext(device_index);
+    if (!c->stream)
+    {
+        delete c;
+        return 0;
+    }
+    return c;
+}
+
+void reclaim_cuda_context(CudaContext* ctx)
+{
+    if (!ctx) return;
+    ContextPool& p = pool();
+    std::lock_guard<std::mutex> lk(p.lock);
+    p.idle[ctx->device_index].push_back(ctx);
+}
+
+CudaWeightAllocator* get_cuda_weight_allocator(int device_index)
+{
+    if (device_index < 0) device_index = ncnn_cuda_get_device();
+    ContextPool& p = pool();
+    std::lock_guard<std::mutex> lk(p.lock);
+    CudaWeightAllocator*& a = p.weights[device_index];
+    if (!a) a = new CudaWeightAllocator(device_index);
+    return a;
+}
+
+CudaCompute::CudaCompute(CudaContext* ctx)
+    : h2d_bytes(0), d2h_bytes(0), ctx_(ctx)
+{
+}
+
+CudaCompute::~CudaCompute()
+{
+    if (!downloads_.empty() || !staging_in_flight_.empty() || !keep_alive_.empty()) submit_and_wait();
+}
+
+static size_t mat_bytes(const Mat& m)
+{
+    return (m.n <= 1 ? m.total() : (size_t)m.n * m.nstep) * m.elemsize;
+}
+
+int CudaCompute::record_upload(const Mat& src, CudaMat& dst, const Option& opt)
+{
+    if (src.empty()) return -100;
+    if (src.elemsize != 4u || src.elempack != 1)
+    {
+        NCNN_LOGE("record_upload: only fp32 elempack=1 host Mats are accepted (got elemsize %zu elempack %d)", src.elemsize, src.elempack);
+        return -1;
+    }
+    void* st = stream();
+    const size_t bytes = mat_bytes(src);
+    // raw planar bytes on the device, then one conversion kernel into the backend layout
+    CudaMat raw;
+    raw.create((int)((bytes + 3) / 4), NCNN_CUDA_F32, 1, workspace_allocator(opt));
+    if (raw.empty()) return -100;
+    const void* hsrc = src.data;
+    if (!ncnn_cuda_host_is_pinned(src.data))
+    {
+        Allocator* sa = ctx_->staging_allocator;
+        void* staging = sa->fastMalloc(bytes);
+        if (!staging) return -100;
+        memcpy(staging, src.data, bytes);
+        staging_in_flight_.push_back(staging);
+        hsrc = staging;
+    }
+    int ret = ncnn_cuda_memcpy_h2d_async(raw.data, hsrc, bytes, st);
+    if (ret != 0) return ret;
+    h2d_bytes += bytes;
+    dst.create_like(src, opt.cuda_elemtype(), blob_allocator(opt));
+    if (dst.empty()) return -100;
+    ncnn_cuda_hostmat hm = host_view(src, raw.data);
+    ncnn_cuda_tensor t = dst.view();
+    ret = ncnn_cuda_pack_from_planar(&hm, &t, st);
+    keep_alive_.push_back(raw); // returned to the pool at the next submit; reuse before that would still be stream-ordered
+    return ret;
+}
+
+int CudaCompute::record_download(const CudaMat& src, Mat& dst, const Option& opt)
+{
+    if (src.empty()) return -100;
+    void* st = stream();
+    dst.create_dims(src.dims, src.w, src.h, src.d, src.c, src.n, 4u, opt.blob_allocator);
+    if (dst.empty()) return -100;
+    const size_t bytes = mat_bytes(dst);
+    CudaMat raw;
+    raw.create((int)((bytes + 3) / 4), NCNN_CUDA_F32, 1, workspace_allocator(opt));
+    if (raw.empty()) return -100;
+    ncnn_cuda_hostmat hm = host_view(dst, raw.data);
+    ncnn_cuda_tensor t = src.view();
+    int ret = ncnn_cuda_unpack_to_planar(&t, &hm, st);
+    if (ret != 0) return ret;
+    keep_alive_.push_back(raw);
+    keep_alive_.push_back(src);
+    if (ncnn_cuda_host_is_pinned(dst.data))
+    {
+        ret = ncnn_cuda_memcpy_d2h_async(dst.data, raw.data, bytes, st);
+    }
+    else
+    {
+        Allocator* sa = ctx_->staging_allocator;
+        void* staging = sa->fastMalloc(bytes);
+        if (!staging) return -100;
+        ret = ncnn_cuda_memcpy_d2h_async(staging, raw.data, bytes, st);
+        PendingDownload pd;
+        pd.staging = staging;
+        pd.dst = dst.data;
+        pd.bytes = bytes;
+        downloads_.push_back(pd);
+    }
+    d2h_bytes += bytes;
+    return ret;
+}
+
+int CudaCompute::record_clone(const CudaMat& src, CudaMat& dst, const Option& opt)
+{
+    if (src.empty()) return -100;
+    dst.create_like(src, blob_allocator(opt));
+    if (dst.empty()) return -100;
+    return ncnn_cuda_memcpy_d2d_async(dst.data, src.data, src.total_elems() * src.elemsize(), stream());
+}
+
+int CudaCompute::submit_and_wait()
+{
+    int ret = ncnn_cuda_stream_sync(stream());
+    Allocator* sa = ctx_->staging_allocator;
+    for (size_t i = 0; i < downloads_.size(); i++)
+    {
+        if (ret == 0) memcpy(downloads_[i].dst, downloads_[i].staging, downloads_[i].bytes);
+        sa->fastFree(downloads_[i].staging);
+    }
+    downloads_.clear();
+    for (size_t i = 0; i < staging_in_flight_.size(); i++) sa->fastFree(staging_in_flight_[i]);
+    staging_in_flight_.clear();
+    keep_alive_.clear();
+    return ret;
+}
+
+int CudaCompute::reset()
+{
+    return submit_and_wait();
+}
+
+} // namespace ncnn

@@ -1,0 +1,534 @@
+// mat.cpp -- see mat.h
+#include "mat.h"
+
+namespace ncnn {
+
+Mat::Mat()
+    : data(0), refcount(0), elemsize(0), elempack(0), allocator(0), dims(0), w(0), h(0), d(0), c(0), cstep(0), n(1), nstep(0)
+{
+}
+
+Mat::Mat(int _w, size_t _elemsize, Allocator* _allocator)
+    : data(0), refcount(0), elemsize(0), elempack(0), allocator(0), dims(0), w(0), h(0), d(0), c(0), cstep(0), n(1), nstep(0)
+{
+    create(_w, _elemsize, _allocator);
+}
+
+Mat::Mat(int _w, int _h, size_t _elemsize, Allocator* _allocator)
+    : data(0), refcount(0), elemsize(0), elempack(0), allocator(0), dims(0), w(0), h(0), d(0), c(0), cstep(0), n(1), nstep(0)
+{
+    create(_w, _h, _elemsize, _allocator);
+}
+
+Mat::Mat(int _w, int _h, int _c, size_t _elemsize, Allocator* _allocator)
+    : data(0), refcount(0), elemsize(0), elempack(0), allocator(0), dims(0), w(0), h(0), d(0), c(0), cstep(0), n(1), nstep(0)
+{
+    create(_w, _h, _c, _elemsize, _allocator);
+}
+
+Mat::Mat(int _w, int _h, int _d, int _c, size_t _elemsize, Allocator* _allocator)
+    : data(0), refcount(0), elemsize(0), elempack(0), allocator(0), dims(0), w(0), h(0), d(0), c(0), cstep(0), n(1), nstep(0)
+{
+    create(_w, _h, _d, _c, _elemsize, _allocator);
+}
+
+Mat::Mat(const Mat& m)
+    : data(m.data), refcount(m.refcount), elemsize(m.elemsize), elempack(m.elempack), allocator(m.allocator), dims(m.dims), w(m.w), h(m.h), d(m.d), c(m.c),
+      cstep(m.cstep), n(m.n), nstep(m.nstep)
+{
+    addref();
+}
+
+Mat::Mat(int _w, void* _data, size_t _elemsize, Allocator* _allocator)
+    : data(_data), refcount(0), elemsize(_elemsize), elempack(1), allocator(_allocator), dims(1), w(_w), h(1), d(1), c(1), n(1)
+{
+    cstep = alignSize((size_t)w * elemsize, 16) / elemsize;
+    nstep = cstep;
+}
+
+Mat::Mat(int _w, int _h, void* _data, size_t _elemsize, Allocator* _allocator)
+    : data(_data), refcount(0), elemsize(_elemsize), elempack(1), allocator(_allocator), dims(2), w(_w), h(_h), d(1), c(1), n(1)
+{
+    cstep = alignSize((size_t)w * h * elemsize, 16) / elemsize;
+    nstep = cstep;
+}
+
+Mat::Mat(int _w, int _h, int _c, void* _data, size_t _elemsize, Allocator* _allocator)
+    : data(_data), refcount(0), elemsize(_elemsize), elempack(1), allocator(_allocator), dims(3), w(_w), h(_h), d(1), c(_c), n(1)
+{
+    cstep = alignSize((size_t)w * h * elemsize, 16) / elemsize;
+    nstep = cstep * c;
+}
+
+Mat::Mat(int _w, int _h, int _d, int _c, void* _data, size_t _elemsize, Allocator* _allocator)
+    : data(_data), refcount(0), elemsize(_elemsize), elempack(1), allocator(_allocator), dims(4), w(_w), h(_h), d(_d), c(_c), n(1)
+{
+    cstep = alignSize((size_t)w * h * d * elemsize, 16) / elemsize;
+    nstep = cstep * c;
+}
+
+Mat::~Mat()
+{
+    release();
+}
+
+Mat& Mat::operator=(const Mat& m)
+{
+    if (this == &m) return *this;
+    if (m.refcount) NCNN_XADD(m.refcount, 1);
+    release();
+    data = m.data;
+    refcount = m.refcount;
+    elemsize = m.elemsize;
+    elempack = m.elempack;
+    allocator = m.allocator;
+    dims = m.dims;
+    w = m.w;
+    h = m.h;
+    d = m.d;
+    c = m.c;
+    cstep = m.cstep;
+    n = m.n;
+    nstep = m.nstep;
+    return *this;
+}
+
+void Mat::addref()
+{
+    if (refcount) NCNN_XADD(refcount, 1);
+}
+
+void Mat::release()
+{
+    if (refcount && NCNN_XADD(refcount, -1) == 1)
+    {
+        if (allocator)
+            allocator->fastFree(data);
+        else
+            fastFree(data);
+    }
+    data = 0;
+    elemsize = 0;
+    elempack = 0;
+    dims = 0;
+    w = h = d = c = 0;
+    cstep = 0;
+    n = 1;
+    nstep = 0;
+    refcount = 0;
+}
+
+bool Mat::empty() const
+{
+    return data == 0 || total() == 0;
+}
+
+size_t Mat::total() const
+{
+    return cstep * c;
+}
+
+int Mat::elembits() const
+{
+    return elempack ? (int)(elemsize * 8) / elempack : 0;
+}
+
+Mat Mat::shape() const
+{
+    if (dims == 1) return Mat(w * elempack, (void*)0);
+    if (dims == 2) return Mat(w, h * elempack, (void*)0);
+    if (dims == 3) return Mat(w, h, c * elempack, (void*)0);
+    if (dims == 4) return Mat(w, h, d, c * elempack, (void*)0);
+    return Mat();
+}
+
+void Mat::create_dims(int _dims, int _w, int _h, int _d, int _c, int _n, size_t _elemsize, Allocator* _allocator)
+{
+    if (_dims < 2) _h = 1;
+    if (_dims < 4) _d = 1;
+    if (_dims < 3) _c = 1;
+    if (_n < 1) _n = 1;
+    if (dims == _dims && w == _w && h == _h && d == _d && c == _c && n == _n && elemsize == _elemsize && elempack == 1 && allocator == _allocator && data) return;
+    release();
+    elemsize = _elemsize;
+    elempack = 1;
+    allocator = _allocator;
+    dims = _dims;
+    w = _w;
+    h = _h;
+    d = _d;
+    c = _c;
+    n = _n;
+    cstep = alignSize((size_t)w * h * d * elemsize, 16) / elemsize;
+    if (n > 1)
+        nstep = alignSize(cstep * c * elemsize, 4096) / elemsize; // src/mat.cpp:780
+    else
+        nstep = cstep * c;
+    size_t totalsize = alignSize(nstep * n * elemsize, 4);
+    if (totalsize > 0)
+    {
+        if (allocator)
+            data = allocator->fastMalloc(totalsize + (int)sizeof(*refcount));
+        else
+            data = fastMalloc(totalsize + (int)sizeof(*refcount));
+    }
+    if (data)
+    {
+        refcount = (int*)(((unsigned char*)data) + totalsize);
+        *refcount = 1;
+    }
+}
+
+void Mat::create(int _w, size_t _elemsize, Allocator* _allocator)
+{
+    create_dims(1, _w, 1, 1, 1, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, size_t _elemsize, Allocator* _allocator)
+{
+    create_dims(2, _w, _h, 1, 1, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, int _c, size_t _elemsize, Allocator* _allocator)
+{
+    create_dims(3, _w, _h, 1, _c, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, int _d, int _c, size_t _elemsize, Allocator* _allocator)
+{
+    create_dims(4, _w, _h, _d, _c, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, size_t _elemsize, int, Allocator* _allocator)
+{
+    create_dims(1, _w, 1, 1, 1, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, size_t _elemsize, int, Allocator* _allocator)
+{
+    create_dims(2, _w, _h, 1, 1, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, int _c, size_t _elemsize, int, Allocator* _allocator)
+{
+    create_dims(3, _w, _h, 1, _c, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, int _d, int _c, size_t _elemsize, int, Allocator* _allocator)
+{
+    create_dims(4, _w, _h, _d, _c, 1, _elemsize, _allocator);
+}
+void Mat::create(int _w, size_t _elemsize, int, int _n, Allocator* _allocator)
+{
+    create_dims(1, _w, 1, 1, 1, _n, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, size_t _elemsize, int, int _n, Allocator* _allocator)
+{
+    create_dims(2, _w, _h, 1, 1, _n, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, int _c, size_t _elemsize, int, int _n, Allocator* _allocator)
+{
+    create_dims(3, _w, _h, 1, _c, _n, _elemsize, _allocator);
+}
+void Mat::create(int _w, int _h, int _d, int _c, size_t _elemsize, int, int _n, Allocator* _allocator)
+{
+    create_dims(4, _w, _h, _d, _c, _n, _elemsize, _allocator);
+}
+
+void Mat::create_like(const Mat& m, Allocator* _allocator)
+{
+    create_dims(m.dims, m.w, m.h, m.d, m.c, m.n, m.elemsize, _allocator);
+}
+
+void Mat::create_like(const Mat& m, int _n, Allocator* _allocator)
+{
+    create_dims(m.dims, m.w, m.h, m.d, m.c, _n, m.elemsize, _allocator);
+}
+
+void Mat::fill(float v)
+{
+    size_t count = (size_t)(n < 1 ? 1 : n) * nstep;
+    if (n <= 1) count = total();
+    float* p = (float*)data;
+    for (size_t i = 0; i < count; i++) p[i] = v;
+}
+
+void Mat::fill(int v)
+{
+    size_t count = n <= 1 ? total() : (size_t)n * nstep;
+    int* p = (int*)data;
+    for (size_t i = 0; i < count; i++) p[i] = v;
+}
+
+Mat Mat::clone(Allocator* _allocator) const
+{
+    if (empty()) return Mat();
+    Mat m;
+    m.create_dims(dims, w, h, d, c, n, elemsize, _allocator);
+    if (m.empty()) return m;
+    size_t bytes = (n <= 1 ? total() : (size_t)n * nstep) * elemsize;
+    memcpy(m.data, data, bytes);
+    return m;
+}
+
+void Mat::clone_from(const Mat& mat, Allocator* _allocator)
+{
+    *this = mat.clone(_allocator);
+}
+
+// reshape keeps the logical element order (c, d, h, w); planes are re-aligned when cstep padding differs
+static void copy_logical(const Mat& src, Mat& dst)
+{
+    // walk both in logical order
+    size_t total = (size_t)src.w * src.h * src.d * src.c;
+    size_t splane = (size_t)src.w * src.h * src.d, dplane = (size_t)dst.w * dst.h * dst.d;
+    const unsigned char* s = (const unsigned char*)src.data;
+    unsigned char* t = (unsigned char*)dst.data;
+    size_t es = src.elemsize;
+    size_t i = 0;
+    while (i < total)
+    {
+        size_t sq = i / splane, so = i % splane;
+        size_t dq = i / dplane, dof = i % dplane;
+        size_t run = splane - so;
+        if (dplane - dof < run) run = dplane - dof;
+        memcpy(t + (dq * dst.cstep + dof) * es, s + (sq * src.cstep + so) * es, run * es);
+        i += run;
+    }
+}
+
+Mat Mat::reshape(int _w, Allocator* _allocator) const
+{
+    if ((size_t)w * h * d * c != (size_t)_w) return Mat();
+    Mat m;
+    m.create(_w, elemsize, _allocator);
+    if (!m.empty()) copy_logical(*this, m);
+    return m;
+}
+
+Mat Mat::reshape(int _w, int _h, Allocator* _allocator) const
+{
+    if ((size_t)w * h * d * c != (size_t)_w * _h) return Mat();
+    Mat m;
+    m.create(_w, _h, elemsize, _allocator);
+    if (!m.empty()) copy_logical(*this, m);
+    return m;
+}
+
+Mat Mat::reshape(int _w, int _h, int _c, Allocator* _allocator) const
+{
+    if ((size_t)w * h * d * c != (size_t)_w * _h * _c) return Mat();
+    Mat m;
+    m.create(_w, _h, _c, elemsize, _allocator);
+    if (!m.empty()) copy_logical(*this, m);
+    return m;
+}
+
+Mat Mat::reshape(int _w, int _h, int _d, int _c, Allocator* _allocator) const
+{
+    if ((size_t)w * h * d * c != (size_t)_w * _h * _d * _c) return Mat();
+    Mat m;
+    m.create(_w, _h, _d, _c, elemsize, _allocator);
+    if (!m.empty()) copy_logical(*this, m);
+    return m;
+}
+
+Mat Mat::channel(int _c)
+{
+    Mat m(w, h, d, (unsigned char*)data + cstep * _c * elemsize, elemsize, allocator);
+    m.dims = dims - 1;
+    if (dims == 4) m.cstep = (size_t)w * h;
+    return m;
+}
+
+const Mat Mat::channel(int _c) const
+{
+    Mat m(w, h, d, (unsigned char*)data + cstep * _c * elemsize, elemsize, allocator);
+    m.dims = dims - 1;
+    if (dims == 4) m.cstep = (size_t)w * h;
+    return m;
+}
+
+Mat Mat::batch(int b)
+{
+    return ((const Mat*)this)->batch(b);
+}
+
+const Mat Mat::batch(int b) const
+{
+    Mat m;
+    m.data = (unsigned char*)data + nstep * b * elemsize;
+    m.refcount = 0;
+    m.elemsize = elemsize;
+    m.elempack = elempack;
+    m.allocator = allocator;
+    m.dims = dims;
+    m.w = w;
+    m.h = h;
+    m.d = d;
+    m.c = c;
+    m.cstep = cstep;
+    m.n = 1;
+    m.nstep = cstep * c;
+    return m;
+}
+
+Mat Mat::batch_range(int b, int batches)
+{
+    return ((const Mat*)this)->batch_range(b, batches);
+}
+
+const Mat Mat::batch_range(int b, int batches) const
+{
+    Mat m = batch(b);
+    m.n = batches;
+    m.nstep = nstep;
+    return m;
+}
+
+float* Mat::row(int y)
+{
+    return (float*)((unsigned char*)data + (size_t)w * y * elemsize);
+}
+
+const float* Mat::row(int y) const
+{
+    return (const float*)((unsigned char*)data + (size_t)w * y * elemsize);
+}
+
+// ------------------------------------------------------------------ CudaMat
+CudaMat::CudaMat()
+    : data(0), refcount(0), allocator(0), elemtype(NCNN_CUDA_F32), dims(0), w(0), h(0), d(0), c(0), n(1), cpitch(0), nstep(0)
+{
+}
+
+CudaMat::CudaMat(const CudaMat& m)
+    : data(m.data), refcount(m.refcount), allocator(m.allocator), elemtype(m.elemtype), dims(m.dims), w(m.w), h(m.h), d(m.d), c(m.c), n(m.n), cpitch(m.cpitch),
+      nstep(m.nstep)
+{
+    addref();
+}
+
+CudaMat::~CudaMat()
+{
+    release();
+}
+
+CudaMat& CudaMat::operator=(const CudaMat& m)
+{
+    if (this == &m) return *this;
+    if (m.refcount) NCNN_XADD(m.refcount, 1);
+    release();
+    data = m.data;
+    refcount = m.refcount;
+    allocator = m.allocator;
+    elemtype = m.elemtype;
+    dims = m.dims;
+    w = m.w;
+    h = m.h;
+    d = m.d;
+    c = m.c;
+    n = m.n;
+    cpitch = m.cpitch;
+    nstep = m.nstep;
+    return *this;
+}
+
+void CudaMat::addref()
+{
+    if (refcount) NCNN_XADD(refcount, 1);
+}
+
+void CudaMat::release()
+{
+    if (refcount && NCNN_XADD(refcount, -1) == 1)
+    {
+        if (allocator && data) allocator->fastFree(data);
+        delete refcount;
+    }
+    data = 0;
+    refcount = 0;
+    dims = 0;
+    w = h = d = c = 0;
+    n = 1;
+    cpitch = 0;
+    nstep = 0;
+}
+
+int CudaMat::pixels() const
+{
+    if (dims == 1) return 1;
+    if (dims == 2) return h;
+    if (dims == 3) return h * w;
+    return d * h * w;
+}
+
+int CudaMat::channels() const
+{
+    return dims <= 2 ? w : c;
+}
+
+void CudaMat::create_dims(int _dims, int _w, int _h, int _d, int _c, int _elemtype, int _n, CudaAllocator* _allocator)
+{
+    if (_dims < 2) _h = 1;
+    if (_dims < 4) _d = 1;
+    if (_dims < 3) _c = 1;
+    if (_n < 1) _n = 1;
+    release();
+    allocator = _allocator;
+    elemtype = _elemtype;
+    dims = _dims;
+    w = _w;
+    h = _h;
+    d = _d;
+    c = _c;
+    n = _n;
+    const int vec = _elemtype == NCNN_CUDA_F32 ? 4 : 8; // 16-byte channel vectors; TMA needs 16-byte pixel strides
+    const int C = channels();
+    cpitch = (C + vec - 1) / vec * vec;
+    nstep = (size_t)pixels() * cpitch;
+    size_t bytes = nstep * n * elemsize();
+    if (bytes == 0 || !allocator) return;
+    data = allocator->fastMalloc(bytes);
+    if (data)
+    {
+        refcount = new int;
+        *refcount = 1;
+    }
+}
+
+void CudaMat::create(int _w, int _elemtype, int _n, CudaAllocator* _allocator)
+{
+    create_dims(1, _w, 1, 1, 1, _elemtype, _n, _allocator);
+}
+void CudaMat::create(int _w, int _h, int _elemtype, int _n, CudaAllocator* _allocator)
+{
+    create_dims(2, _w, _h, 1, 1, _elemtype, _n, _allocator);
+}
+void CudaMat::create(int _w, int _h, int _c, int _elemtype, int _n, CudaAllocator* _allocator)
+{
+    create_dims(3, _w, _h, 1, _c, _elemtype, _n, _allocator);
+}
+void CudaMat::create(int _w, int _h, int _d, int _c, int _elemtype, int _n, CudaAllocator* _allocator)
+{
+    create_dims(4, _w, _h, _d, _c, _elemtype, _n, _allocator);
+}
+void CudaMat::create_like(const CudaMat& m, CudaAllocator* _allocator)
+{
+    create_dims(m.dims, m.w, m.h, m.d, m.c, m.elemtype, m.n, _allocator);
+}
+void CudaMat::create_like(const Mat& m, int _elemtype, CudaAllocator* _allocator)
+{
+    create_dims(m.dims, m.w, m.h, m.d, m.c, _elemtype, m.n, _allocator);
+}
+
+ncnn_cuda_tensor CudaMat::view() const
+{
+    ncnn_cuda_tensor t;
+    t.data = data;
+    t.dims = dims;
+    t.w = w;
+    t.h = h;
+    t.d = d;
+    t.c = c;
+    t.n = n < 1 ? 1 : n;
+    t.elemtype = elemtype;
+    t.cpitch = cpitch;
+    t.nstep = (long long)nstep;
+    return t;
+}
+
+} // namespace ncnn

@@ -1,0 +1,1159 @@
+// net.cpp -- see net.h.  Control flow mirrors the reference's src/net.cpp (line references per function).
+#include "net.h"
+
+#include <ctype.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "layer/cuda_layers.h"
+#include "modelbin.h"
+#include "paramdict.h"
+
+namespace ncnn {
+
+struct custom_layer_registry_entry
+{
+    std::string name;
+    layer_creator_func creator;
+    layer_destroyer_func destroyer;
+    void* userdata;
+};
+
+class NetPrivate
+{
+public:
+    NetPrivate()
+        : device_index(-1), fused_layers(0)
+    {
+    }
+    std::vector<Blob> blobs;
+    std::vector<Layer*> layers;
+    std::vector<int> layer_custom_index; // -1 built-in
+    std::vector<int> input_blob_indexes;
+    std::vector<int> output_blob_indexes;
+    std::vector<const char*> input_blob_names;
+    std::vector<const char*> output_blob_names;
+    std::vector<custom_layer_registry_entry> custom_layer_registry;
+    int device_index;
+    int fused_layers;
+
+    void update_input_output_indexes();
+    void update_input_output_names();
+    int fuse_graph(const Option& opt);
+    int forward_layer(int layer_index, std::vector<Mat>& blob_mats, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const;
+    int do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const;
+};
+
+Net::Net()
+    : d(new NetPrivate)
+{
+}
+
+Net::~Net()
+{
+    clear();
+    delete d;
+}
+
+void Net::set_cuda_device(int device_index)
+{
+    d->device_index = device_index;
+    opt.cuda_device_index = device_index;
+}
+
+int Net::cuda_device() const
+{
+    return d->device_index;
+}
+
+int Net::register_custom_layer(const char* type, layer_creator_func creator, layer_destroyer_func destroyer, void* userdata)
+{
+    for (size_t i = 0; i < d->custom_layer_registry.size(); i++)
+    {
+        if (d->custom_layer_registry[i].name == type)
+        {
+            NCNN_LOGE("overwrite existing custom layer type %s", type);
+            d->custom_layer_registry[i].creator = creator;
+            d->custom_layer_registry[i].destroyer = destroyer;
+            d->custom_layer_registry[i].userdata = userdata;
+            return 0;
+        }
+    }
+    if (layer_to_index(type) != -1) NCNN_LOGE("overwrite built-in layer type %s", type);
+    custom_layer_registry_entry e;
+    e.name = type;
+    e.creator = creator;
+    e.destroyer = destroyer;
+    e.userdata = userdata;
+    d->custom_layer_registry.push_back(e);
+    return 0;
+}
+
+Layer* Net::create_layer_by_type(const char* type, int* custom_index)
+{
+    *custom_index = -1;
+    // registered types win over built-ins (src/net.cpp:1399-1413)
+    for (size_t i = 0; i < d->custom_layer_registry.size(); i++)
+    {
+        if (d->custom_layer_registry[i].name == type && d->custom_layer_registry[i].creator)
+        {
+            Layer* layer = d->custom_layer_registry[i].creator(d->custom_layer_registry[i].userdata);
+            if (layer) *custom_index = (int)i;
+            return layer;
+        }
+    }
+    return create_layer_cuda(type);
+}
+
+void NetPrivate::update_input_output_indexes()
+{
+    // inputs = tops of Input layers, outputs = blobs with a producer and no consumer (src/net.cpp:1145-1169)
+    input_blob_indexes.clear();
+    output_blob_indexes.clear();
+    for (size_t i = 0; i < layers.size(); i++)
+    {
+        if (layers[i] && layers[i]->type == "Input" && !layers[i]->tops.empty()) input_blob_indexes.push_back(layers[i]->tops[0]);
+    }
+    for (size_t i = 0; i < blobs.size(); i++)
+    {
+        if (blobs[i].producer != -1 && blobs[i].consumer == -1) output_blob_indexes.push_back((int)i);
+    }
+}
+
+void NetPrivate::update_input_output_names()
+{
+    input_blob_names.clear();
+    output_blob_names.clear();
+    for (size_t i = 0; i < input_blob_indexes.size(); i++) input_blob_names.push_back(blobs[input_blob_indexes[i]].name.c_str());
+    for (size_t i = 0; i < output_blob_indexes.size(); i++) output_blob_names.push_back(blobs[output_blob_indexes[i]].name.c_str());
+}
+
+static bool next_line(const std::string& text, size_t& pos, std::string& line)
+{
+    while (pos < text.size())
+    {
+        size_t e = text.find('\n', pos);
+        if (e == std::string::npos) e = text.size();
+        line.assign(text, pos, e - pos);
+        pos = e + 1;
+        // skip blank lines
+        size_t k = 0;
+        while (k < line.size() && isspace((unsigned char)line[k])) k++;
+        if (k < line.size()) return true;
+    }
+    return false;
+}
+
+static const char* next_token(const char* p, const char* end, std::string& tok)
+{
+    while (p < end && isspace((unsigned char)*p)) p++;
+    const char* b = p;
+    while (p < end && !isspace((unsigned char)*p)) p++;
+    tok.assign(b, p);
+    return p;
+}
+
+static Mat shape_hint_mat(int dims, int w, int h, int dd, int c)
+{
+    Mat m;
+    m.dims = dims;
+    m.w = w;
+    m.h = h;
+    m.d = dd;
+    m.c = c;
+    m.elemsize = 4u;
+    m.elempack = 1;
+    return m;
+}
+
+// src/net.cpp:1305-1665
+int Net::load_param_text(const std::string& text)
+{
+    clear();
+    size_t pos = 0;
+    std::string line;
+    if (!next_line(text, pos, line)) return -1;
+    int magic = atoi(line.c_str());
+    if (magic != 7767517)
+    {
+        NCNN_LOGE("param is too old, please regenerate");
+        return -1;
+    }
+    if (!next_line(text, pos, line)) return -1;
+    int layer_count = 0, blob_count = 0;
+    if (sscanf(line.c_str(), "%d %d", &layer_count, &blob_count) != 2 || layer_count <= 0 || blob_count <= 0)
+    {
+        NCNN_LOGE("invalid layer_count or blob_count");
+        return -1;
+    }
+    if (!opt.use_cuda_compute)
+    {
+        NCNN_LOGE("opt.use_cuda_compute is off: this runtime has no CPU compute path");
+        return -1;
+    }
+    d->layers.resize((size_t)layer_count, 0);
+    d->layer_custom_index.resize((size_t)layer_count, -1);
+    d->blobs.resize((size_t)blob_count);
+
+    ParamDict pd;
+    int blob_index = 0;
+    for (int i = 0; i < layer_count; i++)
+    {
+        if (!next_line(text, pos, line))
+        {
+            NCNN_LOGE("parse layer %d failed: unexpected end of param", i);
+            clear();
+            return -1;
+        }
+        const char* p = line.c_str();
+        const char* end = p + line.size();
+        std::string layer_type, layer_name, tok;
+        p = next_token(p, end, layer_type);
+        p = next_token(p, end, layer_name);
+        p = next_token(p, end, tok);
+        int bottom_count = atoi(tok.c_str());
+        p = next_token(p, end, tok);
+        int top_count = atoi(tok.c_str());
+        if (layer_type.empty() || layer_name.empty() || bottom_count < 0 || top_count < 0)
+        {
+            NCNN_LOGE("parse layer %d failed", i);
+            clear();
+            return -1;
+        }
+        int custom_index = -1;
+        Layer* layer = create_layer_by_type(layer_type.c_str(), &custom_index);
+        if (!layer)
+        {
+            NCNN_LOGE("layer %s not exists or registered (the CUDA backend has no CPU fallback)", layer_type.c_str());
+            clear();
+            return -1;
+        }
+        layer->type = layer_type;
+        layer->name = layer_name;
+        layer->bottoms.resize(bottom_count);
+        for (int j = 0; j < bottom_count; j++)
+        {
+            p = next_token(p, end, tok);
+            int bottom_blob_index = find_blob_index_by_name(tok.c_str());
+            if (bottom_blob_index == -1)
+            {
+                if (blob_index >= blob_count)
+                {
+                    NCNN_LOGE("blob count exceeds the header's %d", blob_count);
+                    delete layer;
+                    clear();
+                    return -1;
+                }
+                bottom_blob_index = blob_index;
+                d->blobs[blob_index].name = tok;
+                blob_index++;
+            }
+            d->blobs[bottom_blob_index].consumer = i;
+            layer->bottoms[j] = bottom_blob_index;
+        }
+        layer->tops.resize(top_count);
+        for (int j = 0; j < top_count; j++)
+        {
+            p = next_token(p, end, tok);
+            if (blob_index >= blob_count || tok.empty())
+            {
+                NCNN_LOGE("blob count exceeds the header's %d", blob_count);
+                delete layer;
+                clear();
+                return -1;
+            }
+            d->blobs[blob_index].name = tok;
+            d->blobs[blob_index].producer = i;
+            layer->tops[j] = blob_index;
+            blob_index++;
+        }
+        if (pd.load_param_text(p, end) != 0)
+        {
+            NCNN_LOGE("ParamDict load_param %d %s failed", i, layer_name.c_str());
+            delete layer;
+            clear();
+            return -1;
+        }
+        // top shape hints, id 30 (src/net.cpp:1487-1519)
+        Mat shape_hints = pd.get(30, Mat());
+        if (!shape_hints.empty() && top_count > 0)
+        {
+            const int psh_step = shape_hints.w / top_count;
+            const int* psh = (const int*)shape_hints.data;
+            for (int j = 0; j < top_count; j++)
+            {
+                Blob& blob = d->blobs[layer->tops[j]];
+                int dims = psh[0];
+                if (dims == 1) blob.shape = shape_hint_mat(1, psh[1], 1, 1, 1);
+                if (dims == 2) blob.shape = shape_hint_mat(2, psh[1], psh[2], 1, 1);
+                if (dims == 3) blob.shape = psh_step == 5 ? shape_hint_mat(3, psh[1], psh[2], 1, psh[4]) : shape_hint_mat(3, psh[1], psh[2], 1, psh[3]);
+                if (dims == 4) blob.shape = shape_hint_mat(4, psh[1], psh[2], psh[3], psh[4]);
+                psh += psh_step;
+            }
+        }
+        layer->featmask = pd.get(31, 0);
+        layer->top_count_hint = top_count;
+        int lr = layer->load_param(pd);
+        if (lr != 0)
+        {
+            NCNN_LOGE("layer load_param %d %s failed", i, layer_name.c_str());
+            delete layer;
+            clear();
+            return -1;
+        }
+        layer->bottom_shapes.resize(bottom_count);
+        for (int j = 0; j < bottom_count; j++) layer->bottom_shapes[j] = d->blobs[layer->bottoms[j]].shape;
+        layer->top_shapes.resize(top_count);
+        for (int j = 0; j < top_count; j++) layer->top_shapes[j] = d->blobs[layer->tops[j]].shape;
+        d->layers[i] = layer;
+        d->layer_custom_index[i] = custom_index;
+    }
+    d->update_input_output_indexes();
+    d->update_input_output_names();
+    return 0;
+}
+
+int Net::load_param(const DataReader& dr)
+{
+    // pull the whole text through the reader, then parse it line by line
+    std::string text;
+    char buf[4096];
+    for (;;)
+    {
+        size_t n = dr.read(buf, sizeof(buf));
+        if (n == 0) break;
+        text.append(buf, n);
+        if (n < sizeof(buf)) break;
+    }
+    return load_param_text(text);
+}
+
+int Net::load_param(FILE* fp)
+{
+    std::string text;
+    char buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, n);
+    return load_param_text(text);
+}
+
+int Net::load_param(const char* protopath)
+{
+    FILE* fp = fopen(protopath, "rb");
+    if (!fp)
+    {
+        NCNN_LOGE("fopen %s failed", protopath);
+        return -1;
+    }
+    int ret = load_param(fp);
+    fclose(fp);
+    return ret;
+}
+
+int Net::load_param_mem(const char* mem)
+{
+    return load_param_text(std::string(mem));
+}
+
+// .param.bin (src/net.cpp:1667-2019): int32 magic, layer_count, blob_count; per layer typeindex, bottom_count,
+// top_count, blob indexes, then ParamDict binary records
+int Net::load_param_bin(const DataReader& dr)
+{
+    clear();
+#define READ_VALUE(buf)                                   \
+    if (dr.read(&buf, sizeof(buf)) != sizeof(buf))        \
+    {                                                     \
+        NCNN_LOGE("read " #buf " failed");                \
+        clear();                                          \
+        return -1;                                        \
+    }
+    int magic = 0;
+    READ_VALUE(magic)
+    if (magic != 7767517)
+    {
+        NCNN_LOGE("param is too old, please regenerate");
+        return -1;
+    }
+    int layer_count = 0, blob_count = 0;
+    READ_VALUE(layer_count)
+    READ_VALUE(blob_count)
+    if (layer_count <= 0 || blob_count <= 0)
+    {
+        NCNN_LOGE("invalid layer_count or blob_count");
+        return -1;
+    }
+    d->layers.resize((size_t)layer_count, 0);
+    d->layer_custom_index.resize((size_t)layer_count, -1);
+    d->blobs.resize((size_t)blob_count);
+    ParamDict pd;
+    for (int i = 0; i < layer_count; i++)
+    {
+        int typeindex = 0, bottom_count = 0, top_count = 0;
+        READ_VALUE(typeindex)
+        READ_VALUE(bottom_count)
+        READ_VALUE(top_count)
+        const char* type = layer_index_to_type(typeindex);
+        int custom_index = -1;
+        Layer* layer = type ? create_layer_by_type(type, &custom_index) : 0;
+        if (!layer)
+        {
+            NCNN_LOGE("layer %d not exists or registered (the CUDA backend has no CPU fallback)", typeindex);
+            clear();
+            return -1;
+        }
+        layer->type = type;
+        layer->typeindex = typeindex;
+        char namebuf[32];
+        sprintf(namebuf, "layer%d", i);
+        layer->name = namebuf;
+        layer->bottoms.resize(bottom_count);
+        for (int j = 0; j < bottom_count; j++)
+        {
+            int bottom_blob_index = 0;
+            READ_VALUE(bottom_blob_index)
+            if (bottom_blob_index < 0 || bottom_blob_index >= blob_count)
+            {
+                delete layer;
+                clear();
+                return -1;
+            }
+            d->blobs[bottom_blob_index].consumer = i;
+            layer->bottoms[j] = bottom_blob_index;
+        }
+        layer->tops.resize(top_count);
+        for (int j = 0; j < top_count; j++)
+        {
+            int top_blob_index = 0;
+            READ_VALUE(top_blob_index)
+            if (top_blob_index < 0 || top_blob_index >= blob_count)
+            {
+                delete layer;
+                clear();
+                return -1;
+            }
+            d->blobs[top_blob_index].producer = i;
+            char bn[32];
+            sprintf(bn, "blob%d", top_blob_index);
+            d->blobs[top_blob_index].name = bn;
+            layer->tops[j] = top_blob_index;
+        }
+        if (pd.load_param_bin(dr) != 0)
+        {
+            NCNN_LOGE("ParamDict load_param_bin %d failed", i);
+            delete layer;
+            clear();
+            return -1;
+        }
+        layer->featmask = pd.get(31, 0);
+        layer->top_count_hint = top_count;
+        if (layer->load_param(pd) != 0)
+        {
+            NCNN_LOGE("layer load_param %d failed", i);
+            delete layer;
+            clear();
+            return -1;
+        }
+        layer->bottom_shapes.resize(bottom_count);
+        layer->top_shapes.resize(top_count);
+        d->layers[i] = layer;
+        d->layer_custom_index[i] = custom_index;
+    }
+#undef READ_VALUE
+    d->update_input_output_indexes();
+    d->update_input_output_names();
+    return 0;
+}
+
+int Net::load_param_bin(const char* protopath)
+{
+    FILE* fp = fopen(protopath, "rb");
+    if (!fp)
+    {
+        NCNN_LOGE("fopen %s failed", protopath);
+        return -1;
+    }
+    DataReaderFromStdio dr(fp);
+    int ret = load_param_bin(dr);
+    fclose(fp);
+    return ret;
+}
+
+// src/net.cpp:2021-2155
+int Net::load_model(const DataReader& dr)
+{
+    if (d->layers.empty())
+    {
+        NCNN_LOGE("network graph not ready");
+        return -1;
+    }
+    if (d->device_index < 0) d->device_index = opt.cuda_device_index >= 0 ? opt.cuda_device_index : ncnn_cuda_get_device();
+    if (d->device_index < 0 || ncnn_cuda_set_device(d->device_index) != 0)
+    {
+        NCNN_LOGE("no CUDA device available: %s", ncnn_cuda_last_error());
+        return -1;
+    }
+    opt.cuda_device_index = d->device_index;
+
+    int ret = 0;
+    ModelBinFromDataReader mb(dr);
+    for (size_t i = 0; i < d->layers.size(); i++)
+    {
+        Layer* layer = d->layers[i];
+        if (!layer)
+        {
+            NCNN_LOGE("load_model error at layer %d, parameter file has inconsistent content.", (int)i);
+            ret = -1;
+            break;
+        }
+        int lret = layer->load_model(mb);
+        if (lret != 0)
+        {
+            NCNN_LOGE("layer load_model %d %s failed", (int)i, layer->name.c_str());
+            ret = -1;
+            break;
+        }
+    }
+    if (ret != 0) return ret;
+
+    if (opt.use_cuda_graph_fusion) d->fuse_graph(opt);
+
+    for (size_t i = 0; i < d->layers.size(); i++)
+    {
+        Layer* layer = d->layers[i];
+        int cret = layer->create_pipeline(opt);
+        if (cret != 0)
+        {
+            NCNN_LOGE("layer create_pipeline %d %s failed", (int)i, layer->name.c_str());
+            ret = -1;
+            break;
+        }
+    }
+    ncnn_cuda_device_sync();
+    return ret;
+}
+
+int Net::load_model(FILE* fp)
+{
+    DataReaderFromStdio dr(fp);
+    return load_model(dr);
+}
+
+int Net::load_model(const char* modelpath)
+{
+    FILE* fp = fopen(modelpath, "rb");
+    if (!fp)
+    {
+        NCNN_LOGE("fopen %s failed", modelpath);
+        return -1;
+    }
+    int ret = load_model(fp);
+    fclose(fp);
+    return ret;
+}
+
+size_t Net::load_model(const unsigned char* _mem)
+{
+    const unsigned char* mem = _mem;
+    DataReaderFromMemory dr(mem);
+    load_model(dr);
+    return mem - _mem;
+}
+
+void Net::clear()
+{
+    Option o = opt;
+    for (size_t i = 0; i < d->layers.size(); i++)
+    {
+        Layer* layer = d->layers[i];
+        if (!layer) continue;
+        layer->destroy_pipeline(o);
+        int ci = i < d->layer_custom_index.size() ? d->layer_custom_index[i] : -1;
+        if (ci >= 0 && d->custom_layer_registry[ci].destroyer)
+            d->custom_layer_registry[ci].destroyer(layer, d->custom_layer_registry[ci].userdata);
+        else
+            delete layer;
+    }
+    d->layers.clear();
+    d->layer_custom_index.clear();
+    d->blobs.clear();
+    d->input_blob_indexes.clear();
+    d->output_blob_indexes.clear();
+    d->input_blob_names.clear();
+    d->output_blob_names.clear();
+    d->fused_layers = 0;
+}
+
+Extractor Net::create_extractor() const
+{
+    return Extractor(this, d->blobs.size());
+}
+
+const std::vector<int>& Net::input_indexes() const
+{
+    return d->input_blob_indexes;
+}
+const std::vector<int>& Net::output_indexes() const
+{
+    return d->output_blob_indexes;
+}
+const std::vector<const char*>& Net::input_names() const
+{
+    return d->input_blob_names;
+}
+const std::vector<const char*>& Net::output_names() const
+{
+    return d->output_blob_names;
+}
+const std::vector<Blob>& Net::blobs() const
+{
+    return d->blobs;
+}
+const std::vector<Layer*>& Net::layers() const
+{
+    return d->layers;
+}
+int Net::fused_layer_count() const
+{
+    return d->fused_layers;
+}
+
+int Net::find_blob_index_by_name(const char* name) const
+{
+    for (size_t i = 0; i < d->blobs.size(); i++)
+        if (d->blobs[i].name == name) return (int)i;
+    return -1;
+}
+
+int Net::find_layer_index_by_name(const char* name) const
+{
+    for (size_t i = 0; i < d->layers.size(); i++)
+        if (d->layers[i] && d->layers[i]->name == name) return (int)i;
+    return -1;
+}
+
+// ------------------------------------------------------------------ load-time graph fusion
+// What tools/ncnnoptimize.cpp does offline (fuse_convolution_activation :1268-1419 and friends), done here on the
+// loaded graph so that un-optimised .param files get the same kernels.  A folded layer is taken out of the walk by
+// re-wiring: the producer takes over the folded layer's top blob and the folded layer is replaced by a disconnected Noop.
+//   Convolution / ConvolutionDepthWise / InnerProduct (activation_type 0) -> ReLU | Clip | Sigmoid | Mish | HardSwish   => epilogue activation
+//   Convolution (activation_type 0) -> Swish                                       => epilogue activation (code 7)
+//   Convolution (activation_type 0) -> Eltwise(SUM, 2 inputs, no coeffs) [-> ReLU]  => residual add (+ReLU) in the epilogue
+//   Eltwise -> ReLU                                                               => fused_relu
+namespace {
+class Noop : public Layer
+{
+public:
+    Noop()
+    {
+        one_blob_only = false;
+        support_inplace = false;
+    }
+    virtual int forward(const std::vector<CudaMat>&, std::vector<CudaMat>&, CudaCompute&, const Option&) const
+    {
+        return 0;
+    }
+};
+} // namespace
+
+int NetPrivate::fuse_graph(const Option&)
+{
+    const int L = (int)layers.size();
+    // a blob must not be a net output to be folded away
+    auto sole_consumer = [&](int blob) -> int { return blobs[blob].consumer; };
+    auto retire = [&](int li) {
+        // turn layer li into a disconnected no-op
+        Layer* old = layers[li];
+        Noop* n = new Noop;
+        n->type = "Noop";
+        n->name = old->name;
+        int ci = layer_custom_index[li];
+        if (ci >= 0 && custom_layer_registry[ci].destroyer)
+            custom_layer_registry[ci].destroyer(old, custom_layer_registry[ci].userdata);
+        else
+            delete old;
+        layers[li] = n;
+        layer_custom_index[li] = -1;
+        fused_layers++;
+    };
+    for (int i = 0; i < L; i++)
+    {
+        if (layer_custom_index[i] >= 0) continue;
+        Layer* l = layers[i];
+        // ---- X -> activation
+        int* act_slot = 0;
+        Mat* act_params = 0;
+        bool is_conv = false;
+        if (l->type == "Convolution")
+        {
+            Convolution* c = (Convolution*)l;
+            act_slot = &c->activation_type;
+            act_params = &c->activation_params;
+            is_conv = true;
+        }
+        else if (l->type == "ConvolutionDepthWise")
+        {
+            ConvolutionDepthWise* c = (ConvolutionDepthWise*)l;
+            act_slot = &c->activation_type;
+            act_params = &c->activation_params;
+        }
+        else if (l->type == "InnerProduct")
+        {
+            InnerProduct* c = (InnerProduct*)l;
+            act_slot = &c->activation_type;
+            act_params = &c->activation_params;
+        }
+        if (act_slot && *act_slot == 0 && l->tops.size() == 1)
+        {
+            int top = l->tops[0];
+            int j = sole_consumer(top);
+            if (j > i && layer_custom_index[j] < 0 && layers[j]->bottoms.size() == 1 && layers[j]->tops.size() == 1)
+            {
+                Layer* a = layers[j];
+                int code = -1;
+                float p0 = 0.f, p1 = 0.f;
+                int np = 0;
+                if (a->type == "ReLU")
+                {
+                    float slope = ((ReLU*)a)->p0;
+                    if (slope == 0.f)
+                        code = 1;
+                    else
+                    {
+                        code = 2;
+                        p0 = slope;
+                        np = 1;
+                    }
+                }
+                else if (a->type == "Clip")
+                {
+                    code = 3;
+                    p0 = ((Clip*)a)->p0;
+                    p1 = ((Clip*)a)->p1;
+                    np = 2;
+                }
+                else if (a->type == "Sigmoid")
+                    code = 4;
+                else if (a->type == "Mish")
+                    code = 5;
+                else if (a->type == "HardSwish")
+                {
+                    code = 6;
+                    p0 = ((HardSwish*)a)->p0;
+                    p1 = ((HardSwish*)a)->p1;
+                    np = 2;
+                }
+                else if (a->type == "Swish" && is_conv)
+                    code = 7; // backend-private epilogue code (common.cuh apply_activation)
+                if (code > 0)
+                {
+                    *act_slot = code;
+                    if (np > 0)
+                    {
+                        Mat ap(np);
+                        ((float*)ap.data)[0] = p0;
+                        if (np > 1) ((float*)ap.data)[1] = p1;
+                        *act_params = ap;
+                    }
+                    // the producer now writes the activation's top blob
+                    int newtop = a->tops[0];
+                    l->tops[0] = newtop;
+                    blobs[newtop].producer = i;
+                    blobs[top].producer = -1;
+                    blobs[top].consumer = -1;
+                    a->bottoms.clear();
+                    a->tops.clear();
+                    retire(j);
+                    continue;
+                }
+            }
+        }
+    }
+
+    // ---- Convolution -> Eltwise(SUM) [-> ReLU]
+    for (int j = 0; j < L; j++)
+    {
+        if (layer_custom_index[j] >= 0) continue;
+        Layer* e = layers[j];
+        if (e->type != "Eltwise") continue;
+        Eltwise* el = (Eltwise*)e;
+        // Eltwise -> ReLU first
+        int etop = e->tops.size() == 1 ? e->tops[0] : -1;
+        int relu_layer = -1;
+        if (etop >= 0)
+        {
+            int k = blobs[etop].consumer;
+            if (k > j && layer_custom_index[k] < 0 && layers[k]->type == "ReLU" && ((ReLU*)layers[k])->p0 == 0.f && layers[k]->tops.size() == 1) relu_layer = k;
+        }
+        bool folded_into_conv = false;
+        if (el->op_type == 1 && el->coeffs.empty() && e->bottoms.size() == 2 && etop >= 0)
+        {
+            // pick the operand produced LAST by a plain Convolution whose only consumer is this Eltwise
+            int best = -1, best_slot = -1;
+            for (int s = 0; s < 2; s++)
+            {
+                int b = e->bottoms[s];
+                int p = blobs[b].producer;
+                if (p < 0 || p >= j || layer_custom_index[p] >= 0) continue;
+                if (layers[p]->type != "Convolution") continue;
+                Convolution* c = (Convolution*)layers[p];
+                if (c->activation_type != 0 || c->fused_residual || c->tops.size() != 1 || blobs[b].consumer != j) continue;
+                if (p > best)
+                {
+                    best = p;
+                    best_slot = s;
+                }
+            }
+            if (best >= 0)
+            {
+                int other_blob = e->bottoms[1 - best_slot];
+                int other_prod = blobs[other_blob].producer;
+                // the residual must exist before the conv runs: its producer has to come earlier in layer order
+                if (other_prod < best)
+                {
+                    Convolution* c = (Convolution*)layers[best];
+                    int conv_top = c->tops[0];
+                    c->fused_residual = true;
+                    c->one_blob_only = false;
+                    c->bottoms.push_back(other_blob);
+                    blobs[other_blob].consumer = best;
+                    int final_top = etop;
+                    c->fused_post_activation = -1;
+                    if (relu_layer >= 0)
+                    {
+                        c->fused_post_activation = 1;
+                        final_top = layers[relu_layer]->tops[0];
+                        layers[relu_layer]->bottoms.clear();
+                        layers[relu_layer]->tops.clear();
+                        blobs[etop].producer = -1;
+                        blobs[etop].consumer = -1;
+                        retire(relu_layer);
+                    }
+                    c->tops[0] = final_top;
+                    blobs[final_top].producer = best;
+                    blobs[conv_top].producer = -1;
+                    blobs[conv_top].consumer = -1;
+                    e->bottoms.clear();
+                    e->tops.clear();
+                    retire(j);
+                    folded_into_conv = true;
+                }
+            }
+        }
+        if (!folded_into_conv && relu_layer >= 0)
+        {
+            el->fused_relu = true;
+            int newtop = layers[relu_layer]->tops[0];
+            e->tops[0] = newtop;
+            blobs[newtop].producer = j;
+            blobs[etop].producer = -1;
+            blobs[etop].consumer = -1;
+            layers[relu_layer]->bottoms.clear();
+            layers[relu_layer]->tops.clear();
+            retire(relu_layer);
+        }
+    }
+    update_input_output_indexes();
+    update_input_output_names();
+    return 0;
+}
+
+// ------------------------------------------------------------------ executor
+// src/net.cpp:192-356 (Vulkan forward_layer): depth-first, lazy
+int NetPrivate::forward_layer(int layer_index, std::vector<Mat>& blob_mats, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const
+{
+    const Layer* layer = layers[layer_index];
+    for (size_t i = 0; i < layer->bottoms.size(); i++)
+    {
+        int bottom_blob_index = layer->bottoms[i];
+        if (!blob_mats_gpu[bottom_blob_index].empty()) continue;
+        if (!blob_mats[bottom_blob_index].empty())
+        {
+            // host -> device boundary: upload once (src/net.cpp:215-228)
+            int ret = cmd.record_upload(blob_mats[bottom_blob_index], blob_mats_gpu[bottom_blob_index], opt);
+            if (ret != 0) return ret;
+            if (opt.lightmode) blob_mats[bottom_blob_index].release();
+            continue;
+        }
+        int producer = blobs[bottom_blob_index].producer;
+        if (producer < 0)
+        {
+            NCNN_LOGE("blob %s has no producer and was not given as input", blobs[bottom_blob_index].name.c_str());
+            return -1;
+        }
+        int ret = forward_layer(producer, blob_mats, blob_mats_gpu, cmd, opt);
+        if (ret != 0) return ret;
+    }
+    int ret = do_forward_layer(layer, blob_mats_gpu, cmd, opt);
+    if (ret != 0) NCNN_LOGE("layer %s (%s) forward failed: %d %s", layer->name.c_str(), layer->type.c_str(), ret, ncnn_cuda_last_error());
+    return ret;
+}
+
+// src/net.cpp:886-1140 (Vulkan do_forward_layer): lightmode recycling, in-place clone rule; no per-sample batch loop
+int NetPrivate::do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const
+{
+    if (layer->one_blob_only)
+    {
+        int bottom_blob_index = layer->bottoms[0];
+        int top_blob_index = layer->tops[0];
+        CudaMat& bottom_blob_ref = blob_mats_gpu[bottom_blob_index];
+        CudaMat bottom_blob;
+        if (opt.lightmode && layer->support_inplace)
+        {
+            // deep copy for inplace forward if data is shared (src/net.cpp:635-644)
+            if (bottom_blob_ref.refcount && *bottom_blob_ref.refcount != 1)
+            {
+                int ret = cmd.record_clone(bottom_blob_ref, bottom_blob, opt);
+                if (ret != 0) return ret;
+            }
+        }
+        if (bottom_blob.dims == 0) bottom_blob = bottom_blob_ref;
+        int ret;
+        if (opt.lightmode && layer->support_inplace)
+        {
+            CudaMat& bottom_top_blob = bottom_blob;
+            ret = layer->forward_inplace(bottom_top_blob, cmd, opt);
+            if (ret != 0) return ret;
+            blob_mats_gpu[top_blob_index] = bottom_top_blob;
+        }
+        else
+        {
+            CudaMat top_blob;
+            ret = layer->forward(bottom_blob, top_blob, cmd, opt);
+            if (ret != 0) return ret;
+            blob_mats_gpu[top_blob_index] = top_blob;
+        }
+        if (opt.lightmode) blob_mats_gpu[bottom_blob_index].release();
+        return 0;
+    }
+
+    std::vector<CudaMat> bottom_blobs(layer->bottoms.size());
+    for (size_t i = 0; i < layer->bottoms.size(); i++)
+    {
+        int bottom_blob_index = layer->bottoms[i];
+        CudaMat& ref = blob_mats_gpu[bottom_blob_index];
+        if (opt.lightmode && layer->support_inplace && ref.refcount && *ref.refcount != 1)
+        {
+            int ret = cmd.record_clone(ref, bottom_blobs[i], opt);
+            if (ret != 0) return ret;
+        }
+        if (bottom_blobs[i].dims == 0) bottom_blobs[i] = ref;
+    }
+    int ret;
+    if (opt.lightmode && layer->support_inplace)
+    {
+        ret = layer->forward_inplace(bottom_blobs, cmd, opt);
+        if (ret != 0) return ret;
+        for (size_t i = 0; i < layer->tops.size(); i++) blob_mats_gpu[layer->tops[i]] = bottom_blobs[i];
+    }
+    else
+    {
+        std::vector<CudaMat> top_blobs(layer->tops.size());
+        ret = layer->forward(bottom_blobs, top_blobs, cmd, opt);
+        if (ret != 0) return ret;
+        for (size_t i = 0; i < layer->tops.size(); i++) blob_mats_gpu[layer->tops[i]] = top_blobs[i];
+    }
+    if (opt.lightmode)
+    {
+        for (size_t i = 0; i < layer->bottoms.size(); i++) blob_mats_gpu[layer->bottoms[i]].release();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ Extractor
+class ExtractorPrivate
+{
+public:
+    explicit ExtractorPrivate(const Net* _net)
+        : net(_net), h2d(0), d2h(0)
+    {
+    }
+    const Net* net;
+    std::vector<Mat> blob_mats;
+    std::vector<CudaMat> blob_mats_gpu;
+    Option opt;
+    size_t h2d, d2h;
+};
+
+Extractor::Extractor(const Net* _net, size_t blob_count)
+    : d(new ExtractorPrivate(_net))
+{
+    d->blob_mats.resize(blob_count);
+    d->blob_mats_gpu.resize(blob_count);
+    d->opt = _net->opt;
+}
+
+Extractor::~Extractor()
+{
+    clear();
+    delete d;
+}
+
+Extractor::Extractor(const Extractor& rhs)
+    : d(new ExtractorPrivate(rhs.d->net))
+{
+    d->blob_mats = rhs.d->blob_mats;
+    d->blob_mats_gpu = rhs.d->blob_mats_gpu;
+    d->opt = rhs.d->opt;
+}
+
+Extractor& Extractor::operator=(const Extractor& rhs)
+{
+    if (this == &rhs) return *this;
+    d->net = rhs.d->net;
+    d->blob_mats = rhs.d->blob_mats;
+    d->blob_mats_gpu = rhs.d->blob_mats_gpu;
+    d->opt = rhs.d->opt;
+    return *this;
+}
+
+void Extractor::clear()
+{
+    d->blob_mats.clear();
+    d->blob_mats_gpu.clear();
+}
+
+void Extractor::set_light_mode(bool enable)
+{
+    d->opt.lightmode = enable;
+}
+void Extractor::set_blob_allocator(Allocator* allocator)
+{
+    d->opt.blob_allocator = allocator;
+}
+void Extractor::set_workspace_allocator(Allocator* allocator)
+{
+    d->opt.workspace_allocator = allocator;
+}
+void Extractor::set_blob_cuda_allocator(CudaAllocator* allocator)
+{
+    d->opt.blob_cuda_allocator = allocator;
+}
+
+int Extractor::input(const char* blob_name, const Mat& in)
+{
+    int blob_index = d->net->find_blob_index_by_name(blob_name);
+    if (blob_index == -1)
+    {
+        NCNN_LOGE("Try");
+        const std::vector<const char*>& names = d->net->input_names();
+        for (size_t i = 0; i < names.size(); i++) NCNN_LOGE("    ex.input(\"%s\", in%d);", names[i], (int)i);
+        return -1;
+    }
+    return input(blob_index, in);
+}
+
+int Extractor::input(int blob_index, const Mat& in)
+{
+    if (blob_index < 0 || blob_index >= (int)d->blob_mats.size()) return -1;
+    d->blob_mats[blob_index] = in;
+    d->blob_mats_gpu[blob_index].release();
+    return 0;
+}
+
+int Extractor::input(const char* blob_name, const CudaMat& in)
+{
+    int blob_index = d->net->find_blob_index_by_name(blob_name);
+    if (blob_index == -1) return -1;
+    return input(blob_index, in);
+}
+
+int Extractor::input(int blob_index, const CudaMat& in)
+{
+    if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
+    d->blob_mats_gpu[blob_index] = in;
+    d->blob_mats[blob_index].release();
+    return 0;
+}
+
+int Extractor::extract(const char* blob_name, Mat& feat, int type)
+{
+    int blob_index = d->net->find_blob_index_by_name(blob_name);
+    if (blob_index == -1)
+    {
+        NCNN_LOGE("Try");
+        const std::vector<const char*>& names = d->net->output_names();
+        for (size_t i = 0; i < names.size(); i++) NCNN_LOGE("    ex.extract(\"%s\", out%d);", names[i], (int)i);
+        return -1;
+    }
+    return extract(blob_index, feat, type);
+}
+
+// src/net.cpp:2855-3025, Vulkan branch :2885-2933
+int Extractor::extract(int blob_index, Mat& feat, int /*type*/)
+{
+    if (blob_index < 0 || blob_index >= (int)d->blob_mats.size()) return -1;
+    if (!d->blob_mats[blob_index].empty())
+    {
+        feat = d->blob_mats[blob_index];
+        return 0;
+    }
+    CudaContext* ctx = acquire_cuda_context(d->net->opt.cuda_device_index);
+    if (!ctx)
+    {
+        NCNN_LOGE("no CUDA device available: %s", ncnn_cuda_last_error());
+        return -1;
+    }
+    int ret;
+    {
+        CudaCompute cmd(ctx);
+        CudaMat feat_gpu;
+        ret = extract(blob_index, feat_gpu, cmd);
+        if (ret == 0)
+        {
+            ret = cmd.record_download(feat_gpu, d->blob_mats[blob_index], d->opt);
+        }
+        int sret = cmd.submit_and_wait(); // the single device sync of an extract (src/net.cpp:2912-2916)
+        if (ret == 0) ret = sret;
+        d->h2d = cmd.h2d_bytes;
+        d->d2h = cmd.d2h_bytes;
+    }
+    reclaim_cuda_context(ctx);
+    if (ret != 0) return ret;
+    feat = d->blob_mats[blob_index];
+    return 0;
+}
+
+int Extractor::extract(const char* blob_name, CudaMat& feat, CudaCompute& cmd)
+{
+    int blob_index = d->net->find_blob_index_by_name(blob_name);
+    if (blob_index == -1) return -1;
+    return extract(blob_index, feat, cmd);
+}
+
+// src/net.cpp:3083-3116
+int Extractor::extract(int blob_index, CudaMat& feat, CudaCompute& cmd)
+{
+    if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
+    int ret = 0;
+    if (d->blob_mats_gpu[blob_index].empty())
+    {
+        if (!d->blob_mats[blob_index].empty())
+        {
+            ret = cmd.record_upload(d->blob_mats[blob_index], d->blob_mats_gpu[blob_index], d->opt);
+        }
+        else
+        {
+            int layer_index = d->net->blobs()[blob_index].producer;
+            if (layer_index < 0)
+            {
+                NCNN_LOGE("blob %s has no producer", d->net->blobs()[blob_index].name.c_str());
+                return -1;
+            }
+            ret = d->net->d->forward_layer(layer_index, d->blob_mats, d->blob_mats_gpu, cmd, d->opt);
+        }
+    }
+    if (ret != 0) return ret;
+    feat = d->blob_mats_gpu[blob_index];
+    return 0;
+}
+
+size_t Extractor::last_h2d_bytes() const
+{
+    return d->h2d;
+}
+size_t Extractor::last_d2h_bytes() const
+{
+    return d->d2h;
+}
+
+} // namespace ncnn

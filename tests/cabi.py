@@ -62,7 +62,7 @@ class GemmArgs(C.Structure):
 # every symbol include/ncnn_cuda.h declares (checked by the CPU-side export test)
 KERNEL_ABI_SYMBOLS = [
     "ncnn_cuda_device_count", "ncnn_cuda_set_device", "ncnn_cuda_get_device", "ncnn_cuda_device_info", "ncnn_cuda_last_error",
-    "ncnn_cuda_malloc", "ncnn_cuda_free", "ncnn_cuda_malloc_host", "ncnn_cuda_free_host", "ncnn_cuda_memcpy_h2d_async", "ncnn_cuda_memcpy_d2h_async",
+    "ncnn_cuda_malloc", "ncnn_cuda_free", "ncnn_cuda_malloc_host", "ncnn_cuda_free_host", "ncnn_cuda_host_is_pinned", "ncnn_cuda_memcpy_h2d_async", "ncnn_cuda_memcpy_d2h_async",
     "ncnn_cuda_memcpy_d2d_async", "ncnn_cuda_memset_async", "ncnn_cuda_stream_create", "ncnn_cuda_stream_destroy", "ncnn_cuda_stream_sync",
     "ncnn_cuda_device_sync", "ncnn_cuda_event_create", "ncnn_cuda_event_destroy", "ncnn_cuda_event_record", "ncnn_cuda_event_sync",
     "ncnn_cuda_event_elapsed_ms", "ncnn_cuda_graph_begin_capture", "ncnn_cuda_graph_end_capture", "ncnn_cuda_graph_launch", "ncnn_cuda_graph_destroy",
