@@ -244,6 +244,15 @@ NCNN_C_API void* ncnn_cuda_compute_get_stream(ncnn_cuda_compute_t cmd);
 NCNN_C_API int ncnn_cuda_compute_record_upload(ncnn_cuda_compute_t cmd, const ncnn_mat_t src, ncnn_cuda_mat_t* dst, const ncnn_option_t opt);
 NCNN_C_API int ncnn_cuda_compute_record_download(ncnn_cuda_compute_t cmd, const ncnn_cuda_mat_t src, ncnn_mat_t* dst, const ncnn_option_t opt);
 NCNN_C_API int ncnn_cuda_compute_submit_and_wait(ncnn_cuda_compute_t cmd);
+/* per-layer device times of the walks recorded on `cmd` (the reference's NCNN_BENCHMARK layer timing, src/net.cpp:145-180,
+ * :302-315): shape = {dims, w, h, d, c, n} of the layer's first top blob; valid after submit_and_wait */
+NCNN_C_API void ncnn_cuda_compute_set_profiling(ncnn_cuda_compute_t cmd, int enable);
+NCNN_C_API int ncnn_cuda_compute_get_profile_count(ncnn_cuda_compute_t cmd);
+NCNN_C_API int ncnn_cuda_compute_get_profile(ncnn_cuda_compute_t cmd, int i, int* layer_index, float* ms, int shape[6]);
+NCNN_C_API void ncnn_cuda_compute_clear_profile(ncnn_cuda_compute_t cmd);
+NCNN_C_API int ncnn_net_get_layer_count(const ncnn_net_t net);
+NCNN_C_API const char* ncnn_net_get_layer_type(const ncnn_net_t net, int i);
+NCNN_C_API const char* ncnn_net_get_layer_name(const ncnn_net_t net, int i);
 NCNN_C_API void ncnn_cuda_mat_destroy(ncnn_cuda_mat_t mat);
 NCNN_C_API int ncnn_cuda_mat_get_dims(const ncnn_cuda_mat_t mat);
 NCNN_C_API int ncnn_cuda_mat_get_w(const ncnn_cuda_mat_t mat);

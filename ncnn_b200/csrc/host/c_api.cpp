@@ -1075,6 +1075,44 @@ int ncnn_cuda_compute_submit_and_wait(ncnn_cuda_compute_t cmd)
 {
     return ((ComputeHolder*)cmd)->cmd->submit_and_wait();
 }
+void ncnn_cuda_compute_set_profiling(ncnn_cuda_compute_t cmd, int enable)
+{
+    ((ComputeHolder*)cmd)->cmd->set_profiling(enable != 0);
+}
+int ncnn_cuda_compute_get_profile_count(ncnn_cuda_compute_t cmd)
+{
+    return (int)((ComputeHolder*)cmd)->cmd->timings().size();
+}
+int ncnn_cuda_compute_get_profile(ncnn_cuda_compute_t cmd, int i, int* layer_index, float* ms, int shape[6])
+{
+    const std::vector<CudaCompute::LayerTiming>& t = ((ComputeHolder*)cmd)->cmd->timings();
+    if (i < 0 || i >= (int)t.size()) return -1;
+    *layer_index = t[i].layer_index;
+    *ms = t[i].ms;
+    shape[0] = t[i].dims;
+    shape[1] = t[i].w;
+    shape[2] = t[i].h;
+    shape[3] = t[i].d;
+    shape[4] = t[i].c;
+    shape[5] = t[i].n;
+    return 0;
+}
+void ncnn_cuda_compute_clear_profile(ncnn_cuda_compute_t cmd)
+{
+    ((ComputeHolder*)cmd)->cmd->clear_timings();
+}
+int ncnn_net_get_layer_count(const ncnn_net_t net)
+{
+    return (int)((const Net*)net->pthis)->layers().size();
+}
+const char* ncnn_net_get_layer_type(const ncnn_net_t net, int i)
+{
+    return ((const Net*)net->pthis)->layers()[i]->type.c_str();
+}
+const char* ncnn_net_get_layer_name(const ncnn_net_t net, int i)
+{
+    return ((const Net*)net->pthis)->layers()[i]->name.c_str();
+}
 void ncnn_cuda_mat_destroy(ncnn_cuda_mat_t mat)
 {
     delete (CudaMat*)mat;

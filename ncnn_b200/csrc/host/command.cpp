@@ -91,13 +91,48 @@ CudaWeightAllocator* get_cuda_weight_allocator(int device_index)
 }
 
 CudaCompute::CudaCompute(CudaContext* ctx)
-    : h2d_bytes(0), d2h_bytes(0), ctx_(ctx)
+    : h2d_bytes(0), d2h_bytes(0), ctx_(ctx), profiling_(false)
 {
+}
+
+void CudaCompute::profile_begin(int layer_index)
+{
+    LayerTiming t;
+    memset(&t, 0, sizeof(t));
+    t.layer_index = layer_index;
+    ncnn_cuda_event_create(&t.start);
+    ncnn_cuda_event_create(&t.stop);
+    ncnn_cuda_event_record(t.start, stream());
+    timings_.push_back(t);
+}
+
+void CudaCompute::profile_end(const CudaMat& top)
+{
+    if (timings_.empty()) return;
+    LayerTiming& t = timings_.back();
+    ncnn_cuda_event_record(t.stop, stream());
+    t.dims = top.dims;
+    t.w = top.w;
+    t.h = top.h;
+    t.d = top.d;
+    t.c = top.c;
+    t.n = top.n;
+}
+
+void CudaCompute::clear_timings()
+{
+    for (size_t i = 0; i < timings_.size(); i++)
+    {
+        if (timings_[i].start) ncnn_cuda_event_destroy(timings_[i].start);
+        if (timings_[i].stop) ncnn_cuda_event_destroy(timings_[i].stop);
+    }
+    timings_.clear();
 }
 
 CudaCompute::~CudaCompute()
 {
     if (!downloads_.empty() || !staging_in_flight_.empty() || !keep_alive_.empty()) submit_and_wait();
+    clear_timings();
 }
 
 static size_t mat_bytes(const Mat& m)
@@ -188,6 +223,11 @@ int CudaCompute::record_clone(const CudaMat& src, CudaMat& dst, const Option& op
 int CudaCompute::submit_and_wait()
 {
     int ret = ncnn_cuda_stream_sync(stream());
+    for (size_t i = 0; i < timings_.size(); i++)
+    {
+        if (ret == 0 && timings_[i].start && timings_[i].stop && timings_[i].ms == 0.f)
+            ncnn_cuda_event_elapsed_ms(timings_[i].start, timings_[i].stop, &timings_[i].ms);
+    }
     Allocator* sa = ctx_->staging_allocator;
     for (size_t i = 0; i < downloads_.size(); i++)
     {

@@ -65,6 +65,32 @@ public:
     int submit_and_wait();
     int reset();
 
+    // per-layer device timing, the CUDA form of the reference's NCNN_BENCHMARK / Vulkan timestamp queries
+    // (src/net.cpp:302-315, src/benchmark.cpp:30-152): an event pair around every layer of the walk
+    struct LayerTiming
+    {
+        int layer_index;
+        void* start;
+        void* stop;
+        int dims, w, h, d, c, n; // shape of the layer's first top blob
+        float ms;                // valid after submit_and_wait()
+    };
+    void set_profiling(bool enable)
+    {
+        profiling_ = enable;
+    }
+    bool profiling() const
+    {
+        return profiling_;
+    }
+    void profile_begin(int layer_index);
+    void profile_end(const CudaMat& top);
+    const std::vector<LayerTiming>& timings() const
+    {
+        return timings_;
+    }
+    void clear_timings();
+
     // bytes moved by record_upload / record_download since construction (bench.py's e2e accounting)
     size_t h2d_bytes;
     size_t d2h_bytes;
@@ -77,6 +103,8 @@ private:
         size_t bytes;
     };
     CudaContext* ctx_;
+    bool profiling_;
+    std::vector<LayerTiming> timings_;
     std::vector<PendingDownload> downloads_;
     std::vector<void*> staging_in_flight_;
     std::vector<CudaMat> keep_alive_;

@@ -883,7 +883,9 @@ int NetPrivate::forward_layer(int layer_index, std::vector<Mat>& blob_mats, std:
         int ret = forward_layer(producer, blob_mats, blob_mats_gpu, cmd, opt);
         if (ret != 0) return ret;
     }
+    if (cmd.profiling()) cmd.profile_begin(layer_index);
     int ret = do_forward_layer(layer, blob_mats_gpu, cmd, opt);
+    if (cmd.profiling()) cmd.profile_end(layer->tops.empty() ? CudaMat() : blob_mats_gpu[layer->tops[0]]);
     if (ret != 0) NCNN_LOGE("layer %s (%s) forward failed: %d %s", layer->name.c_str(), layer->type.c_str(), ret, ncnn_cuda_last_error());
     return ret;
 }
