@@ -91,6 +91,8 @@ static void fill_call(const ncnn_cuda_conv2d* conv, const Geom2& g, const ncnn_c
     c->act_type = act.type;
     c->act_p0 = act.p0;
     c->act_p1 = act.p1;
+    c->workspace = 0;
+    c->workspace_size = 0;
     c->tiled = (d.kernel_w == 1 && d.kernel_h == 1 && d.stride_w == 1 && d.stride_h == 1 && pad_left == 0 && pad_top == 0 && g.outw == g.inw && g.outh == g.inh) ? 1 : 0;
 }
 
@@ -144,7 +146,11 @@ int ncnn_cuda_conv2d_create(ncnn_cuda_conv2d_t* out, const ncnn_cuda_conv2d_desc
     c->has_tc = false;
     if (desc->elemtype != NCNN_CUDA_F32 && tc_available())
     {
-        if (tc_plan_create(&c->tc, desc->elemtype, inch, outch, taps, wt.data(), desc->bias_term ? bias : 0, stream) == 0) c->has_tc = true;
+        // the A_ROWS stem variant needs the explicit left padding; SAME modes resolve per input size -> -1 disables it
+        const int pad_left_known = (desc->pad_left >= 0 && desc->pad_right >= 0 && desc->pad_top >= 0 && desc->pad_bottom >= 0) ? desc->pad_left : -1;
+        if (tc_plan_create(&c->tc, desc->elemtype, inch, outch, desc->kernel_w, desc->kernel_h, desc->stride_w, desc->dilation_w, pad_left_known, wt.data(),
+                           desc->bias_term ? bias : 0, stream) == 0)
+            c->has_tc = true;
     }
 
     // SIMT pack: [Kpad][wp_ld], k-major rows so a CTA's B tile is contiguous float4 loads
@@ -190,9 +196,16 @@ int ncnn_cuda_conv2d_destroy(ncnn_cuda_conv2d_t c)
     return 0;
 }
 
-size_t ncnn_cuda_conv2d_workspace_size(ncnn_cuda_conv2d_t, const ncnn_cuda_tensor*, const ncnn_cuda_tensor*)
+size_t ncnn_cuda_conv2d_workspace_size(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top)
 {
-    return 0; // every path is an implicit GEMM: no im2col buffer, no padded copy
+    // only the small-channel stem variant keeps a (zero-padded, 4/8-channel) copy of its input; everything else is an
+    // implicit GEMM straight from the blob
+    if (!conv || !conv->has_tc || !bottom || !top || bottom->elemtype != conv->desc.elemtype) return 0;
+    Geom2 g;
+    if (geom_of(conv, bottom, top, &g) != 0) return 0;
+    TcConvCall call;
+    fill_call(conv, g, bottom, top, conv->desc.pad_left, conv->desc.pad_top, 0, conv->desc.act, &call);
+    return tc_conv_workspace(&conv->tc, &call);
 }
 
 int ncnn_cuda_conv2d_algo(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom)
@@ -201,7 +214,7 @@ int ncnn_cuda_conv2d_algo(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* botto
 }
 
 int ncnn_cuda_conv2d_forward(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int pad_left, int pad_top,
-                             const ncnn_cuda_tensor* residual, const ncnn_cuda_activation* act_override, void*, size_t, void* stream_)
+                             const ncnn_cuda_tensor* residual, const ncnn_cuda_activation* act_override, void* workspace, size_t workspace_size, void* stream_)
 {
     cudaStream_t stream = as_stream(stream_);
     NC_REQUIRE(conv && bottom && top && bottom->data && top->data, "conv2d_forward: null argument");
@@ -213,6 +226,8 @@ int ncnn_cuda_conv2d_forward(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bo
 
     TcConvCall call;
     fill_call(conv, g, bottom, top, pad_left, pad_top, residual, act, &call);
+    call.workspace = workspace;
+    call.workspace_size = workspace_size;
     int algo = pick_algo(conv, g, bottom, top, pad_left, pad_top, residual, &call);
     if (algo != 0)
     {

@@ -1,6 +1,7 @@
 // tc_gemm.cu -- host side of the tcgen05 implicit-GEMM path: weight re-packing (the create_pipeline step of
 // Convolution / InnerProduct, cf. src/layer/x86/convolution_x86.cpp:279-500 in the reference), TMA descriptor
-// encoding (tiled for weights and 1x1 convs, im2col mode for everything else) and the persistent-kernel launch.
+// encoding (tiled for weights, outputs, residuals and 1x1 convs; im2col mode for general convs; overlapping-stride
+// tiled maps for small-channel stems) and the persistent-kernel launch.
 #include "tc_gemm.cuh"
 
 #include <mutex>
@@ -73,9 +74,14 @@ static inline uint16_t f32_to_16(float f, int elemtype)
     return u;
 }
 
+static CUtensorMapSwizzle swizzle_for_bytes(int row_bytes)
+{
+    return row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 static CUtensorMapSwizzle swizzle_for(int block_k)
 {
-    return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    return swizzle_for_bytes(block_k * 2);
 }
 
 static CUtensorMapDataType dtype_for(int elemtype)
@@ -83,10 +89,23 @@ static CUtensorMapDataType dtype_for(int elemtype)
     return elemtype == NCNN_CUDA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
-int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int taps, const float* w, const float* bias, cudaStream_t stream)
+static int encode_weights(CUtensorMap* map, int elemtype, void* w, int Kp, int outch, int block_k, int block_n)
+{
+    cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)outch};
+    cuuint64_t gstride[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encodeTiled(map, dtype_for(elemtype), 2, w, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int kernel_w, int kernel_h, int stride_w, int dil_w, int pad_left, const float* w,
+                   const float* bias, cudaStream_t stream)
 {
     memset(plan, 0, sizeof(*plan));
     if (!tc_available()) return -1;
+    const int taps = kernel_w * kernel_h;
     plan->elemtype = elemtype;
     plan->block_k = tc_pick_block_k(inch);
     plan->block_n = tc_pick_block_n(outch);
@@ -112,19 +131,60 @@ int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int taps, co
     if (bias) memcpy(bpad.data(), bias, sizeof(float) * outch);
     NC_CHECK(cudaMalloc((void**)&plan->bias_pad, bpad.size() * sizeof(float)));
     NC_CHECK(cudaMemcpyAsync(plan->bias_pad, bpad.data(), bpad.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+
+    // ---- A_ROWS variant for small-channel stems (see tc_gemm.cuh): needs the layer's explicit left padding
+    std::vector<uint16_t> rows;
+    if (inch <= 8 && taps > 1 && dil_w == 1 && pad_left >= 0 && kernel_w <= 16)
+    {
+        int cp, shift, wp;
+        if (inch <= 4 && (stride_w % 2) == 0)
+        {
+            cp = 4;                     // 8-byte pixels: the window start (stride_w * ox - pad_left - shift pixels) must be 16-byte aligned
+            shift = pad_left & 1;
+            wp = ((kernel_w + shift + 3) / 4) * 4;
+        }
+        else
+        {
+            cp = 8;                     // 16-byte pixels: any start is aligned
+            shift = 0;
+            wp = ((kernel_w + 1) / 2) * 2;
+        }
+        const int krow = wp * cp;
+        if (krow == 16 || krow == 32 || krow == 64 || krow == 128)
+        {
+            plan->rows_cp = cp;
+            plan->rows_wp = wp;
+            plan->rows_shift = shift;
+            plan->rows_block_k = krow > 64 ? 64 : krow;
+            plan->rows_cblocks = krow / plan->rows_block_k;
+            plan->rows_Kp = kernel_h * krow;
+            rows.assign((size_t)outch * plan->rows_Kp, 0);
+            for (int oc = 0; oc < outch; oc++)
+                for (int ky = 0; ky < kernel_h; ky++)
+                    for (int kx = 0; kx < kernel_w; kx++)
+                    {
+                        const float* src = w + ((size_t)oc * taps + ky * kernel_w + kx) * inch;
+                        uint16_t* dst = rows.data() + (size_t)oc * plan->rows_Kp + (size_t)ky * krow + (size_t)(kx + shift) * cp;
+                        for (int ci = 0; ci < inch; ci++) dst[ci] = f32_to_16(src[ci], elemtype);
+                    }
+            NC_CHECK(cudaMalloc(&plan->w_rows, rows.size() * 2));
+            NC_CHECK(cudaMemcpyAsync(plan->w_rows, rows.data(), rows.size() * 2, cudaMemcpyHostToDevice, stream));
+            plan->rows_ok = 1;
+        }
+    }
     NC_CHECK(cudaStreamSynchronize(stream)); // the staging vectors die at scope exit
 
-    cuuint64_t gdim[2] = {(cuuint64_t)plan->Kp, (cuuint64_t)outch};
-    cuuint64_t gstride[1] = {(cuuint64_t)plan->Kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)plan->block_k, (cuuint32_t)plan->block_n};
-    cuuint32_t estride[2] = {1, 1};
-    CUresult r = g_encodeTiled(&plan->tmap_b, dtype_for(elemtype), 2, plan->w_packed, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               swizzle_for(plan->block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
+    if (encode_weights(&plan->tmap_b, elemtype, plan->w_packed, plan->Kp, outch, plan->block_k, plan->block_n) != 0)
     {
         set_last_error_msg("cuTensorMapEncodeTiled(weights) failed");
         tc_plan_destroy(plan);
         return -1;
+    }
+    if (plan->rows_ok && encode_weights(&plan->tmap_b_rows, elemtype, plan->w_rows, plan->rows_Kp, outch, plan->rows_block_k, plan->block_n) != 0)
+    {
+        cudaFree(plan->w_rows);
+        plan->w_rows = 0;
+        plan->rows_ok = 0;
     }
     return 0;
 }
@@ -133,8 +193,73 @@ void tc_plan_destroy(TcPlan* plan)
 {
     if (plan->w_packed) cudaFree(plan->w_packed);
     if (plan->bias_pad) cudaFree(plan->bias_pad);
+    if (plan->w_rows) cudaFree(plan->w_rows);
     plan->w_packed = 0;
     plan->bias_pad = 0;
+    plan->w_rows = 0;
+}
+
+// ---------------------------------------------------------------- A_ROWS geometry
+struct RowsGeom
+{
+    int Lp, Hp, Wpitch; // physical left pad, padded rows, padded row pitch (pixels)
+    size_t bytes;
+};
+
+static bool rows_applicable(const TcPlan* plan, const TcConvCall* c, RowsGeom* g)
+{
+    if (!plan->rows_ok || c->tiled || c->residual) return false;
+    if (c->dil_w != 1) return false;
+    const int cp = plan->rows_cp, wp = plan->rows_wp;
+    if (cp == 4 && (((c->pad_left + plan->rows_shift) & 1) || (c->stride_w & 1))) return false;
+    g->Lp = c->pad_left + plan->rows_shift;
+    int need_w = c->stride_w * (c->outw - 1) + wp;
+    int wpitch = g->Lp + c->inw > need_w ? g->Lp + c->inw : need_w;
+    if (cp == 4) wpitch = (wpitch + 1) & ~1; // 16-byte row pitch
+    int need_h = c->stride_h * (c->outh - 1) + (c->kernel_h - 1) * c->dil_h + 1;
+    int hp = c->pad_top + c->inh > need_h ? c->pad_top + c->inh : need_h;
+    g->Wpitch = wpitch;
+    g->Hp = hp;
+    g->bytes = (size_t)c->n * hp * wpitch * cp * 2;
+    if ((long long)c->n * c->outh > 0x7fffffffLL) return false;
+    return true;
+}
+
+size_t tc_conv_workspace(const TcPlan* plan, const TcConvCall* c)
+{
+    RowsGeom g;
+    if (!plan->w_packed || !rows_applicable(plan, c, &g)) return 0;
+    return g.bytes;
+}
+
+// NHWC blob (cpitch channels per pixel) -> zero-padded [n][Hp][Wpitch][CP] copy; one thread per destination pixel
+template<int CP>
+__global__ void __launch_bounds__(256) rows_pack_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int inh, int inw, int inch, int in_cpitch,
+                                                        int Hp, int Wpitch, int Lp, int pad_top)
+{
+    const long long total = (long long)n * Hp * Wpitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const int x = (int)(i % Wpitch);
+        long long r = i / Wpitch;
+        const int y = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        const int sx = x - Lp, sy = y - pad_top;
+        uint16_t v[CP];
+#pragma unroll
+        for (int k = 0; k < CP; k++) v[k] = 0;
+        if (sx >= 0 && sx < inw && sy >= 0 && sy < inh)
+        {
+            const uint16_t* src = in + ((long long)b * inh * inw + (long long)sy * inw + sx) * in_cpitch;
+#pragma unroll
+            for (int k = 0; k < CP; k++)
+                if (k < inch) v[k] = src[k];
+        }
+        if (CP == 4)
+            *reinterpret_cast<uint2*>(out + i * CP) = *reinterpret_cast<const uint2*>(v);
+        else
+            *reinterpret_cast<uint4*>(out + i * CP) = *reinterpret_cast<const uint4*>(v);
+    }
 }
 
 int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
@@ -143,6 +268,7 @@ int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
     if ((c->in_cpitch & 7) || (c->out_cpitch & 7)) return 0;
     if (((uintptr_t)c->in & 15) || ((uintptr_t)c->out & 15)) return 0;
     if (c->residual && ((c->res_cpitch & 7) || ((uintptr_t)c->residual & 15))) return 0;
+    if ((long long)c->n * c->outh * c->outw > 0x7fffff00LL) return 0;
     if (c->tiled) return 1;
     // TMA im2col limits for 2 spatial dims: corners in [-128, 127], filter offsets <= 255
     // (cutlass/conv/collective/sm100_implicit_gemm_umma_warpspecialized.hpp can_implement)
@@ -159,29 +285,31 @@ int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
     return 1;
 }
 
-template<typename T, int BLOCK_N, int BLOCK_K, bool IM2COL>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Params& p, cudaStream_t stream)
+template<typename T, int BLOCK_N, int BLOCK_K, int AMODE>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const tc::Params& p, long long tiles,
+                     cudaStream_t stream)
 {
     using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K>;
-    auto kern = tc::tc_gemm_kernel<T, BLOCK_N, BLOCK_K, IM2COL>;
+    static_assert(Plan::kStages >= 2, "not enough shared memory for a 2-stage pipeline");
+    auto kern = tc::tc_gemm_kernel<T, BLOCK_N, BLOCK_K, AMODE>;
     static bool attr_set = false;
     if (!attr_set)
     {
         NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::total));
         attr_set = true;
     }
-    long long tiles = ((p.M + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, tc::kNumThreads, Plan::total, stream>>>(ta, tb, p);
+    kern<<<grid, tc::kNumThreads, Plan::total, stream>>>(ta, tb, to, tr, p);
     NC_LAUNCH_CHECK();
     return 0;
 }
 
-template<typename T, bool IM2COL>
-static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const tc::Params& p, cudaStream_t stream)
+template<typename T, int AMODE>
+static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const tc::Params& p,
+                       long long tiles, cudaStream_t stream)
 {
 #define NC_TC(BN, BK) \
-    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, IM2COL>(ta, tb, p, stream)
+    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, to, tr, p, tiles, stream)
     NC_TC(256, 64);
     NC_TC(128, 64);
     NC_TC(64, 64);
@@ -199,13 +327,65 @@ static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CU
     return -1;
 }
 
+// (channels, columns, rows) map of a channel-innermost blob for the epilogue's TMA store / residual load
+static int encode_out(CUtensorMap* map, int elemtype, const void* ptr, int C, int cpitch, long long cols, long long rows, int epi_n)
+{
+    cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[2] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * (cuuint64_t)cols};
+    cuuint32_t box[3] = {(cuuint32_t)epi_n, (cuuint32_t)tc::BLOCK_M, 1};
+    cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = g_encodeTiled(map, dtype_for(elemtype), 3, (void*)ptr, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(epi_n * 2),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream)
 {
     if (!tc_conv_supported(plan, c)) return -1;
-    CUtensorMap ta;
+    CUtensorMap ta, to, tr;
     const long long M = (long long)c->n * c->outh * c->outw;
     if (M == 0) return 0;
-    if (c->tiled)
+    const int epi_n = plan->block_n < 64 ? plan->block_n : 64;
+
+    RowsGeom rg;
+    const bool use_rows = rows_applicable(plan, c, &rg) && c->workspace && c->workspace_size >= rg.bytes;
+    int amode = c->tiled ? tc::A_TILED : tc::A_IM2COL;
+    int block_k = plan->block_k;
+    const CUtensorMap* tb = &plan->tmap_b;
+
+    tc::Params p;
+    memset(&p, 0, sizeof(p));
+    if (use_rows)
+    {
+        const int cp = plan->rows_cp;
+        // zero-padded small-channel copy of the input
+        const long long total = (long long)c->n * rg.Hp * rg.Wpitch;
+        int grid = grid_for(total, 256, 16);
+        if (cp == 4)
+            rows_pack_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
+                                                         c->pad_top);
+        else
+            rows_pack_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
+                                                         c->pad_top);
+        NC_LAUNCH_CHECK();
+        // dims: (window elements, output column, padded row, image); the column stride is the conv stride -> overlapping windows
+        cuuint64_t gdim[4] = {(cuuint64_t)(plan->rows_wp * cp), (cuuint64_t)c->outw, (cuuint64_t)rg.Hp, (cuuint64_t)c->n};
+        cuuint64_t gstride[3] = {(cuuint64_t)c->stride_w * cp * 2, (cuuint64_t)rg.Wpitch * cp * 2, (cuuint64_t)rg.Hp * rg.Wpitch * cp * 2};
+        cuuint32_t box[4] = {(cuuint32_t)plan->rows_block_k, (cuuint32_t)tc::BLOCK_M, 1, 1};
+        cuuint32_t estride[4] = {1, 1, 1, 1};
+        CUresult r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, c->workspace, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   swizzle_for(plan->rows_block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+        {
+            amode = tc::A_ROWS;
+            block_k = plan->rows_block_k;
+            tb = &plan->tmap_b_rows;
+            p.cblocks = plan->rows_cblocks;
+            p.num_k_blocks = c->kernel_h * plan->rows_cblocks;
+            p.chunks_per_row = (c->outw + tc::BLOCK_M - 1) / tc::BLOCK_M;
+        }
+    }
+    if (amode == tc::A_TILED)
     {
         cuuint64_t gdim[2] = {(cuuint64_t)c->inch, (cuuint64_t)M};
         cuuint64_t gstride[1] = {(cuuint64_t)c->in_cpitch * 2};
@@ -219,7 +399,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
             return -1;
         }
     }
-    else
+    else if (amode == tc::A_IM2COL)
     {
         cuuint64_t gdim[4] = {(cuuint64_t)c->inch, (cuuint64_t)c->inw, (cuuint64_t)c->inh, (cuuint64_t)c->n};
         cuuint64_t gstride[3] = {(cuuint64_t)c->in_cpitch * 2, (cuuint64_t)c->in_cpitch * 2 * c->inw, (cuuint64_t)c->in_cpitch * 2 * c->inw * c->inh};
@@ -242,12 +422,34 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
             if (bytes < 131072) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
         }
     }
+    if (amode != tc::A_ROWS)
+    {
+        p.cblocks = plan->cblocks;
+        p.num_k_blocks = plan->num_k_blocks;
+        p.chunks_per_row = 1;
+    }
 
-    tc::Params p;
+    // output / residual maps
+    const long long cols = amode == tc::A_ROWS ? c->outw : M;
+    const long long rows = amode == tc::A_ROWS ? (long long)c->n * c->outh : 1;
+    if (encode_out(&to, plan->elemtype, c->out, plan->outch, c->out_cpitch, cols, rows, epi_n) != 0)
+    {
+        set_last_error_msg("cuTensorMapEncodeTiled(output) failed");
+        return -1;
+    }
+    if (c->residual)
+    {
+        if (encode_out(&tr, plan->elemtype, c->residual, plan->outch, c->res_cpitch, cols, rows, epi_n) != 0)
+        {
+            set_last_error_msg("cuTensorMapEncodeTiled(residual) failed");
+            return -1;
+        }
+    }
+    else
+        tr = to;
+
     p.M = M;
     p.N = plan->outch;
-    p.num_k_blocks = plan->num_k_blocks;
-    p.cblocks = plan->cblocks;
     p.taps_w = c->kernel_w;
     p.outw = c->outw;
     p.outh = c->outh;
@@ -266,11 +468,19 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     p.act_p0 = c->act_p0;
     p.act_p1 = c->act_p1;
 
+    const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row : (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+    const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);
+
+#define NC_MODE(T)                                                                                                            \
+    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, to, tr, p, tiles, stream);  \
+    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, to, tr, p, tiles, stream); \
+    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, to, tr, p, tiles, stream)
     if (plan->elemtype == NCNN_CUDA_BF16)
-        return c->tiled ? dispatch_tc<__nv_bfloat16, false>(plan->block_n, plan->block_k, ta, plan->tmap_b, p, stream)
-                        : dispatch_tc<__nv_bfloat16, true>(plan->block_n, plan->block_k, ta, plan->tmap_b, p, stream);
-    return c->tiled ? dispatch_tc<__half, false>(plan->block_n, plan->block_k, ta, plan->tmap_b, p, stream)
-                    : dispatch_tc<__half, true>(plan->block_n, plan->block_k, ta, plan->tmap_b, p, stream);
+    {
+        NC_MODE(__nv_bfloat16);
+    }
+    NC_MODE(__half);
+#undef NC_MODE
 }
 
 } // namespace ncnn_cuda

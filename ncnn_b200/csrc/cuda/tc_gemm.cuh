@@ -37,6 +37,8 @@ struct Params
     // im2col geometry
     int outw, outh;
     int stride_w, stride_h, dil_w, dil_h, pad_left, pad_top;
+    // A_ROWS geometry: chunks of 128 output columns per output row; rows = n * outh
+    int chunks_per_row;
     // epilogue
     const float* bias; // padded to a multiple of BLOCK_N, never NULL
     void* out;
@@ -122,6 +124,49 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+// shared -> global tensor store (bulk async group); out-of-range rows / columns are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template<int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template<int N>
+__device__ __forceinline__ void tma_store_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void epi_bar_sync()
+{
+    asm volatile("bar.sync 1, 128;" ::: "memory"); // the four epilogue warps only
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -173,6 +218,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_wait_ld()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -202,17 +258,38 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format /*0 f16, 1 bf16*
     return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// A-operand addressing modes
+//   A_TILED  : A is a plain [M][C] matrix (1x1 stride-1 unpadded conv, InnerProduct, Gemm): 2-D TMA tiles
+//   A_IM2COL : TMA im2col mode over the NHWC blob, one (tap, 64-channel slab) per k-block
+//   A_ROWS   : small-channel stems (cin <= 8): the input is re-packed once per call into a zero-padded
+//              [n][Hp][Wp][Cp] image (Cp = 4 or 8) and a k-block is one filter ROW: kw' consecutive pixels x Cp channels
+//              are contiguous in memory, so a 4-D *tiled* TMA whose pixel stride is the conv stride (overlapping
+//              windows) delivers, for 128 consecutive output columns of one output row, their kw'*Cp-wide K slab.
+//              One tile = one (image, output row, 128-column chunk).
+enum
+{
+    A_TILED = 0,
+    A_IM2COL = 1,
+    A_ROWS = 2
+};
+
 template<int BLOCK_N, int BLOCK_K>
 struct SmemPlan
 {
     static constexpr int a_bytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int b_bytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int stage_bytes = a_bytes + b_bytes; // both multiples of 1024 for the tile sizes used
-    static constexpr int max_bytes = 200 * 1024;
+    // epilogue staging: the accumulator tile leaves through shared memory in EPI_N-column chunks (TMA store), the
+    // fused residual arrives the same way (TMA load); two buffers each
+    static constexpr int EPI_N = BLOCK_N < 64 ? BLOCK_N : 64;
+    static constexpr int epi_chunk_bytes = BLOCK_M * EPI_N * 2;
+    static constexpr int epi_bytes = 4 * epi_chunk_bytes;
+    static constexpr int bias_bytes = 1024;
+    static constexpr int barrier_bytes = 256;
+    static constexpr int max_bytes = 225 * 1024 - epi_bytes - bias_bytes - barrier_bytes - 1024;
     static constexpr int stages_raw = max_bytes / stage_bytes;
     static constexpr int kStages = stages_raw > 8 ? 8 : stages_raw;
-    static constexpr int barrier_bytes = 256;
-    static constexpr int total = kStages * stage_bytes + barrier_bytes + 1024; // + alignment slack
+    static constexpr int total = kStages * stage_bytes + epi_bytes + bias_bytes + barrier_bytes + 1024; // + alignment slack
 };
 
 template<typename T>
@@ -273,37 +350,57 @@ struct Pack8<__half>
 };
 
 // ---------------------------------------------------------------- the kernel
-template<typename T, int BLOCK_N, int BLOCK_K, bool IM2COL>
+// Output (and residual) tensor maps are rank 3: (channels, columns, rows)
+//   A_TILED / A_IM2COL : (C, M, 1)            tile rows m0 .. m0+127 are consecutive output pixels
+//   A_ROWS             : (C, outw, n*outh)    tile rows are 128 consecutive columns of one output row
+template<typename T, int BLOCK_N, int BLOCK_K, int AMODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+               const __grid_constant__ CUtensorMap tmap_res, const Params p)
 {
     using Plan = SmemPlan<BLOCK_N, BLOCK_K>;
     constexpr int kStages = Plan::kStages;
+    constexpr int EPI_N = Plan::EPI_N;
+    constexpr int NCHUNK = BLOCK_N / EPI_N;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N; // power of two for BLOCK_N in {16..256}
+    // swizzle of the epilogue staging tiles: rows of EPI_N 16-bit values = 128 / 64 / 32 bytes
+    constexpr int EPI_ROW_BYTES = EPI_N * 2;
+    constexpr int EPI_CHUNKS16 = EPI_ROW_BYTES / 16; // 16-byte units per row: 8 / 4 / 2
 
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operand tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Plan::a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Plan::stage_bytes);
-    uint64_t* full_bar = bars;                  // [kStages]
-    uint64_t* empty_bar = bars + kStages;       // [kStages]
-    uint64_t* tmem_full_bar = bars + 2 * kStages;  // [2]
+    uint8_t* smem_out = smem + kStages * Plan::stage_bytes;      // [2][BLOCK_M][EPI_N]
+    uint8_t* smem_res = smem_out + 2 * Plan::epi_chunk_bytes;    // [2][BLOCK_M][EPI_N]
+    float* smem_bias = reinterpret_cast<float*>(smem_res + 2 * Plan::epi_chunk_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + Plan::bias_bytes);
+    uint64_t* full_bar = bars;                         // [kStages]
+    uint64_t* empty_bar = bars + kStages;              // [kStages]
+    uint64_t* tmem_full_bar = bars + 2 * kStages;      // [2]
     uint64_t* tmem_empty_bar = bars + 2 * kStages + 2; // [2]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* res_full_bar = bars + 2 * kStages + 4;   // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int num_m_blocks = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+    int num_m_blocks;
+    if (AMODE == A_ROWS)
+        num_m_blocks = (int)(p.M / p.outw) * p.chunks_per_row; // rows * chunks
+    else
+        num_m_blocks = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     const int num_tiles = num_m_blocks * num_n_blocks;
+    const bool has_res = p.residual != nullptr;
 
     if (warp == 0 && lane == 0)
     {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_out);
+        if (has_res) prefetch_tmap(&tmap_res);
     }
     if (warp == 1 && lane == 0)
     {
@@ -316,6 +413,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+            mbar_init(smem_u32(&res_full_bar[i]), 1);
         }
         fence_barrier_init();
     }
@@ -341,7 +439,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int m_blk = tile / num_n_blocks;
                 const long long m0 = (long long)m_blk * BLOCK_M;
                 int base_w = 0, base_h = 0, base_n = 0;
-                if (IM2COL)
+                if (AMODE == A_IM2COL)
                 {
                     const int opix = p.outw * p.outh;
                     base_n = (int)(m0 / opix);
@@ -351,6 +449,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     base_w = ox * p.stride_w - p.pad_left;
                     base_h = oy * p.stride_h - p.pad_top;
                 }
+                else if (AMODE == A_ROWS)
+                {
+                    const int chunk = m_blk % p.chunks_per_row;
+                    const int row = m_blk / p.chunks_per_row; // img * outh + oy
+                    base_n = row / p.outh;
+                    base_h = (row - base_n * p.outh) * p.stride_h; // physical row of filter row 0 (top padding is materialised)
+                    base_w = chunk * BLOCK_M;                      // first output column of the chunk
+                }
                 for (int kb = 0; kb < p.num_k_blocks; kb++)
                 {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -358,12 +464,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_expect_tx(fb, Plan::stage_bytes);
                     const int tap = kb / p.cblocks;
                     const int cb = kb - tap * p.cblocks;
-                    if (IM2COL)
+                    if (AMODE == A_IM2COL)
                     {
                         const int ky = tap / p.taps_w;
                         const int kx = tap - ky * p.taps_w;
                         tma_load_im2col_4d(smem_u32(smem_a + stage * Plan::a_bytes), &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n,
                                            (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
+                    }
+                    else if (AMODE == A_ROWS)
+                    {
+                        // tap = filter row; the K slab of that row is cb * BLOCK_K .. +BLOCK_K of the (pixels x Cp) window
+                        tma_load_4d(smem_u32(smem_a + stage * Plan::a_bytes), &tmap_a, fb, cb * BLOCK_K, base_w, base_h + tap * p.dil_h, base_n);
                     }
                     else
                     {
@@ -421,74 +532,157 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     else
     {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..5, 128 threads) =====================
+        // TMEM -> registers (+bias, +residual, activation) -> swizzled shared memory -> TMA store, EPI_N columns at a
+        // time through two staging buffers; the residual tile comes in by TMA load two chunks ahead.
         const int lane_group = warp & 3; // TMEM lanes [32*lane_group, +32) are the ones this warp may read
+        const int row = lane_group * 32 + lane;
+        const bool leader = (warp == kEpilogueWarp0 && lane == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        T* out = reinterpret_cast<T*>(p.out);
-        const T* res = reinterpret_cast<const T*>(p.residual);
+        uint32_t g = 0; // running chunk counter of this CTA (buffer = g & 1, parity = (g >> 1) & 1)
+
+        const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const uint32_t total_chunks = (uint32_t)my_tiles * NCHUNK;
+
+        // coordinates of chunk number q (0-based over this CTA's tiles) in the (C, col, row) output tensor
+        auto chunk_coords = [&](uint32_t q, int& c0, int& c1, int& c2) {
+            const int tile = blockIdx.x + (int)(q / NCHUNK) * gridDim.x;
+            const int cc = (int)(q % NCHUNK);
+            const int n_blk = tile % num_n_blocks;
+            const int m_blk = tile / num_n_blocks;
+            c0 = n_blk * BLOCK_N + cc * EPI_N;
+            if (AMODE == A_ROWS)
+            {
+                c1 = (m_blk % p.chunks_per_row) * BLOCK_M;
+                c2 = m_blk / p.chunks_per_row;
+            }
+            else
+            {
+                c1 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
+                c2 = 0;
+            }
+        };
+        auto issue_residual = [&](uint32_t q) {
+            int c0, c1, c2;
+            chunk_coords(q, c0, c1, c2);
+            const uint32_t bar = smem_u32(&res_full_bar[q & 1]);
+            mbar_expect_tx(bar, Plan::epi_chunk_bytes);
+            tma_load_3d(smem_u32(smem_res + (q & 1) * Plan::epi_chunk_bytes), &tmap_res, bar, c0, c1, c2);
+        };
+        if (has_res && leader)
+        {
+            if (total_chunks > 0) issue_residual(0);
+            if (total_chunks > 1) issue_residual(1);
+        }
+
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
             const int n_blk = tile % num_n_blocks;
-            const int m_blk = tile / num_n_blocks;
-            const long long m = (long long)m_blk * BLOCK_M + lane_group * 32 + lane;
-            const bool row_ok = m < p.M;
             const int n0 = n_blk * BLOCK_N;
+            // bias of this tile's columns (the previous tile's readers are past their last chunk barrier)
+            for (int i = threadIdx.x - kEpilogueWarp0 * 32; i < BLOCK_N; i += 128) smem_bias[i] = __ldg(p.bias + n0 + i);
+
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            T* orow = out + m * p.out_cpitch;
-            const T* rrow = res ? res + m * p.res_cpitch : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32)
+            for (int cc = 0; cc < NCHUNK; cc++, g++)
             {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + (uint32_t)c, r);
-                tmem_wait_ld();
-                if (row_ok)
+                const int buf = (int)(g & 1);
+                uint8_t* obuf = smem_out + buf * Plan::epi_chunk_bytes;
+                const uint8_t* rbuf = smem_res + buf * Plan::epi_chunk_bytes;
+                // the TMA store that last used this buffer (chunk g-2) must have finished reading it
+                if (leader) tma_store_wait_read<1>();
+                epi_bar_sync(); // also publishes smem_bias on the first chunk
+                if (has_res) mbar_wait(smem_u32(&res_full_bar[buf]), (g >> 1) & 1);
+
+                // gather the chunk row: EPI_N accumulators (+bias, +residual) in registers
+                float v[EPI_N];
+#pragma unroll
+                for (int h = 0; h < EPI_N / 32; h++)
+                {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * EPI_N + h * 32), r);
+                    tmem_wait_ld();
+                    const float* bs = smem_bias + cc * EPI_N + h * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[h * 32 + j] = __uint_as_float(r[j]) + bs[j];
+                }
+                if (has_res)
                 {
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; g8++)
+                    for (int u = 0; u < EPI_CHUNKS16; u++)
                     {
-                        const int col = n0 + c + g8 * 8;
-                        if (col < p.out_cpitch)
-                        {
-                            float v[8];
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                            v[0] = __uint_as_float(r[g8 * 8 + 0]) + b0.x;
-                            v[1] = __uint_as_float(r[g8 * 8 + 1]) + b0.y;
-                            v[2] = __uint_as_float(r[g8 * 8 + 2]) + b0.z;
-                            v[3] = __uint_as_float(r[g8 * 8 + 3]) + b0.w;
-                            v[4] = __uint_as_float(r[g8 * 8 + 4]) + b1.x;
-                            v[5] = __uint_as_float(r[g8 * 8 + 5]) + b1.y;
-                            v[6] = __uint_as_float(r[g8 * 8 + 6]) + b1.z;
-                            v[7] = __uint_as_float(r[g8 * 8 + 7]) + b1.w;
-                            if (rrow)
-                            {
-                                float rv[8];
-                                const uint4 ru = *reinterpret_cast<const uint4*>(rrow + col);
-                                Pack8<T>::unpack(ru, rv);
+                        const int sw = u ^ ((EPI_CHUNKS16 == 8) ? (row & 7) : (EPI_CHUNKS16 == 4 ? ((row >> 1) & 3) : ((row >> 2) & 1)));
+                        float rv[8];
+                        const uint4 ru = *reinterpret_cast<const uint4*>(rbuf + row * EPI_ROW_BYTES + sw * 16);
+                        Pack8<T>::unpack(ru, rv);
 #pragma unroll
-                                for (int j = 0; j < 8; j++) v[j] += rv[j];
-                            }
-                            if (p.act_type != 0)
-                            {
-#pragma unroll
-                                for (int j = 0; j < 8; j++) v[j] = apply_activation(v[j], p.act_type, p.act_p0, p.act_p1);
-                            }
-                            *reinterpret_cast<uint4*>(orow + col) = Pack8<T>::pack(v);
-                        }
+                        for (int j = 0; j < 8; j++) v[u * 8 + j] += rv[j];
                     }
                 }
+                // activation: one uniform branch per chunk, not per element (a per-element switch gets if-converted
+                // into every transcendental path)
+                const int act = p.act_type;
+                if (act == 1)
+                {
+#pragma unroll
+                    for (int j = 0; j < EPI_N; j++) v[j] = fmaxf(v[j], 0.f);
+                }
+                else if (act == 7)
+                {
+#pragma unroll
+                    for (int j = 0; j < EPI_N; j++) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+                }
+                else if (act == 2)
+                {
+#pragma unroll
+                    for (int j = 0; j < EPI_N; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_p0;
+                }
+                else if (act == 3)
+                {
+#pragma unroll
+                    for (int j = 0; j < EPI_N; j++) v[j] = fminf(fmaxf(v[j], p.act_p0), p.act_p1);
+                }
+                else if (act != 0)
+                {
+#pragma unroll
+                    for (int j = 0; j < EPI_N; j++) v[j] = apply_activation(v[j], act, p.act_p0, p.act_p1);
+                }
+#pragma unroll
+                for (int u = 0; u < EPI_CHUNKS16; u++)
+                {
+                    // 128B/64B/32B swizzle as TMA applies it: 16-byte unit index XOR (row bits) restricted to the row width
+                    const int sw = u ^ ((EPI_CHUNKS16 == 8) ? (row & 7) : (EPI_CHUNKS16 == 4 ? ((row >> 1) & 3) : ((row >> 2) & 1)));
+                    float o8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) o8[j] = v[u * 8 + j];
+                    *reinterpret_cast<uint4*>(obuf + row * EPI_ROW_BYTES + sw * 16) = Pack8<T>::pack(o8);
+                }
+                if (cc == NCHUNK - 1)
+                {
+                    // every TMEM read of this accumulator stage is complete: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+                }
+                fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
+                epi_bar_sync();
+                if (leader)
+                {
+                    int c0, c1, c2;
+                    chunk_coords(g, c0, c1, c2);
+                    tma_store_3d(&tmap_out, smem_u32(obuf), c0, c1, c2);
+                    tma_store_commit();
+                    // the residual buffer of this chunk is consumed: prefetch the one two chunks ahead into it
+                    if (has_res && g + 2 < total_chunks) issue_residual(g + 2);
+                }
             }
-            // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (leader) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -503,8 +697,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 } // namespace tc
 
 // ---------------------------------------------------------------- host side
-// Packed weights + geometry for one layer; tensor maps for A are encoded per forward call (they bake
-// the activation pointer and the input shape), the weight map once.
+// Packed weights + geometry for one layer; tensor maps for A / out / residual are encoded per forward call (they bake
+// pointers and shapes), the weight maps once.
 struct TcPlan
 {
     int elemtype;
@@ -512,16 +706,26 @@ struct TcPlan
     int cblocks, taps, num_k_blocks;
     int Kp;            // packed K length (elements)
     int outch, outch_pad;
-    void* w_packed;    // device, [outch_pad][Kp] 16-bit
+    void* w_packed;    // device, [outch][Kp] 16-bit
     float* bias_pad;   // device, [outch_pad + 256] fp32 (zeros when no bias)
     CUtensorMap tmap_b;
+    // A_ROWS variant (small-channel stems), valid when rows_ok
+    int rows_ok;
+    int rows_cp, rows_wp, rows_shift; // channels per pixel of the padded copy, window width in pixels, zero taps on the left
+    int rows_block_k, rows_cblocks;
+    int rows_Kp;
+    void* w_rows;      // device, [outch][kh * wp * cp]
+    CUtensorMap tmap_b_rows;
 };
 
 int tc_available(); // 1 when the driver exposes cuTensorMapEncode* and the device is sm_100
 int tc_pick_block_k(int inch);
 int tc_pick_block_n(int outch);
-// weights_k_major: fp32 host [outch][taps][inch] (already permuted by the caller to tap-major, channel-innermost)
-int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int taps, const float* weights_tap_major, const float* bias, cudaStream_t stream);
+struct ncnn_cuda_conv2d_desc_fwd; // (documentation only)
+// weights_tap_major: fp32 host [outch][taps][inch] (already permuted by the caller to tap-major, channel-innermost)
+// kernel/stride/pad describe the layer for the A_ROWS variant (pad_left < 0: unknown until forward -> no A_ROWS)
+int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int kernel_w, int kernel_h, int stride_w, int dil_w, int pad_left,
+                   const float* weights_tap_major, const float* bias, cudaStream_t stream);
 void tc_plan_destroy(TcPlan* plan);
 
 struct TcConvCall
@@ -537,10 +741,14 @@ struct TcConvCall
     int act_type;
     float act_p0, act_p1;
     int tiled; // 1: A is a plain [M][inch] matrix (1x1 s1 p0 / linear)
+    void* workspace;
+    size_t workspace_size;
 };
 
-// returns 0 ok, -1 if the geometry cannot be expressed as a TMA im2col descriptor (caller falls back)
+// returns 0 ok, -1 if the geometry cannot be expressed as a TMA descriptor (caller falls back)
 int tc_conv_forward(const TcPlan* plan, const TcConvCall* call, cudaStream_t stream);
 int tc_conv_supported(const TcPlan* plan, const TcConvCall* call);
+// bytes of scratch the A_ROWS variant needs for this call (0 when it does not apply)
+size_t tc_conv_workspace(const TcPlan* plan, const TcConvCall* call);
 
 } // namespace ncnn_cuda

@@ -184,7 +184,16 @@ int Convolution::forward_impl(const CudaMat& bottom_blob, const CudaMat* residua
         act.p0 = act.p1 = 0.f;
         actp = &act;
     }
-    return ncnn_cuda_conv2d_forward(handle, &b, &t, pads[0], pads[2], residual ? &r : 0, actp, 0, 0, cmd.stream());
+    // scratch for the stem variant (zero-padded small-channel copy of the input); returned to the pool right after the
+    // launch is enqueued -- reuse is ordered by the stream
+    CudaMat workspace;
+    size_t wsize = residual ? 0 : ncnn_cuda_conv2d_workspace_size(handle, &b, &t);
+    if (wsize > 0)
+    {
+        workspace.create((int)((wsize + 3) / 4), NCNN_CUDA_F32, 1, cmd.workspace_allocator(opt));
+        if (workspace.empty()) wsize = 0;
+    }
+    return ncnn_cuda_conv2d_forward(handle, &b, &t, pads[0], pads[2], residual ? &r : 0, actp, workspace.data, wsize, cmd.stream());
 }
 
 int Convolution::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const

@@ -86,6 +86,7 @@ def lib():
         L.ncnn_cuda_last_error.restype = C.c_char_p
         L.ncnn_cuda_launch_count.restype = C.c_ulonglong
         L.ncnn_cuda_conv2d_workspace_size.restype = C.c_size_t
+        L.ncnn_cuda_conv2d_workspace_size.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

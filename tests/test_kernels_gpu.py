@@ -62,7 +62,7 @@ def act_of(t):
 
 
 # ------------------------------------------------------------------------------------------ Convolution
-def run_conv(ref, rng, elemtype, n, w, h, inch, outch, k, d, s, pad, bias, act_type, pad_value=0.0, kh=None, residual=False, expect_algo=None):
+def run_conv(ref, rng, elemtype, n, w, h, inch, outch, k, d, s, pad, bias, act_type, pad_value=0.0, kh=None, residual=False, expect_algo=None, expect_workspace=None):
     L = cabi.lib()
     kw = k
     kh = kh or k
@@ -103,8 +103,14 @@ def run_conv(ref, rng, elemtype, n, w, h, inch, outch, k, d, s, pad, bias, act_t
         rd = resb.desc()
     if expect_algo is not None:
         assert L.ncnn_cuda_conv2d_algo(handle, C.byref(bd)) == expect_algo
-    cabi.check(L.ncnn_cuda_conv2d_forward(handle, C.byref(bd), C.byref(td), pads[0], pads[2], C.byref(rd) if rd else None, None, None, C.c_size_t(0), None),
-               "conv2d_forward")
+    # scratch for the small-channel stem variant (A_ROWS); 0 for every other geometry
+    import torch
+    wsize = 0 if residual else int(L.ncnn_cuda_conv2d_workspace_size(handle, C.byref(bd), C.byref(td)))
+    if expect_workspace is not None:
+        assert (wsize > 0) == expect_workspace, "workspace %d" % wsize
+    ws = torch.full(((wsize + 3) // 4,), float("nan"), dtype=torch.float32, device="cuda") if wsize else None
+    cabi.check(L.ncnn_cuda_conv2d_forward(handle, C.byref(bd), C.byref(td), pads[0], pads[2], C.byref(rd) if rd else None, None,
+                                          C.c_void_p(ws.data_ptr()) if wsize else None, C.c_size_t(wsize), None), "conv2d_forward")
     sync()
     got = top.numpy()
     L.ncnn_cuda_conv2d_destroy(handle)
@@ -151,6 +157,32 @@ def test_convolution_tensor_core_shapes(ref, elemtype):
     ]
     for (w, h, ci, co, k, s, pad, n) in cases:
         run_conv(ref, rng, elemtype, n, w, h, ci, co, k, 1, s, pad, True, 1, expect_algo=2)
+
+
+@pytest.mark.parametrize("elemtype", [BF16, F16])
+def test_convolution_small_channel_stems(ref, elemtype):
+    """cin <= 8 first layers run the A_ROWS variant (zero-padded 4/8-channel copy + overlapping-window TMA): the five
+    models' stems, odd sizes, rows wider than one 128-column chunk, and the cases that must NOT take it"""
+    rng = np.random.default_rng(5)
+    cases = [
+        # w, h, cin, cout, k, s, pad, n, takes A_ROWS
+        (64, 64, 3, 64, 7, 2, 3, 2, True),       # resnet50 conv1
+        (225, 57, 3, 64, 7, 2, 3, 1, True),      # odd width, outw = 113
+        (33, 31, 3, 32, 3, 2, 1, 3, True),       # mobilenet_v2 / yolov8 stem, odd sizes
+        (640, 24, 3, 32, 3, 2, 1, 1, True),      # yolov8 stem width: outw = 320 -> 3 column chunks
+        (67, 35, 3, 64, 3, 2, 0, 2, True),       # squeezenet conv1 (no padding)
+        (48, 20, 3, 64, 3, 1, 1, 2, True),       # vgg16 conv1_1: stride 1 -> 8-channel pixels
+        (300, 9, 3, 64, 3, 1, 1, 1, True),       # stride 1, outw = 300
+        (40, 40, 1, 16, 5, 2, 2, 2, True),
+        (40, 40, 4, 24, 3, 2, 1, 2, True),
+        (30, 30, 8, 24, 3, 1, 1, 2, True),       # cin = 8
+        (30, 30, 3, 24, 3, 2, -233, 2, True),    # SAME padding, resolved by the caller before create (odd left pad -> shift)
+        (30, 30, 12, 24, 3, 2, 1, 2, False),
+    ]
+    for (w, h, ci, co, k, s, pad, n, rows) in cases:
+        run_conv(ref, rng, elemtype, n, w, h, ci, co, k, 1, s, pad, True, 1, expect_algo=2, expect_workspace=rows)
+    run_conv(ref, rng, elemtype, 2, 41, 37, 3, 48, 7, 1, 2, 3, True, 0, kh=3, expect_workspace=True)
+    run_conv(ref, rng, elemtype, 2, 41, 37, 3, 48, 3, 1, 2, 1, True, 2, kh=5, expect_workspace=True)
 
 
 def test_convolution_pad_value_and_kernel_wh(ref):
