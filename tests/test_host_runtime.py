@@ -1,0 +1,147 @@
+"""Host-side logic of the product library checked against the reference's own host code through the SAME C API
+(src/c_api.h) -- runs without a GPU.  Both libraries are driven by one ctypes binding (ncnn_b200/capi.py), so every
+assertion is "product == reference" on identical calls:
+
+  * Mat allocation layout: cstep 16-byte alignment, nstep 4 KiB alignment, elemsize/elempack, batch views
+    (src/mat.h:50-382, src/mat.cpp:299-861, tests/test_mat_batch.cpp)
+  * Layer capability flags the executor reads (src/layer.h:46-90) for every hot-path layer type
+  * Net::load_param on the five benchmark graphs: input/output blob names and counts (src/net.cpp:1255-1560)
+  * ParamDict set/get round trip (src/paramdict.cpp)
+  * the .bin byte stream the seeded weight generator writes is consumed to the last byte by the reference's
+    load_model -- i.e. tools/modelzoo.py's understanding of ModelBin (src/modelbin.cpp:75-151) matches the reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from netutil import modelzoo
+
+HOT_PATH_LAYERS = ["Convolution", "ConvolutionDepthWise", "Pooling", "InnerProduct", "Gemm", "ReLU", "Eltwise", "BinaryOp", "Concat", "Split", "Softmax",
+                   "Interp", "Swish", "Sigmoid", "Slice", "Reshape", "Permute", "Flatten", "Dropout", "Input", "Padding"]
+
+
+@pytest.fixture(scope="module")
+def ours():
+    from ncnn_b200 import capi
+    return capi.library()
+
+
+SHAPES = [(1,), (7,), (1000,), (4097,), (5, 3), (224, 224), (227, 227, 3), (13, 13, 1000), (7, 7, 2048), (1, 1, 5), (3, 5, 7, 2), (20, 20, 2, 64)]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 5])
+def test_mat_layout_matches_reference(ours, ref, n):
+    for shp in SHAPES:
+        mats = []
+        for api in (ours, ref):
+            L = api.lib
+            if n == 0:
+                f = getattr(L, "ncnn_mat_create_%dd" % len(shp))
+                m = f(*shp, None)
+            else:
+                f = getattr(L, "ncnn_mat_create_%dd_batch" % len(shp))
+                m = f(*shp, n, None)
+            mats.append((api, m))
+        desc = []
+        for api, m in mats:
+            L = api.lib
+            desc.append(tuple(int(getattr(L, "ncnn_mat_get_" + k)(m)) for k in ("dims", "w", "h", "d", "c", "n", "elemsize", "elempack", "cstep", "nstep")))
+            assert L.ncnn_mat_get_data(m) % 16 == 0
+            L.ncnn_mat_destroy(m)
+        assert desc[0] == desc[1], (shp, n, desc)
+        cstep, nstep = desc[0][8], desc[0][9]
+        if len(shp) >= 3:
+            assert (cstep * 4) % 16 == 0
+        if n > 1:
+            assert (nstep * 4) % 4096 == 0  # src/mat.cpp batch stride alignment
+
+
+def test_mat_batch_roundtrip(ours):
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 4, 5, 6)).astype(np.float32)
+    m = ours.mat_from_numpy(a, batched=True)
+    assert ours.lib.ncnn_mat_get_n(m) == 3 and ours.lib.ncnn_mat_get_c(m) == 4
+    assert np.array_equal(ours.mat_to_numpy(m, force_batch=True), a)
+    ours.lib.ncnn_mat_destroy(m)
+
+
+def test_layer_flags_match_reference(ours, ref):
+    for t in HOT_PATH_LAYERS:
+        flags = []
+        for api in (ours, ref):
+            ly = api.lib.ncnn_layer_create_by_type(t.encode())
+            assert ly, (api.path, t)
+            flags.append((api.lib.ncnn_layer_get_one_blob_only(ly), api.lib.ncnn_layer_get_support_inplace(ly)))
+            api.lib.ncnn_layer_destroy(ly)
+        assert flags[0] == flags[1], (t, flags)
+
+
+def test_unknown_layer_type_is_null(ours):
+    assert not ours.lib.ncnn_layer_create_by_type(b"NoSuchLayer")
+
+
+@pytest.mark.parametrize("name", ["squeezenet_v1_1", "mobilenet_v2", "resnet50", "vgg16", "yolov8s"])
+def test_load_param_matches_reference(ours, ref, name):
+    text = modelzoo.param_text(name)
+    seen = []
+    for api in (ours, ref):
+        L = api.lib
+        net = L.ncnn_net_create()
+        assert L.ncnn_net_load_param_memory(net, text.encode()) == 0
+        ins = [L.ncnn_net_get_input_name(net, i) for i in range(L.ncnn_net_get_input_count(net))]
+        outs = [L.ncnn_net_get_output_name(net, i) for i in range(L.ncnn_net_get_output_count(net))]
+        seen.append((ins, outs))
+        L.ncnn_net_destroy(net)
+    assert seen[0] == seen[1] and seen[0][0] and seen[0][1]
+
+
+def test_load_param_rejects_garbage(ours):
+    L = ours.lib
+    for bad in (b"", b"1234\n1 1\n", b"7767517\n2 2\nInput data 0 1 data\n"):
+        net = L.ncnn_net_create()
+        assert L.ncnn_net_load_param_memory(net, bad) != 0
+        L.ncnn_net_destroy(net)
+
+
+def test_paramdict_roundtrip(ours, ref):
+    for api in (ours, ref):
+        L = api.lib
+        L.ncnn_paramdict_get_int.restype = C.c_int
+        L.ncnn_paramdict_get_int.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ncnn_paramdict_get_float.restype = C.c_float
+        L.ncnn_paramdict_get_float.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.ncnn_paramdict_get_type.restype = C.c_int
+        L.ncnn_paramdict_get_type.argtypes = [C.c_void_p, C.c_int]
+        pd = api.make_paramdict({0: 64, 1: 3, 9: 2, 18: 0.25, 10: [0.1, 0.2]})
+        assert L.ncnn_paramdict_get_int(pd, 0, -1) == 64
+        assert L.ncnn_paramdict_get_int(pd, 5, -7) == -7  # default for an absent id
+        assert abs(L.ncnn_paramdict_get_float(pd, 18, 0.0) - 0.25) < 1e-7
+        assert L.ncnn_paramdict_get_type(pd, 31) == 0
+        L.ncnn_paramdict_destroy(pd)
+
+
+@pytest.mark.parametrize("name", ["squeezenet_v1_1", "mobilenet_v2", "yolov8s"])
+def test_seeded_weight_stream_is_consumed_exactly(ref, name):
+    """the reference reads the generated .bin to its last byte and not beyond"""
+    from ncnn_b200 import capi
+    text = modelzoo.param_text(name)
+    weights = modelzoo.random_model_bytes(text, seed=7)
+    L = ref.lib
+    opt = ref.strict_fp32_option()
+    net = L.ncnn_net_create()
+    L.ncnn_net_set_option(net, opt)
+    assert L.ncnn_net_load_param_memory(net, text.encode()) == 0
+    rd = capi.MemoryReader(ref, weights)
+    assert L.ncnn_net_load_model_datareader(net, rd.dr) == 0
+    assert rd.pos == len(weights), (rd.pos, len(weights))
+    rd.close()
+    L.ncnn_net_destroy(net)
+    # a truncated stream must be refused
+    net = L.ncnn_net_create()
+    L.ncnn_net_set_option(net, opt)
+    L.ncnn_net_load_param_memory(net, text.encode())
+    rd = capi.MemoryReader(ref, weights[:len(weights) // 2])
+    assert L.ncnn_net_load_model_datareader(net, rd.dr) != 0
+    rd.close()
+    L.ncnn_net_destroy(net)
+    L.ncnn_option_destroy(opt)
