@@ -178,12 +178,8 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
-    import torch  # plumbing only: process group for the barrier / max-over-ranks
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend="nccl")
+    from ncnn_b200 import replicas  # torch.distributed plumbing only: rendezvous, barrier, max-over-ranks
+    group = replicas.Group(backend="nccl" if world > 1 else None)
 
     from ncnn_b200 import runner
     text = with_input_size(modelzoo.param_text(model), size)
@@ -198,15 +194,9 @@ def main():
 
     def barrier():
         sess.sync()
-        if dist is not None:
-            dist.barrier()
+        group.barrier()
 
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = group.max
 
     # ---- device-resident throughput
     for _ in range(max(args.warmup, 3)):
@@ -229,7 +219,7 @@ def main():
     t_wall1 = time.time()
     launches = sess.launch_count() - launches0
     ms = max_over_ranks(ms)
-    value = batch * world * args.steps / (ms / 1000.0)
+    value = replicas.throughput(batch, args.steps, world, ms)
 
     # ---- end to end through the reference-facing call (host Mat in, host Mat out)
     for _ in range(3):
@@ -240,7 +230,7 @@ def main():
         lib.ncnn_mat_destroy(sess.extract_host(host_in))
     e2e_s = time.perf_counter() - t0
     e2e_s = max_over_ranks(e2e_s)
-    e2e_value = batch * world * args.steps / e2e_s
+    e2e_value = replicas.throughput(batch, args.steps, world, e2e_s * 1000.0)
     h2d, d2h = int(sess.last_h2d), int(sess.last_d2h)
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
     if rank == 0:
@@ -309,8 +299,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     sess.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    group.close()
     return 0
 
 

@@ -233,6 +233,10 @@ NCNN_C_API void ncnn_option_set_use_cuda_graph_fusion(ncnn_option_t opt, int ena
 NCNN_C_API int ncnn_get_cuda_device_count(void);
 NCNN_C_API void ncnn_net_set_cuda_device(ncnn_net_t net, int device_index);
 NCNN_C_API int ncnn_net_get_fused_layer_count(const ncnn_net_t net);
+/* zero-copy view of samples [b, b + batches) of a batched Mat (Mat::batch_range, src/mat.h:241-242): how a host batch
+ * is split across per-GPU replicas; the view does not own the data (refcount NULL, as in the reference): the parent
+ * must outlive it.  NULL when the range is out of bounds. */
+NCNN_C_API ncnn_mat_t ncnn_mat_batch_range(const ncnn_mat_t mat, int b, int batches);
 /* pinned host Mats: async H2D/D2H without a staging copy */
 NCNN_C_API ncnn_allocator_t ncnn_allocator_create_cuda_staging_allocator(void);
 /* device-resident tensors and the stream recorder */

@@ -276,6 +276,12 @@ void* ncnn_mat_get_batch_data(const ncnn_mat_t mat, int b)
     const Mat* m = (const Mat*)mat;
     return (unsigned char*)m->data + m->nstep * b * m->elemsize;
 }
+ncnn_mat_t ncnn_mat_batch_range(const ncnn_mat_t mat, int b, int batches)
+{
+    const Mat* m = (const Mat*)mat;
+    if (!m || b < 0 || batches <= 0 || b + batches > (m->n > 0 ? m->n : 1)) return 0;
+    return (ncnn_mat_t)(new Mat(m->batch_range(b, batches)));
+}
 void* ncnn_mat_get_channel_data(const ncnn_mat_t mat, int c)
 {
     const Mat* m = (const Mat*)mat;
