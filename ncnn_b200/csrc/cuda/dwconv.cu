@@ -6,6 +6,7 @@
 // reuse comes from L1/L2 (a CTA covers whole output rows).  Accumulation is fp32 in the reference's tap order.
 // Grouped branch (:216-267): plain CUDA-core kernel (not on the named models' path).
 #include "common.cuh"
+#include "dwconv_tma.cuh"
 
 #include <string.h>
 #include <vector>
@@ -180,6 +181,35 @@ static int run_depthwise(const ncnn_cuda_dwconv2d* conv, const ncnn_cuda_tensor*
                         && (((g.C + VEC - 1) / VEC) * VEC <= g.in_cpitch) && (((g.C + VEC - 1) / VEC) * VEC <= g.out_cpitch);
     const T* in = (const T*)bottom->data;
     T* out = (T*)top->data;
+    if (g.kw == 3 && g.kh == 3 && g.dw == 1 && g.dh == 1 && g.sw == g.sh && g.pad_value == 0.f && g.n > 0)
+    {
+        // the bandwidth path: TMA-staged halo tiles (dwconv_tma.cuh); anything it declines runs on the generic kernel below
+        dwt::Call c;
+        c.in = in;
+        c.out = out;
+        c.elemtype = bottom->elemtype;
+        c.C = g.C;
+        c.inw = g.inw;
+        c.inh = g.inh;
+        c.outw = g.outw;
+        c.outh = g.outh;
+        c.n = g.n;
+        c.stride = g.sw;
+        c.pad_left = g.pad_left;
+        c.pad_top = g.pad_top;
+        c.in_cpitch = g.in_cpitch;
+        c.out_cpitch = g.out_cpitch;
+        c.in_nstep = g.in_nstep;
+        c.out_nstep = g.out_nstep;
+        c.w = conv->w_dev;
+        c.bias = conv->bias_dev;
+        c.cpad = g.cpad;
+        c.act_type = g.act_type;
+        c.act_p0 = g.act_p0;
+        c.act_p1 = g.act_p1;
+        int r = dwt::forward<T>(c, stream);
+        if (r <= 0) return r;
+    }
     if (vec_ok)
     {
         const int CV = (g.C + VEC - 1) / VEC;

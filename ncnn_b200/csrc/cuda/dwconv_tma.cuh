@@ -1,0 +1,414 @@
+// dwconv_tma.cuh -- the bandwidth path of ConvolutionDepthWise (src/layer/convolutiondepthwise.cpp:181-214 of the
+// reference): 3x3 depthwise, stride 1 or 2, dilation 1, zero padding, on channel-innermost blobs.
+//
+// One persistent CTA per SM walks (channel block, image, tile) work items.  A producer warp keeps a kStages-deep ring of
+// input tiles (tile + 1-pixel halo) in shared memory with 4-D tiled TMA loads -- the halo outside the image is the TMA
+// unit's out-of-bounds zero fill, so there is no padded copy (reference: copy_make_border in
+// ConvolutionDepthWise::make_padding) and no per-tap bounds test.  256 consumer threads each own one output column of
+// the tile for a 16-byte channel vector and R consecutive output rows: every input row is read from shared memory once
+// (3 x LDS.128) and feeds up to three output rows from registers; the 9 x VEC filter taps live in registers and are
+// reloaded only when the CTA moves to another channel block.  fp32 accumulation with packed FFMA2, in the reference's
+// tap order (ky major), bias first.  Outputs leave as 16-byte vector stores (a warp writes whole pixels' channel runs).
+//
+// HBM traffic is the algorithmic minimum (input once, output once); the halo re-reads (<= 1.4x of the input) are L2 hits.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace ncnn_cuda {
+namespace dwt {
+
+constexpr int kConsumers = 256;
+constexpr int kThreads = kConsumers + 32;
+
+struct Params
+{
+    int C, outw, outh, n;
+    int tiles_x, tiles_y;
+    int n_spatial; // n * tiles_y * tiles_x
+    int num_tiles; // cblocks * n_spatial
+    int pad_left, pad_top;
+    int out_cpitch;
+    long long out_nstep;
+    const float* w;    // [9][cpad]
+    const float* bias; // [C] or NULL
+    int cpad;
+    int act_type;
+    float act_p0, act_p1;
+};
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+// 16 bytes of T in shared memory -> VEC/2 float2
+template<typename T>
+struct Vec16;
+template<>
+struct Vec16<__half>
+{
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ void load(const void* p, float2 (&v)[4])
+    {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = __half22float2(h[i]);
+    }
+    static __device__ __forceinline__ void store(void* p, const float2 (&v)[4])
+    {
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[i].x, v[i].y);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+template<>
+struct Vec16<__nv_bfloat16>
+{
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ void load(const void* p, float2 (&v)[4])
+    {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            // bf16 -> fp32 is a 16-bit shift: integer pipe, not the FMA pipe
+            v[i].x = __uint_as_float(w[i] << 16);
+            v[i].y = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(void* p, const float2 (&v)[4])
+    {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[i].x, v[i].y);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+template<>
+struct Vec16<float>
+{
+    static constexpr int VEC = 4;
+    static __device__ __forceinline__ void load(const void* p, float2 (&v)[2])
+    {
+        const float4 u = *reinterpret_cast<const float4*>(p);
+        v[0] = make_float2(u.x, u.y);
+        v[1] = make_float2(u.z, u.w);
+    }
+    static __device__ __forceinline__ void store(void* p, const float2 (&v)[2])
+    {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    }
+};
+
+// S stride; CV 16-byte channel vectors per tile; TW output columns per tile (one thread each); TY thread rows; R output rows per thread
+template<typename T, int S, int CV, int TW, int TY, int R>
+struct Cfg
+{
+    static constexpr int VEC = Vec16<T>::VEC;
+    static constexpr int CB = CV * VEC; // channels per tile
+    static constexpr int TH = TY * R;   // output rows per tile
+    static constexpr int IW = (TW - 1) * S + 3;
+    static constexpr int IH = (TH - 1) * S + 3;
+    static constexpr int tile_bytes = IW * IH * CV * 16;
+    static constexpr int stage_bytes = (tile_bytes + 127) / 128 * 128;
+    static constexpr int stages_fit = (176 * 1024) / stage_bytes;
+    static constexpr int kStages = stages_fit > 4 ? 4 : stages_fit;
+    static constexpr int smem_bytes = kStages * stage_bytes + 128 /*alignment*/ + 128 /*barriers*/;
+    static_assert(CV * TW * TY == kConsumers, "one consumer thread per (channel vector, column, thread row)");
+    static_assert(kStages >= 2, "tile too large for a 2-stage ring");
+};
+
+template<typename T, int S, int CV, int TW, int TY, int R>
+__global__ void __launch_bounds__(kThreads, 1) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, T* __restrict__ out, const Params p)
+{
+    using C = Cfg<T, S, CV, TW, TY, R>;
+    constexpr int VEC = C::VEC;
+    constexpr int H2 = VEC / 2; // float2 per channel vector
+    constexpr int kStages = C::kStages;
+    constexpr int NROWS = (R - 1) * S + 3; // input rows a thread walks
+
+    extern __shared__ uint8_t dw_smem_raw[];
+    // (pointer arithmetic, not an integer round trip: keeps the shared address space visible to the compiler -> LDS, not generic LD)
+    uint8_t* smem = dw_smem_raw + ((128u - (tc::smem_u32(dw_smem_raw) & 127u)) & 127u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::stage_bytes);
+    uint64_t* empty_bar = full_bar + kStages;
+
+    const int tid = threadIdx.x;
+    if (tid == 0)
+    {
+        tc::prefetch_tmap(&tmap_in);
+        for (int i = 0; i < kStages; i++)
+        {
+            tc::mbar_init(tc::smem_u32(&full_bar[i]), 1);
+            tc::mbar_init(tc::smem_u32(&empty_bar[i]), kConsumers / 32);
+        }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int tiles_per_image = p.tiles_x * p.tiles_y;
+
+    if (tid >= kConsumers)
+    {
+        // ===================== TMA producer (one lane) =====================
+        if (tid == kConsumers)
+        {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            {
+                const int cb = tile / p.n_spatial;
+                const int sp = tile - cb * p.n_spatial;
+                const int b = sp / tiles_per_image;
+                const int t2 = sp - b * tiles_per_image;
+                const int tyi = t2 / p.tiles_x;
+                const int txi = t2 - tyi * p.tiles_x;
+                tc::mbar_wait(tc::smem_u32(&empty_bar[stage]), phase ^ 1);
+                const uint32_t fb = tc::smem_u32(&full_bar[stage]);
+                tc::mbar_expect_tx(fb, C::tile_bytes);
+                tc::tma_load_4d(tc::smem_u32(smem + stage * C::stage_bytes), &tmap_in, fb, cb * C::CB, txi * TW * S - p.pad_left, tyi * C::TH * S - p.pad_top, b);
+                if (++stage == kStages)
+                {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int cv = tid % CV;
+    const int tx = (tid / CV) % TW;
+    const int ty = tid / (CV * TW);
+    const int lane = tid & 31;
+
+    float2 w[9][H2];
+    float2 bias2[H2];
+    int cur_cb = -1;
+    int stage = 0;
+    uint32_t phase = 0;
+    // byte offset of this thread's first input pixel inside a staged tile
+    const int thread_off = ((ty * R * S) * C::IW + tx * S) * (CV * 16) + cv * 16;
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+    {
+        const int cb = tile / p.n_spatial;
+        const int sp = tile - cb * p.n_spatial;
+        const int b = sp / tiles_per_image;
+        const int t2 = sp - b * tiles_per_image;
+        const int tyi = t2 / p.tiles_x;
+        const int txi = t2 - tyi * p.tiles_x;
+        const int c0 = cb * C::CB + cv * VEC;
+        if (cb != cur_cb)
+        {
+            cur_cb = cb;
+#pragma unroll
+            for (int t = 0; t < 9; t++)
+            {
+                const float* wp = p.w + (long long)t * p.cpad + c0;
+#pragma unroll
+                for (int i = 0; i < H2; i++) w[t][i] = *reinterpret_cast<const float2*>(wp + 2 * i);
+            }
+#pragma unroll
+            for (int i = 0; i < H2; i++) bias2[i] = p.bias ? *reinterpret_cast<const float2*>(p.bias + c0 + 2 * i) : make_float2(0.f, 0.f);
+        }
+
+        float2 acc[R][H2];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int i = 0; i < H2; i++) acc[r][i] = bias2[i];
+
+        tc::mbar_wait(tc::smem_u32(&full_bar[stage]), phase);
+        const uint8_t* base = smem + stage * C::stage_bytes + thread_off;
+#pragma unroll
+        for (int ii = 0; ii < NROWS; ii++)
+        {
+            float2 x[3][H2];
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) Vec16<T>::load(base + (ii * C::IW + kx) * (CV * 16), x[kx]);
+#pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                const int ky = ii - r * S;
+                if (ky >= 0 && ky < 3)
+                {
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+                        for (int i = 0; i < H2; i++) acc[r][i] = ffma2(x[kx][i], w[ky * 3 + kx][i], acc[r][i]);
+                }
+            }
+        }
+        // this warp is done with the staged tile: hand the slot back before the global stores
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty_bar[stage]));
+        if (++stage == kStages)
+        {
+            stage = 0;
+            phase ^= 1;
+        }
+
+        const int ox = txi * TW + tx;
+        const int oy0 = tyi * C::TH + ty * R;
+        if (ox < p.outw)
+        {
+            T* op = out + (long long)b * p.out_nstep + ((long long)oy0 * p.outw + ox) * p.out_cpitch + c0;
+            const int act = p.act_type;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+            {
+                if (oy0 + r < p.outh)
+                {
+                    float2 v[H2];
+#pragma unroll
+                    for (int i = 0; i < H2; i++) v[i] = acc[r][i];
+                    if (act == 1)
+                    {
+#pragma unroll
+                        for (int i = 0; i < H2; i++) v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+                    }
+                    else if (act == 3)
+                    {
+#pragma unroll
+                        for (int i = 0; i < H2; i++) v[i] = make_float2(fminf(fmaxf(v[i].x, p.act_p0), p.act_p1), fminf(fmaxf(v[i].y, p.act_p0), p.act_p1));
+                    }
+                    else if (act != 0)
+                    {
+#pragma unroll
+                        for (int i = 0; i < H2; i++)
+                            v[i] = make_float2(apply_activation(v[i].x, act, p.act_p0, p.act_p1), apply_activation(v[i].y, act, p.act_p0, p.act_p1));
+                    }
+                    Vec16<T>::store(op + (long long)r * p.outw * p.out_cpitch, v);
+                }
+            }
+        }
+    }
+}
+
+template<typename T, int S, int CV, int TW, int TY, int R>
+static int launch_dw_tma(const CUtensorMap& tm, T* out, Params& p, cudaStream_t stream)
+{
+    using C = Cfg<T, S, CV, TW, TY, R>;
+    auto kern = dwconv3x3_tma_kernel<T, S, CV, TW, TY, R>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+        attr_set = true;
+    }
+    p.tiles_x = (p.outw + TW - 1) / TW;
+    p.tiles_y = (p.outh + C::TH - 1) / C::TH;
+    const long long n_spatial = (long long)p.n * p.tiles_x * p.tiles_y;
+    const long long num_tiles = n_spatial * (p.C / C::CB);
+    if (num_tiles > 0x7fffffffLL) return 1; // caller falls back
+    p.n_spatial = (int)n_spatial;
+    p.num_tiles = (int)num_tiles;
+    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    kern<<<grid, kThreads, C::smem_bytes, stream>>>(tm, out, p);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+// box dims of the staged input tile for a configuration
+template<typename T, int S, int CV, int TW, int TY, int R>
+static void box_of(unsigned int (&box)[4])
+{
+    using C = Cfg<T, S, CV, TW, TY, R>;
+    box[0] = C::CB;
+    box[1] = C::IW;
+    box[2] = C::IH;
+    box[3] = 1;
+}
+
+struct Call
+{
+    const void* in;
+    void* out;
+    int elemtype;
+    int C, inw, inh, outw, outh, n;
+    int stride;
+    int pad_left, pad_top;
+    int in_cpitch, out_cpitch;
+    long long in_nstep, out_nstep;
+    const float* w;
+    const float* bias;
+    int cpad;
+    int act_type;
+    float act_p0, act_p1;
+};
+
+// 0 launched, 1 not applicable (caller uses the generic kernel), < 0 error
+template<typename T>
+static int forward(const Call& c, cudaStream_t stream)
+{
+    constexpr int VEC = Vec16<T>::VEC;
+    const int es = (int)sizeof(T);
+    if (!tc_available()) return 1;
+    if (c.stride != 1 && c.stride != 2) return 1;
+    if (c.C % (2 * VEC) != 0) return 1;
+    if (((size_t)c.in_cpitch * es) % 16 || ((size_t)c.in_nstep * es) % 16 || ((uintptr_t)c.in & 15)) return 1;
+    if (((size_t)c.out_cpitch * es) % 16 || ((size_t)c.out_nstep * es) % 16 || ((uintptr_t)c.out & 15)) return 1;
+    if (c.pad_left < 0 || c.pad_top < 0 || c.pad_left > 64 || c.pad_top > 64) return 1;
+    const int cv = (c.C % (8 * VEC) == 0) ? 8 : ((c.C % (4 * VEC) == 0) ? 4 : 2);
+    const bool small = c.outw <= 8;
+
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.C = c.C;
+    p.outw = c.outw;
+    p.outh = c.outh;
+    p.n = c.n;
+    p.pad_left = c.pad_left;
+    p.pad_top = c.pad_top;
+    p.out_cpitch = c.out_cpitch;
+    p.out_nstep = c.out_nstep;
+    p.w = c.w;
+    p.bias = c.bias;
+    p.cpad = c.cpad;
+    p.act_type = c.act_type;
+    p.act_p0 = c.act_p0;
+    p.act_p1 = c.act_p1;
+
+    unsigned int box[4];
+    unsigned long long gdim[4] = {(unsigned long long)c.C, (unsigned long long)c.inw, (unsigned long long)c.inh, (unsigned long long)c.n};
+    unsigned long long gstride[3] = {(unsigned long long)c.in_cpitch * es, (unsigned long long)c.in_cpitch * es * c.inw, (unsigned long long)c.in_nstep * es};
+    CUtensorMap tm;
+
+#define NC_DW(S_, CV_, TW_, TY_, R_)                                                            \
+    do                                                                                          \
+    {                                                                                           \
+        box_of<T, S_, CV_, TW_, TY_, R_>(box);                                                  \
+        if (tma_encode_tiled_plain(&tm, c.elemtype, 4, c.in, gdim, gstride, box) != 0) return 1; \
+        return launch_dw_tma<T, S_, CV_, TW_, TY_, R_>(tm, (T*)c.out, p, stream);               \
+    } while (0)
+
+    if (c.stride == 1)
+    {
+        if (small && cv == 8) NC_DW(1, 8, 8, 4, 2);
+        if (cv == 8) NC_DW(1, 8, 16, 2, 4);
+        if (cv == 4) NC_DW(1, 4, 16, 4, 4);
+        NC_DW(1, 2, 32, 4, 4);
+    }
+    else
+    {
+        if (small && cv == 8) NC_DW(2, 8, 8, 4, 2);
+        if (cv == 8) NC_DW(2, 8, 16, 2, 2);
+        if (cv == 4) NC_DW(2, 4, 16, 4, 2);
+        NC_DW(2, 2, 32, 4, 2);
+    }
+#undef NC_DW
+    return 1;
+}
+
+} // namespace dwt
+} // namespace ncnn_cuda

@@ -89,6 +89,25 @@ static CUtensorMapDataType dtype_for(int elemtype)
     return elemtype == NCNN_CUDA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
+int tma_encode_tiled_plain(CUtensorMap* map, int elemtype, int rank, const void* ptr, const unsigned long long* gdim, const unsigned long long* gstride_bytes,
+                           const unsigned int* box)
+{
+    if (!tc_available() || rank < 1 || rank > 5) return -1;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++)
+    {
+        gd[i] = gdim[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i < rank - 1) gs[i] = gstride_bytes[i];
+    }
+    CUtensorMapDataType dt = elemtype == NCNN_CUDA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype_for(elemtype);
+    CUresult r = g_encodeTiled(map, dt, (cuuint32_t)rank, (void*)ptr, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 static int encode_weights(CUtensorMap* map, int elemtype, void* w, int Kp, int outch, int block_k, int block_n)
 {
     cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)outch};
@@ -286,30 +305,31 @@ int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
 }
 
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const tc::Params& p, long long tiles,
-                     cudaStream_t stream)
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles, cudaStream_t stream)
 {
     using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K>;
-    static_assert(Plan::kStages >= 2, "not enough shared memory for a 2-stage pipeline");
+    static_assert(Plan::stages_for(true) >= 2, "not enough shared memory for a 2-stage pipeline");
     auto kern = tc::tc_gemm_kernel<T, BLOCK_N, BLOCK_K, AMODE>;
     static bool attr_set = false;
     if (!attr_set)
     {
-        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::total));
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::total_for(false)));
         attr_set = true;
     }
+    const bool has_res = p.residual != 0;
+    p.num_stages = Plan::stages_for(has_res);
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, tc::kNumThreads, Plan::total, stream>>>(ta, tb, to, tr, p);
+    kern<<<grid, tc::kNumThreads, Plan::total_for(has_res), stream>>>(ta, tb, tr, p);
     NC_LAUNCH_CHECK();
     return 0;
 }
 
 template<typename T, int AMODE>
-static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const tc::Params& p,
-                       long long tiles, cudaStream_t stream)
+static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles,
+                       cudaStream_t stream)
 {
 #define NC_TC(BN, BK) \
-    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, to, tr, p, tiles, stream)
+    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, p, tiles, stream)
     NC_TC(256, 64);
     NC_TC(128, 64);
     NC_TC(64, 64);
@@ -342,7 +362,7 @@ static int encode_out(CUtensorMap* map, int elemtype, const void* ptr, int C, in
 int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream)
 {
     if (!tc_conv_supported(plan, c)) return -1;
-    CUtensorMap ta, to, tr;
+    CUtensorMap ta, tr;
     const long long M = (long long)c->n * c->outh * c->outw;
     if (M == 0) return 0;
     const int epi_n = plan->block_n < 64 ? plan->block_n : 64;
@@ -429,14 +449,9 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
         p.chunks_per_row = 1;
     }
 
-    // output / residual maps
+    // residual map (the output itself leaves through per-lane vector stores, no descriptor)
     const long long cols = amode == tc::A_ROWS ? c->outw : M;
     const long long rows = amode == tc::A_ROWS ? (long long)c->n * c->outh : 1;
-    if (encode_out(&to, plan->elemtype, c->out, plan->outch, c->out_cpitch, cols, rows, epi_n) != 0)
-    {
-        set_last_error_msg("cuTensorMapEncodeTiled(output) failed");
-        return -1;
-    }
     if (c->residual)
     {
         if (encode_out(&tr, plan->elemtype, c->residual, plan->outch, c->res_cpitch, cols, rows, epi_n) != 0)
@@ -446,7 +461,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
         }
     }
     else
-        tr = to;
+        tr = ta;
 
     p.M = M;
     p.N = plan->outch;
@@ -467,14 +482,15 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     p.act_type = c->act_type;
     p.act_p0 = c->act_p0;
     p.act_p1 = c->act_p1;
+    p.v8_ok = (c->out_cpitch % 16 == 0) && (((uintptr_t)c->out & 31) == 0);
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row : (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
     const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);
 
 #define NC_MODE(T)                                                                                                            \
-    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, to, tr, p, tiles, stream);  \
-    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, to, tr, p, tiles, stream); \
-    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, to, tr, p, tiles, stream)
+    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream);  \
+    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream); \
+    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream)
     if (plan->elemtype == NCNN_CUDA_BF16)
     {
         NC_MODE(__nv_bfloat16);

@@ -40,13 +40,15 @@ struct Params
     // A_ROWS geometry: chunks of 128 output columns per output row; rows = n * outh
     int chunks_per_row;
     // epilogue
-    const float* bias; // padded to a multiple of BLOCK_N, never NULL
+    const float* bias; // padded to a multiple of BLOCK_N (+256), never NULL
     void* out;
     int out_cpitch;
     const void* residual; // same type/shape as out, or NULL
     int res_cpitch;
     int act_type;
     float act_p0, act_p1;
+    int num_stages; // depth of the A/B ring (SmemPlan::stages_for(residual != NULL))
+    int v8_ok;      // output rows are 32-byte aligned: 256-bit stores
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -234,6 +236,31 @@ __device__ __forceinline__ void tmem_wait_ld()
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// tcgen05.wait::ld that also names the 32 destination registers of the load it completes as in/out operands, so that no
+// use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld_pin(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                   "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// one lane writes 32 contiguous bytes = one full DRAM/L2 sector
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* o)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]),
+                 "r"(o[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_global_v4(void* ptr, const uint32_t* o)
+{
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+}
+
 // K-major operand tile in smem, rows of BLOCK_K 16-bit elements = SWIZZLE bytes, 8-row groups SBO apart.
 // Bit layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout_type [61,64) (2 = 128B, 4 = 64B, 6 = 32B swizzle).
@@ -279,17 +306,22 @@ struct SmemPlan
     static constexpr int a_bytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int b_bytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int stage_bytes = a_bytes + b_bytes; // both multiples of 1024 for the tile sizes used
-    // epilogue staging: the accumulator tile leaves through shared memory in EPI_N-column chunks (TMA store), the
-    // fused residual arrives the same way (TMA load); two buffers each
+    // The accumulator tile leaves the SM straight from registers (one output pixel per lane, 32-byte vector stores), so
+    // the only epilogue staging is the fused residual: it arrives by TMA in EPI_N-column slots, a ring of kResSlots.
     static constexpr int EPI_N = BLOCK_N < 64 ? BLOCK_N : 64;
-    static constexpr int epi_chunk_bytes = BLOCK_M * EPI_N * 2;
-    static constexpr int epi_bytes = 4 * epi_chunk_bytes;
-    static constexpr int bias_bytes = 1024;
-    static constexpr int barrier_bytes = 256;
-    static constexpr int max_bytes = 225 * 1024 - epi_bytes - bias_bytes - barrier_bytes - 1024;
-    static constexpr int stages_raw = max_bytes / stage_bytes;
-    static constexpr int kStages = stages_raw > 8 ? 8 : stages_raw;
-    static constexpr int total = kStages * stage_bytes + epi_bytes + bias_bytes + barrier_bytes + 1024; // + alignment slack
+    static constexpr int kResSlots = 4;
+    static constexpr int res_slot_bytes = BLOCK_M * EPI_N * 2;
+    static constexpr int barrier_bytes = 512;
+    static constexpr int budget = 225 * 1024 - barrier_bytes - 1024; // - alignment slack
+    static constexpr int stages_for(bool has_res)
+    {
+        int s = (budget - (has_res ? kResSlots * res_slot_bytes : 0)) / stage_bytes;
+        return s > 8 ? 8 : s;
+    }
+    static constexpr int total_for(bool has_res)
+    {
+        return stages_for(has_res) * stage_bytes + (has_res ? kResSlots * res_slot_bytes : 0) + barrier_bytes + 1024;
+    }
 };
 
 template<typename T>
@@ -319,6 +351,11 @@ struct Pack8<__nv_bfloat16>
             v[2 * i + 1] = f.y;
         }
     }
+    static __device__ __forceinline__ uint32_t pack2(float a, float b)
+    {
+        __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
     static constexpr int ab_format = 1;
 };
 template<>
@@ -346,42 +383,55 @@ struct Pack8<__half>
             v[2 * i + 1] = f.y;
         }
     }
+    static __device__ __forceinline__ uint32_t pack2(float a, float b)
+    {
+        __half2 t = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
     static constexpr int ab_format = 0;
 };
 
+// the rare activations (sigmoid, mish, hardswish) as an out-of-line call: keeps the unrolled epilogue small and its
+// accumulators in registers
+static __device__ __noinline__ float apply_activation_call(float v, int type, float p0, float p1)
+{
+    return apply_activation(v, type, p0, p1);
+}
+
 // ---------------------------------------------------------------- the kernel
-// Output (and residual) tensor maps are rank 3: (channels, columns, rows)
+// The residual tensor map is rank 3: (channels, columns, rows)
 //   A_TILED / A_IM2COL : (C, M, 1)            tile rows m0 .. m0+127 are consecutive output pixels
 //   A_ROWS             : (C, outw, n*outh)    tile rows are 128 consecutive columns of one output row
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
-               const __grid_constant__ CUtensorMap tmap_res, const Params p)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_res, const Params p)
 {
     using Plan = SmemPlan<BLOCK_N, BLOCK_K>;
-    constexpr int kStages = Plan::kStages;
     constexpr int EPI_N = Plan::EPI_N;
-    constexpr int NCHUNK = BLOCK_N / EPI_N;
+    constexpr int NCHUNK = BLOCK_N / EPI_N;    // residual slots per tile
+    constexpr int SUBS = EPI_N / 32;           // 32-column TMEM loads per slot (1 or 2)
+    constexpr int kResSlots = Plan::kResSlots;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N; // power of two for BLOCK_N in {16..256}
-    // swizzle of the epilogue staging tiles: rows of EPI_N 16-bit values = 128 / 64 / 32 bytes
+    // swizzle of the residual staging tiles: rows of EPI_N 16-bit values = 128 / 64 bytes
     constexpr int EPI_ROW_BYTES = EPI_N * 2;
-    constexpr int EPI_CHUNKS16 = EPI_ROW_BYTES / 16; // 16-byte units per row: 8 / 4 / 2
+    constexpr int EPI_CHUNKS16 = EPI_ROW_BYTES / 16; // 16-byte units per row: 8 / 4
 
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B operand tiles need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // SWIZZLE_128B operand tiles need 1024-byte alignment (pointer arithmetic keeps the shared state space visible)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int kStages = p.num_stages;
+    const bool has_res = p.residual != nullptr;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Plan::a_bytes;
-    uint8_t* smem_out = smem + kStages * Plan::stage_bytes;      // [2][BLOCK_M][EPI_N]
-    uint8_t* smem_res = smem_out + 2 * Plan::epi_chunk_bytes;    // [2][BLOCK_M][EPI_N]
-    float* smem_bias = reinterpret_cast<float*>(smem_res + 2 * Plan::epi_chunk_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + Plan::bias_bytes);
-    uint64_t* full_bar = bars;                         // [kStages]
-    uint64_t* empty_bar = bars + kStages;              // [kStages]
-    uint64_t* tmem_full_bar = bars + 2 * kStages;      // [2]
-    uint64_t* tmem_empty_bar = bars + 2 * kStages + 2; // [2]
-    uint64_t* res_full_bar = bars + 2 * kStages + 4;   // [2]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
+    uint8_t* smem_res = smem + kStages * Plan::stage_bytes; // [kResSlots][BLOCK_M][EPI_N], only when has_res
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_res + (has_res ? kResSlots * Plan::res_slot_bytes : 0));
+    uint64_t* full_bar = bars;                  // [8]
+    uint64_t* empty_bar = bars + 8;             // [8]
+    uint64_t* tmem_full_bar = bars + 16;        // [2]
+    uint64_t* tmem_empty_bar = bars + 18;       // [2]
+    uint64_t* res_full_bar = bars + 20;         // [kResSlots]
+    uint64_t* res_empty_bar = bars + 24;        // [kResSlots]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -393,13 +443,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     else
         num_m_blocks = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     const int num_tiles = num_m_blocks * num_n_blocks;
-    const bool has_res = p.residual != nullptr;
 
     if (warp == 0 && lane == 0)
     {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
-        prefetch_tmap(&tmap_out);
         if (has_res) prefetch_tmap(&tmap_res);
     }
     if (warp == 1 && lane == 0)
@@ -413,7 +461,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+        }
+        for (int i = 0; i < kResSlots; i++)
+        {
             mbar_init(smem_u32(&res_full_bar[i]), 1);
+            mbar_init(smem_u32(&res_empty_bar[i]), 4);
         }
         fence_barrier_init();
     }
@@ -433,6 +485,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // ===================== TMA producer =====================
             int stage = 0;
             uint32_t phase = 0;
+            int rslot = 0;
+            uint32_t rphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
             {
                 const int n_blk = tile % num_n_blocks;
@@ -487,6 +541,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         phase ^= 1;
                     }
                 }
+                if (has_res)
+                {
+                    // the fused residual of this tile, EPI_N columns per ring slot; issued after the tile's operand loads so
+                    // that waiting for a free slot (the epilogue is at most one tile behind) never delays the MMA feed
+                    int c1, c2;
+                    if (AMODE == A_ROWS)
+                    {
+                        c1 = (m_blk % p.chunks_per_row) * BLOCK_M;
+                        c2 = m_blk / p.chunks_per_row;
+                    }
+                    else
+                    {
+                        c1 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
+                        c2 = 0;
+                    }
+                    for (int cc = 0; cc < NCHUNK; cc++)
+                    {
+                        const int c0 = n_blk * BLOCK_N + cc * EPI_N;
+                        if (c0 >= p.N) break;
+                        mbar_wait(smem_u32(&res_empty_bar[rslot]), rphase ^ 1);
+                        const uint32_t rb = smem_u32(&res_full_bar[rslot]);
+                        mbar_expect_tx(rb, Plan::res_slot_bytes);
+                        tma_load_3d(smem_u32(smem_res + rslot * Plan::res_slot_bytes), &tmap_res, rb, c0, c1, c2);
+                        if (++rslot == kResSlots)
+                        {
+                            rslot = 0;
+                            rphase ^= 1;
+                        }
+                    }
+                }
             }
         }
     }
@@ -532,157 +616,167 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     else
     {
-        // ===================== epilogue (warps 2..5, 128 threads) =====================
-        // TMEM -> registers (+bias, +residual, activation) -> swizzled shared memory -> TMA store, EPI_N columns at a
-        // time through two staging buffers; the residual tile comes in by TMA load two chunks ahead.
-        const int lane_group = warp & 3; // TMEM lanes [32*lane_group, +32) are the ones this warp may read
+        // ===================== epilogue (warps 2..5): four independent warps, no CTA-wide synchronisation =====================
+        // Warp w owns TMEM lanes [32*(w&3), +32) = 32 output pixels, one per lane.  Per 32 accumulator columns:
+        // tcgen05.ld (double-buffered in registers) -> +bias (broadcast __ldg) -> +residual (swizzled TMA slot) ->
+        // activation -> 16-bit pack -> two 32-byte st.global.v8 per lane (each a full sector of the pixel's channel run).
+        const int lane_group = warp & 3;
         const int row = lane_group * 32 + lane;
-        const bool leader = (warp == kEpilogueWarp0 && lane == 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t g = 0; // running chunk counter of this CTA (buffer = g & 1, parity = (g >> 1) & 1)
-
-        const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-        const uint32_t total_chunks = (uint32_t)my_tiles * NCHUNK;
-
-        // coordinates of chunk number q (0-based over this CTA's tiles) in the (C, col, row) output tensor
-        auto chunk_coords = [&](uint32_t q, int& c0, int& c1, int& c2) {
-            const int tile = blockIdx.x + (int)(q / NCHUNK) * gridDim.x;
-            const int cc = (int)(q % NCHUNK);
-            const int n_blk = tile % num_n_blocks;
-            const int m_blk = tile / num_n_blocks;
-            c0 = n_blk * BLOCK_N + cc * EPI_N;
-            if (AMODE == A_ROWS)
-            {
-                c1 = (m_blk % p.chunks_per_row) * BLOCK_M;
-                c2 = m_blk / p.chunks_per_row;
-            }
-            else
-            {
-                c1 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
-                c2 = 0;
-            }
-        };
-        auto issue_residual = [&](uint32_t q) {
-            int c0, c1, c2;
-            chunk_coords(q, c0, c1, c2);
-            const uint32_t bar = smem_u32(&res_full_bar[q & 1]);
-            mbar_expect_tx(bar, Plan::epi_chunk_bytes);
-            tma_load_3d(smem_u32(smem_res + (q & 1) * Plan::epi_chunk_bytes), &tmap_res, bar, c0, c1, c2);
-        };
-        if (has_res && leader)
-        {
-            if (total_chunks > 0) issue_residual(0);
-            if (total_chunks > 1) issue_residual(1);
-        }
+        int rslot = 0;
+        uint32_t rphase = 0;
+        const int n8 = (p.N + 7) & ~7; // the blob's padding lanes up to the next 16-byte unit may be written
+        const int act = p.act_type;
+        const int sw_row = (EPI_CHUNKS16 == 8) ? (row & 7) : ((row >> 1) & 3);
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
             const int n_blk = tile % num_n_blocks;
+            const int m_blk = tile / num_n_blocks;
             const int n0 = n_blk * BLOCK_N;
-            // bias of this tile's columns (the previous tile's readers are past their last chunk barrier)
-            for (int i = threadIdx.x - kEpilogueWarp0 * 32; i < BLOCK_N; i += 128) smem_bias[i] = __ldg(p.bias + n0 + i);
-
-            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#pragma unroll 1
-            for (int cc = 0; cc < NCHUNK; cc++, g++)
+            long long pix;
+            bool row_ok;
+            if (AMODE == A_ROWS)
             {
-                const int buf = (int)(g & 1);
-                uint8_t* obuf = smem_out + buf * Plan::epi_chunk_bytes;
-                const uint8_t* rbuf = smem_res + buf * Plan::epi_chunk_bytes;
-                // the TMA store that last used this buffer (chunk g-2) must have finished reading it
-                if (leader) tma_store_wait_read<1>();
-                epi_bar_sync(); // also publishes smem_bias on the first chunk
-                if (has_res) mbar_wait(smem_u32(&res_full_bar[buf]), (g >> 1) & 1);
+                const int col = (m_blk % p.chunks_per_row) * BLOCK_M + row;
+                row_ok = col < p.outw;
+                pix = (long long)(m_blk / p.chunks_per_row) * p.outw + col;
+            }
+            else
+            {
+                pix = (long long)m_blk * BLOCK_M + row;
+                row_ok = pix < p.M;
+            }
+            T* const orow = reinterpret_cast<T*>(p.out) + pix * p.out_cpitch + n0;
+            const float* const brow = p.bias + n0;
 
-                // gather the chunk row: EPI_N accumulators (+bias, +residual) in registers
-                float v[EPI_N];
+            // one 32-column group: r holds the raw accumulators
+            auto process = [&](const int sub, uint32_t(&r)[32], const uint8_t* rbuf, const int slot_sub) {
+                const int col0 = sub * 32; // within the tile
+                float v[32];
 #pragma unroll
-                for (int h = 0; h < EPI_N / 32; h++)
+                for (int q = 0; q < 8; q++)
                 {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * EPI_N + h * 32), r);
-                    tmem_wait_ld();
-                    const float* bs = smem_bias + cc * EPI_N + h * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[h * 32 + j] = __uint_as_float(r[j]) + bs[j];
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col0) + q);
+                    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+                    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+                    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+                    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
                 }
                 if (has_res)
                 {
 #pragma unroll
-                    for (int u = 0; u < EPI_CHUNKS16; u++)
+                    for (int u = 0; u < 4; u++)
                     {
-                        const int sw = u ^ ((EPI_CHUNKS16 == 8) ? (row & 7) : (EPI_CHUNKS16 == 4 ? ((row >> 1) & 3) : ((row >> 2) & 1)));
+                        const int unit = slot_sub * 4 + u; // 16-byte unit of the slot row
                         float rv[8];
-                        const uint4 ru = *reinterpret_cast<const uint4*>(rbuf + row * EPI_ROW_BYTES + sw * 16);
+                        const uint4 ru = *reinterpret_cast<const uint4*>(rbuf + row * EPI_ROW_BYTES + ((unit ^ sw_row) * 16));
                         Pack8<T>::unpack(ru, rv);
 #pragma unroll
                         for (int j = 0; j < 8; j++) v[u * 8 + j] += rv[j];
                     }
                 }
-                // activation: one uniform branch per chunk, not per element (a per-element switch gets if-converted
-                // into every transcendental path)
-                const int act = p.act_type;
+                // activation: one uniform branch per group, not per element
                 if (act == 1)
                 {
 #pragma unroll
-                    for (int j = 0; j < EPI_N; j++) v[j] = fmaxf(v[j], 0.f);
+                    for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
                 }
                 else if (act == 7)
                 {
 #pragma unroll
-                    for (int j = 0; j < EPI_N; j++) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
-                }
-                else if (act == 2)
-                {
-#pragma unroll
-                    for (int j = 0; j < EPI_N; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_p0;
+                    for (int j = 0; j < 32; j++) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
                 }
                 else if (act == 3)
                 {
 #pragma unroll
-                    for (int j = 0; j < EPI_N; j++) v[j] = fminf(fmaxf(v[j], p.act_p0), p.act_p1);
+                    for (int j = 0; j < 32; j++) v[j] = fminf(fmaxf(v[j], p.act_p0), p.act_p1);
+                }
+                else if (act == 2)
+                {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_p0;
                 }
                 else if (act != 0)
                 {
 #pragma unroll
-                    for (int j = 0; j < EPI_N; j++) v[j] = apply_activation(v[j], act, p.act_p0, p.act_p1);
+                    for (int j = 0; j < 32; j++) v[j] = apply_activation_call(v[j], act, p.act_p0, p.act_p1);
                 }
+                uint32_t o[16];
 #pragma unroll
-                for (int u = 0; u < EPI_CHUNKS16; u++)
+                for (int j = 0; j < 16; j++) o[j] = Pack8<T>::pack2(v[2 * j], v[2 * j + 1]);
+                if (row_ok)
                 {
-                    // 128B/64B/32B swizzle as TMA applies it: 16-byte unit index XOR (row bits) restricted to the row width
-                    const int sw = u ^ ((EPI_CHUNKS16 == 8) ? (row & 7) : (EPI_CHUNKS16 == 4 ? ((row >> 1) & 3) : ((row >> 2) & 1)));
-                    float o8[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) o8[j] = v[u * 8 + j];
-                    *reinterpret_cast<uint4*>(obuf + row * EPI_ROW_BYTES + sw * 16) = Pack8<T>::pack(o8);
+                    for (int h = 0; h < 2; h++)
+                    {
+                        const int c = n0 + col0 + h * 16;
+                        T* dst = orow + col0 + h * 16;
+                        if (p.v8_ok && c + 16 <= n8)
+                            st_global_v8(dst, &o[h * 8]);
+                        else
+                        {
+                            if (c < n8) st_global_v4(dst, &o[h * 8]);
+                            if (c + 8 < n8) st_global_v4(dst + 8, &o[h * 8 + 4]);
+                        }
+                    }
                 }
-                if (cc == NCHUNK - 1)
+            };
+            // the accumulator stage goes back to the MMA warp as soon as its last column group sits in registers
+            auto release_tmem = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+            };
+
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(taddr, r0);
+#pragma unroll 1
+            for (int cc = 0; cc < NCHUNK; cc++)
+            {
+                const int c0 = n0 + cc * EPI_N;
+                if (c0 >= p.N) break;
+                const bool v1 = SUBS == 2 && (c0 + 32 < p.N);
+                const bool vnext = (cc + 1 < NCHUNK) && (c0 + EPI_N < p.N);
+                const uint8_t* rbuf = smem_res + rslot * Plan::res_slot_bytes;
+                if (has_res) mbar_wait(smem_u32(&res_full_bar[rslot]), rphase);
+
+                tmem_wait_ld_pin(r0);
+                if (v1)
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * EPI_N + 32), r1);
+                else if (vnext)
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)((cc + 1) * EPI_N), r0);
+                else
+                    release_tmem();
+                process(cc * SUBS, r0, rbuf, 0);
+                if (SUBS == 2 && v1)
                 {
-                    // every TMEM read of this accumulator stage is complete: hand it back to the MMA warp
-                    tc_fence_before();
+                    tmem_wait_ld_pin(r1);
+                    if (vnext)
+                        tmem_ld_32x32b_x32(taddr + (uint32_t)((cc + 1) * EPI_N), r0);
+                    else
+                        release_tmem();
+                    process(cc * SUBS + 1, r1, rbuf, 1);
+                }
+                if (has_res)
+                {
+                    // this warp has read its rows of the slot
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-                }
-                fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
-                epi_bar_sync();
-                if (leader)
-                {
-                    int c0, c1, c2;
-                    chunk_coords(g, c0, c1, c2);
-                    tma_store_3d(&tmap_out, smem_u32(obuf), c0, c1, c2);
-                    tma_store_commit();
-                    // the residual buffer of this chunk is consumed: prefetch the one two chunks ahead into it
-                    if (has_res && g + 2 < total_chunks) issue_residual(g + 2);
+                    if (lane == 0) mbar_arrive(smem_u32(&res_empty_bar[rslot]));
+                    if (++rslot == kResSlots)
+                    {
+                        rslot = 0;
+                        rphase ^= 1;
+                    }
                 }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (leader) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -719,6 +813,10 @@ struct TcPlan
 };
 
 int tc_available(); // 1 when the driver exposes cuTensorMapEncode* and the device is sm_100
+// cuTensorMapEncodeTiled for the bandwidth kernels (depthwise, pooling): channel-innermost blob, no swizzle, zero OOB fill.
+// rank <= 5; gstride has rank-1 entries (bytes, multiples of 16).  Returns 0 / -1.
+int tma_encode_tiled_plain(CUtensorMap* map, int elemtype, int rank, const void* ptr, const unsigned long long* gdim, const unsigned long long* gstride_bytes,
+                           const unsigned int* box);
 int tc_pick_block_k(int inch);
 int tc_pick_block_n(int outch);
 struct ncnn_cuda_conv2d_desc_fwd; // (documentation only)

@@ -244,10 +244,23 @@ def test_convolutiondepthwise_grid(ref, elemtype):
             i += 1
 
 
-def test_convolutiondepthwise_mobilenet_shapes(ref):
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_convolutiondepthwise_mobilenet_shapes(ref, elemtype):
+    """the 3x3 stride-1/2 depthwise shapes of MobileNetV2 (TMA-staged halo-tile kernel, dwconv_tma.cuh): every channel-block
+    width (C % 64, % 32, % 16), odd and even map sizes, maps smaller than a tile, ReLU and ReLU6 (Clip) epilogues"""
     rng = np.random.default_rng(12)
-    for (w, c, s) in [(56, 32, 1), (56, 96, 2), (28, 144, 1), (14, 384, 1), (14, 576, 2), (7, 960, 1)]:
-        run_dw(ref, rng, F32, 2, w, w, c, c, c, 3, 1, s, 1, True, 1)
+    for (w, c, s, act) in [(56, 32, 1, 1), (56, 96, 2, 3), (28, 144, 1, 3), (29, 144, 2, 0), (14, 384, 1, 3), (14, 576, 2, 1), (7, 960, 1, 3), (15, 192, 2, 3),
+                           (33, 48, 1, 2), (9, 64, 2, 4)]:
+        run_dw(ref, rng, elemtype, 2, w, w + (w % 3), c, c, c, 3, 1, s, 1, True, act)
+
+
+def test_convolutiondepthwise_many_tiles(ref):
+    """more tiles than 4 ring stages x 148 persistent CTAs: the stage/phase wrap of the TMA ring and the weight reload
+    when a CTA moves to the next channel block"""
+    rng = np.random.default_rng(13)
+    run_dw(ref, rng, F16, 16, 112, 112, 32, 32, 32, 3, 1, 1, 1, True, 3)
+    run_dw(ref, rng, BF16, 24, 56, 56, 96, 96, 96, 3, 1, 2, 1, False, 1)
+    run_dw(ref, rng, F16, 40, 14, 14, 384, 384, 384, 3, 1, 1, 1, True, 3)
 
 
 # ------------------------------------------------------------------------------------------ Pooling
