@@ -5,10 +5,12 @@
 // input tiles (tile + 1-pixel halo) in shared memory with 4-D tiled TMA loads -- the halo outside the image is the TMA
 // unit's out-of-bounds zero fill, so there is no padded copy (reference: copy_make_border in
 // ConvolutionDepthWise::make_padding) and no per-tap bounds test.  256 consumer threads each own one output column of
-// the tile for a 16-byte channel vector and R consecutive output rows: every input row is read from shared memory once
-// (3 x LDS.128) and feeds up to three output rows from registers; the 9 x VEC filter taps live in registers and are
-// reloaded only when the CTA moves to another channel block.  fp32 accumulation with packed FFMA2, in the reference's
-// tap order (ky major), bias first.  Outputs leave as 16-byte vector stores (a warp writes whole pixels' channel runs).
+// the tile for a 16-byte channel vector and R consecutive output rows: every input pixel is read from shared memory once
+// (LDS.128), converted once and feeds up to three output rows from registers.  The layer's whole filter bank ([9][C] fp32)
+// and bias sit in shared memory for the lifetime of the CTA; the loop is filter-column major so that only three taps are
+// live in registers at a time (<= 113 registers -> two CTAs per SM, 16 consumer warps hide the LDS/convert latency).
+// fp32 accumulation with packed FFMA2, bias first.  Outputs leave as 16-byte vector stores (a warp writes whole
+// pixels' channel runs).  Tile indices are decoded with multiply-shift division (no integer divide in the loop).
 //
 // HBM traffic is the algorithmic minimum (input once, output once); the halo re-reads (<= 1.4x of the input) are L2 hits.
 #pragma once
@@ -20,20 +22,45 @@ namespace dwt {
 constexpr int kConsumers = 256;
 constexpr int kThreads = kConsumers + 32;
 
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (d >= 1)
+struct FastDiv
+{
+    unsigned int d, m, s;
+};
+
+static inline FastDiv make_fastdiv(unsigned int d)
+{
+    FastDiv f;
+    f.d = d;
+    unsigned int s = 0;
+    while ((1ull << s) < d) s++;
+    f.s = s;
+    f.m = (unsigned int)((((1ull << s) - d) << 32) / d + 1);
+    return f;
+}
+
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f)
+{
+    return (int)((__umulhi((unsigned int)n, f.m) + (unsigned int)n) >> f.s);
+}
+
 struct Params
 {
     int C, outw, outh, n;
     int tiles_x, tiles_y;
+    FastDiv div_cblocks, div_image, div_tiles_x;
     int n_spatial; // n * tiles_y * tiles_x
     int num_tiles; // cblocks * n_spatial
     int pad_left, pad_top;
     int out_cpitch;
     long long out_nstep;
+    long long out_row_stride; // outw * out_cpitch
     const float* w;    // [9][cpad]
     const float* bias; // [C] or NULL
     int cpad;
     int act_type;
     float act_p0, act_p1;
+    int num_stages;
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
@@ -119,27 +146,37 @@ struct Cfg
     static constexpr int IH = (TH - 1) * S + 3;
     static constexpr int tile_bytes = IW * IH * CV * 16;
     static constexpr int stage_bytes = (tile_bytes + 127) / 128 * 128;
-    static constexpr int stages_fit = (176 * 1024) / stage_bytes;
-    static constexpr int kStages = stages_fit > 4 ? 4 : stages_fit;
-    static constexpr int smem_bytes = kStages * stage_bytes + 128 /*alignment*/ + 128 /*barriers*/;
+    // two CTAs per SM: each gets half of the 227 KB
+    static constexpr int cta_budget = 111 * 1024;
+    static constexpr int fixed_bytes = 128 /*alignment*/ + 128 /*barriers*/;
     static_assert(CV * TW * TY == kConsumers, "one consumer thread per (channel vector, column, thread row)");
-    static_assert(kStages >= 2, "tile too large for a 2-stage ring");
+    // ring depth once the filter bank (10 * cpad floats: 9 taps + bias) is resident
+    static int stages_for(int cpad)
+    {
+        int s = (cta_budget - fixed_bytes - 10 * cpad * 4) / stage_bytes;
+        return s > 4 ? 4 : s;
+    }
+    static int smem_for(int cpad)
+    {
+        return stages_for(cpad) * stage_bytes + 10 * cpad * 4 + fixed_bytes;
+    }
 };
 
 template<typename T, int S, int CV, int TW, int TY, int R>
-__global__ void __launch_bounds__(kThreads, 1) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, T* __restrict__ out, const Params p)
+__global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, T* __restrict__ out, const Params p)
 {
     using C = Cfg<T, S, CV, TW, TY, R>;
     constexpr int VEC = C::VEC;
     constexpr int H2 = VEC / 2; // float2 per channel vector
-    constexpr int kStages = C::kStages;
     constexpr int NROWS = (R - 1) * S + 3; // input rows a thread walks
+    const int kStages = p.num_stages;
 
     extern __shared__ uint8_t dw_smem_raw[];
     // (pointer arithmetic, not an integer round trip: keeps the shared address space visible to the compiler -> LDS, not generic LD)
     uint8_t* smem = dw_smem_raw + ((128u - (tc::smem_u32(dw_smem_raw) & 127u)) & 127u);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::stage_bytes);
-    uint64_t* empty_bar = full_bar + kStages;
+    float* smem_w = reinterpret_cast<float*>(smem + kStages * C::stage_bytes); // [9][cpad] taps, then [cpad] bias
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_w + 10 * p.cpad);
+    uint64_t* empty_bar = full_bar + 4;
 
     const int tid = threadIdx.x;
     if (tid == 0)
@@ -152,9 +189,10 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3x3_tma_kernel(const __grid
         }
         tc::fence_barrier_init();
     }
+    // the layer's filter bank and bias: resident for the whole kernel
+    for (int i = tid; i < 9 * p.cpad; i += kThreads) smem_w[i] = p.w[i];
+    for (int i = tid; i < p.cpad; i += kThreads) smem_w[9 * p.cpad + i] = (p.bias && i < p.C) ? p.bias[i] : 0.f;
     __syncthreads();
-
-    const int tiles_per_image = p.tiles_x * p.tiles_y;
 
     if (tid >= kConsumers)
     {
@@ -165,11 +203,12 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3x3_tma_kernel(const __grid
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
             {
-                const int cb = tile / p.n_spatial;
-                const int sp = tile - cb * p.n_spatial;
-                const int b = sp / tiles_per_image;
-                const int t2 = sp - b * tiles_per_image;
-                const int tyi = t2 / p.tiles_x;
+                // channel block fastest: the CTAs working on one spatial tile at the same time share its DRAM pages / L2 lines
+                const int sp = fast_div(tile, p.div_cblocks);
+                const int cb = tile - sp * (int)p.div_cblocks.d;
+                const int b = fast_div(sp, p.div_image);
+                const int t2 = sp - b * (int)p.div_image.d;
+                const int tyi = fast_div(t2, p.div_tiles_x);
                 const int txi = t2 - tyi * p.tiles_x;
                 tc::mbar_wait(tc::smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t fb = tc::smem_u32(&full_bar[stage]);
@@ -191,61 +230,70 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3x3_tma_kernel(const __grid
     const int ty = tid / (CV * TW);
     const int lane = tid & 31;
 
-    float2 w[9][H2];
-    float2 bias2[H2];
-    int cur_cb = -1;
     int stage = 0;
     uint32_t phase = 0;
     // byte offset of this thread's first input pixel inside a staged tile
     const int thread_off = ((ty * R * S) * C::IW + tx * S) * (CV * 16) + cv * 16;
+    const int act = p.act_type;
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
     {
-        const int cb = tile / p.n_spatial;
-        const int sp = tile - cb * p.n_spatial;
-        const int b = sp / tiles_per_image;
-        const int t2 = sp - b * tiles_per_image;
-        const int tyi = t2 / p.tiles_x;
+        const int sp = fast_div(tile, p.div_cblocks);
+        const int cb = tile - sp * (int)p.div_cblocks.d;
+        const int b = fast_div(sp, p.div_image);
+        const int t2 = sp - b * (int)p.div_image.d;
+        const int tyi = fast_div(t2, p.div_tiles_x);
         const int txi = t2 - tyi * p.tiles_x;
         const int c0 = cb * C::CB + cv * VEC;
-        if (cb != cur_cb)
-        {
-            cur_cb = cb;
-#pragma unroll
-            for (int t = 0; t < 9; t++)
-            {
-                const float* wp = p.w + (long long)t * p.cpad + c0;
-#pragma unroll
-                for (int i = 0; i < H2; i++) w[t][i] = *reinterpret_cast<const float2*>(wp + 2 * i);
-            }
-#pragma unroll
-            for (int i = 0; i < H2; i++) bias2[i] = p.bias ? *reinterpret_cast<const float2*>(p.bias + c0 + 2 * i) : make_float2(0.f, 0.f);
-        }
+        const float* wc = smem_w + c0;
 
         float2 acc[R][H2];
+        {
+            float2 bias2[H2];
 #pragma unroll
-        for (int r = 0; r < R; r++)
+            for (int i = 0; i < H2; i += 2)
+            {
+                // cpad and c0 are multiples of 4 floats: 16-byte broadcast loads
+                const float4 t = *reinterpret_cast<const float4*>(wc + 9 * p.cpad + 2 * i);
+                bias2[i] = make_float2(t.x, t.y);
+                bias2[i + 1] = make_float2(t.z, t.w);
+            }
 #pragma unroll
-            for (int i = 0; i < H2; i++) acc[r][i] = bias2[i];
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int i = 0; i < H2; i++) acc[r][i] = bias2[i];
+        }
 
         tc::mbar_wait(tc::smem_u32(&full_bar[stage]), phase);
         const uint8_t* base = smem + stage * C::stage_bytes + thread_off;
 #pragma unroll
-        for (int ii = 0; ii < NROWS; ii++)
+        for (int kx = 0; kx < 3; kx++)
         {
-            float2 x[3][H2];
+            // the three taps of this filter column
+            float2 w[3][H2];
 #pragma unroll
-            for (int kx = 0; kx < 3; kx++) Vec16<T>::load(base + (ii * C::IW + kx) * (CV * 16), x[kx]);
+            for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-            for (int r = 0; r < R; r++)
-            {
-                const int ky = ii - r * S;
-                if (ky >= 0 && ky < 3)
+                for (int i = 0; i < H2; i += 2)
                 {
+                    const float4 t = *reinterpret_cast<const float4*>(wc + (ky * 3 + kx) * p.cpad + 2 * i);
+                    w[ky][i] = make_float2(t.x, t.y);
+                    w[ky][i + 1] = make_float2(t.z, t.w);
+                }
 #pragma unroll
-                    for (int kx = 0; kx < 3; kx++)
+            for (int ii = 0; ii < NROWS; ii++)
+            {
+                float2 x[H2];
+                Vec16<T>::load(base + (ii * C::IW + kx) * (CV * 16), x);
 #pragma unroll
-                        for (int i = 0; i < H2; i++) acc[r][i] = ffma2(x[kx][i], w[ky * 3 + kx][i], acc[r][i]);
+                for (int r = 0; r < R; r++)
+                {
+                    const int ky = ii - r * S;
+                    if (ky >= 0 && ky < 3)
+                    {
+#pragma unroll
+                        for (int i = 0; i < H2; i++) acc[r][i] = ffma2(x[i], w[ky][i], acc[r][i]);
+                    }
                 }
             }
         }
@@ -258,38 +306,40 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3x3_tma_kernel(const __grid
             phase ^= 1;
         }
 
+        // activation on the whole register tile (one uniform branch), then the stores
+        if (act == 1)
+        {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int i = 0; i < H2; i++) acc[r][i] = make_float2(fmaxf(acc[r][i].x, 0.f), fmaxf(acc[r][i].y, 0.f));
+        }
+        else if (act == 3)
+        {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int i = 0; i < H2; i++)
+                    acc[r][i] = make_float2(fminf(fmaxf(acc[r][i].x, p.act_p0), p.act_p1), fminf(fmaxf(acc[r][i].y, p.act_p0), p.act_p1));
+        }
+        else if (act != 0)
+        {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int i = 0; i < H2; i++)
+                    acc[r][i] = make_float2(tc::apply_activation_call(acc[r][i].x, act, p.act_p0, p.act_p1), tc::apply_activation_call(acc[r][i].y, act, p.act_p0, p.act_p1));
+        }
         const int ox = txi * TW + tx;
         const int oy0 = tyi * C::TH + ty * R;
         if (ox < p.outw)
         {
-            T* op = out + (long long)b * p.out_nstep + ((long long)oy0 * p.outw + ox) * p.out_cpitch + c0;
-            const int act = p.act_type;
+            T* op = out + ((long long)b * p.out_nstep + ((long long)oy0 * p.outw + ox) * p.out_cpitch + c0);
 #pragma unroll
             for (int r = 0; r < R; r++)
             {
-                if (oy0 + r < p.outh)
-                {
-                    float2 v[H2];
-#pragma unroll
-                    for (int i = 0; i < H2; i++) v[i] = acc[r][i];
-                    if (act == 1)
-                    {
-#pragma unroll
-                        for (int i = 0; i < H2; i++) v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
-                    }
-                    else if (act == 3)
-                    {
-#pragma unroll
-                        for (int i = 0; i < H2; i++) v[i] = make_float2(fminf(fmaxf(v[i].x, p.act_p0), p.act_p1), fminf(fmaxf(v[i].y, p.act_p0), p.act_p1));
-                    }
-                    else if (act != 0)
-                    {
-#pragma unroll
-                        for (int i = 0; i < H2; i++)
-                            v[i] = make_float2(apply_activation(v[i].x, act, p.act_p0, p.act_p1), apply_activation(v[i].y, act, p.act_p0, p.act_p1));
-                    }
-                    Vec16<T>::store(op + (long long)r * p.outw * p.out_cpitch, v);
-                }
+                if (oy0 + r < p.outh) Vec16<T>::store(op, acc[r]);
+                op += p.out_row_stride;
             }
         }
     }
@@ -303,18 +353,24 @@ static int launch_dw_tma(const CUtensorMap& tm, T* out, Params& p, cudaStream_t 
     static bool attr_set = false;
     if (!attr_set)
     {
-        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::cta_budget));
         attr_set = true;
     }
+    p.num_stages = C::stages_for(p.cpad);
+    if (p.num_stages < 2) return 1; // filter bank too large to keep resident: generic kernel
     p.tiles_x = (p.outw + TW - 1) / TW;
     p.tiles_y = (p.outh + C::TH - 1) / C::TH;
     const long long n_spatial = (long long)p.n * p.tiles_x * p.tiles_y;
     const long long num_tiles = n_spatial * (p.C / C::CB);
-    if (num_tiles > 0x7fffffffLL) return 1; // caller falls back
+    if (num_tiles > 0x3fffffffLL) return 1; // caller falls back
     p.n_spatial = (int)n_spatial;
     p.num_tiles = (int)num_tiles;
-    const int grid = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
-    kern<<<grid, kThreads, C::smem_bytes, stream>>>(tm, out, p);
+    p.div_cblocks = make_fastdiv((unsigned int)(p.C / C::CB));
+    p.div_image = make_fastdiv((unsigned int)(p.tiles_x * p.tiles_y));
+    p.div_tiles_x = make_fastdiv((unsigned int)p.tiles_x);
+    const long long max_ctas = 2LL * sm_count();
+    const int grid = (int)(num_tiles < max_ctas ? num_tiles : max_ctas);
+    kern<<<grid, kThreads, C::smem_for(p.cpad), stream>>>(tm, out, p);
     NC_LAUNCH_CHECK();
     return 0;
 }
@@ -372,6 +428,7 @@ static int forward(const Call& c, cudaStream_t stream)
     p.pad_top = c.pad_top;
     p.out_cpitch = c.out_cpitch;
     p.out_nstep = c.out_nstep;
+    p.out_row_stride = (long long)c.outw * c.out_cpitch;
     p.w = c.w;
     p.bias = c.bias;
     p.cpad = c.cpad;

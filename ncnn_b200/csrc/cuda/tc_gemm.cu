@@ -103,8 +103,10 @@ int tma_encode_tiled_plain(CUtensorMap* map, int elemtype, int rank, const void*
         if (i < rank - 1) gs[i] = gstride_bytes[i];
     }
     CUtensorMapDataType dt = elemtype == NCNN_CUDA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype_for(elemtype);
+    // 128-byte promotion: a tile row can be as narrow as 32 bytes of a pixel's channel run; wider promotion only helps when
+    // the neighbouring channel blocks are consumed soon after (they are: channel block is the fastest tile index)
     CUresult r = g_encodeTiled(map, dt, (cuuint32_t)rank, (void*)ptr, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
 }
 
@@ -313,7 +315,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     static bool attr_set = false;
     if (!attr_set)
     {
-        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::total_for(false)));
+        constexpr int max_smem = Plan::total_for(false) > Plan::total_for(true) ? Plan::total_for(false) : Plan::total_for(true);
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set = true;
     }
     const bool has_res = p.residual != 0;

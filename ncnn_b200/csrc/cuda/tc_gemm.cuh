@@ -13,7 +13,8 @@
 //   warp 0 lane 0 : TMA producer      -- cp.async.bulk.tensor -> kStages-deep smem ring (128B-swizzled)
 //   warp 1 lane 0 : MMA issuer        -- tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM,
 //                                        2 accumulator stages so the epilogue of tile i overlaps tile i+1
-//   warps 2..5    : epilogue          -- tcgen05.ld TMEM->registers, +bias, +residual, activation, 16-byte stores
+//   warps 2..9    : epilogue          -- tcgen05.ld TMEM->registers, +bias, +residual, activation, 32-byte stores;
+//                                        two warps per TMEM lane quarter, alternating 64-column chunks, no CTA-wide sync
 //   full/empty mbarriers between producer and MMA, tmem_full/tmem_empty between MMA and epilogue.
 #pragma once
 #include "common.cuh"
@@ -24,8 +25,10 @@ namespace ncnn_cuda {
 namespace tc {
 
 constexpr int BLOCK_M = 128;
-constexpr int kNumThreads = 192;
 constexpr int kEpilogueWarp0 = 2;
+constexpr int kEpilogueWarps = 8; // two per TMEM lane quarter
+constexpr int kNumThreads = (kEpilogueWarp0 + kEpilogueWarps) * 32;
+constexpr int kBiasSmemFloats = 4096; // layers up to this many (padded) output channels keep their bias in shared memory
 
 struct Params
 {
@@ -312,7 +315,8 @@ struct SmemPlan
     static constexpr int kResSlots = 4;
     static constexpr int res_slot_bytes = BLOCK_M * EPI_N * 2;
     static constexpr int barrier_bytes = 512;
-    static constexpr int budget = 225 * 1024 - barrier_bytes - 1024; // - alignment slack
+    static constexpr int bias_bytes = kBiasSmemFloats * 4;
+    static constexpr int budget = 227 * 1024 - barrier_bytes - bias_bytes - 1024; // - alignment slack
     static constexpr int stages_for(bool has_res)
     {
         int s = (budget - (has_res ? kResSlots * res_slot_bytes : 0)) / stage_bytes;
@@ -320,7 +324,7 @@ struct SmemPlan
     }
     static constexpr int total_for(bool has_res)
     {
-        return stages_for(has_res) * stage_bytes + (has_res ? kResSlots * res_slot_bytes : 0) + barrier_bytes + 1024;
+        return stages_for(has_res) * stage_bytes + (has_res ? kResSlots * res_slot_bytes : 0) + bias_bytes + barrier_bytes + 1024;
     }
 };
 
@@ -424,7 +428,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Plan::a_bytes;
     uint8_t* smem_res = smem + kStages * Plan::stage_bytes; // [kResSlots][BLOCK_M][EPI_N], only when has_res
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_res + (has_res ? kResSlots * Plan::res_slot_bytes : 0));
+    float* smem_bias = reinterpret_cast<float*>(smem_res + (has_res ? kResSlots * Plan::res_slot_bytes : 0)); // [kBiasSmemFloats]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + Plan::bias_bytes);
     uint64_t* full_bar = bars;                  // [8]
     uint64_t* empty_bar = bars + 8;             // [8]
     uint64_t* tmem_full_bar = bars + 16;        // [2]
@@ -460,12 +465,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 2; i++)
         {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+            mbar_init(smem_u32(&tmem_empty_bar[i]), kEpilogueWarps);
         }
         for (int i = 0; i < kResSlots; i++)
         {
             mbar_init(smem_u32(&res_full_bar[i]), 1);
-            mbar_init(smem_u32(&res_empty_bar[i]), 4);
+            // readers of one residual slot: the four warps of the half that owns the chunk, or all eight when the tile is a
+            // single 64-column chunk split between the halves
+            mbar_init(smem_u32(&res_empty_bar[i]), (NCHUNK == 1 && SUBS == 2) ? 8 : 4);
         }
         fence_barrier_init();
     }
@@ -473,6 +480,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     {
         tmem_alloc(smem_u32(tmem_base_slot), kTmemCols);
     }
+    // the layer's (padded) bias vector: resident in shared memory when it fits
+    const int bias_count = ((p.N + BLOCK_N - 1) / BLOCK_N) * BLOCK_N;
+    const bool bias_in_smem = bias_count <= kBiasSmemFloats;
+    if (bias_in_smem)
+        for (int i = threadIdx.x; i < bias_count; i += kNumThreads) smem_bias[i] = __ldg(p.bias + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -616,19 +628,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     else
     {
-        // ===================== epilogue (warps 2..5): four independent warps, no CTA-wide synchronisation =====================
-        // Warp w owns TMEM lanes [32*(w&3), +32) = 32 output pixels, one per lane.  Per 32 accumulator columns:
-        // tcgen05.ld (double-buffered in registers) -> +bias (broadcast __ldg) -> +residual (swizzled TMA slot) ->
-        // activation -> 16-bit pack -> two 32-byte st.global.v8 per lane (each a full sector of the pixel's channel run).
+        // ===================== epilogue (warps 2..9): eight independent warps, no CTA-wide synchronisation =====================
+        // Warp w may read TMEM lanes [32*(w&3), +32) = 32 output pixels, one per lane; the two warps of a lane quarter
+        // ("halves") split the tile's columns: alternate 64-column chunks (BLOCK_N >= 128) or the two 32-column groups of
+        // the single chunk (BLOCK_N = 64).  Per 32 accumulator columns: tcgen05.ld -> +bias (shared-memory broadcast,
+        // fetched while the TMEM load is in flight) -> +residual (swizzled TMA slot) -> activation -> 16-bit pack -> two
+        // 32-byte st.global.v8 per lane (each one full sector of the pixel's channel run).
         const int lane_group = warp & 3;
+        const int half = (warp - kEpilogueWarp0) >> 2;
         const int row = lane_group * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        int rslot = 0;
-        uint32_t rphase = 0;
+        uint32_t slots_seen = 0; // residual slots consumed by the CTA so far (both halves count every slot)
         const int n8 = (p.N + 7) & ~7; // the blob's padding lanes up to the next 16-byte unit may be written
         const int act = p.act_type;
+        const float act_p0 = p.act_p0, act_p1 = p.act_p1;
         const int sw_row = (EPI_CHUNKS16 == 8) ? (row & 7) : ((row >> 1) & 3);
+        const bool v8ok = p.v8_ok != 0;
+        const int N = p.N;
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
@@ -649,32 +666,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 row_ok = pix < p.M;
             }
             T* const orow = reinterpret_cast<T*>(p.out) + pix * p.out_cpitch + n0;
-            const float* const brow = p.bias + n0;
+            const float* const brow = bias_in_smem ? (smem_bias + n0) : (p.bias + n0);
 
-            // one 32-column group: r holds the raw accumulators
-            auto process = [&](const int sub, uint32_t(&r)[32], const uint8_t* rbuf, const int slot_sub) {
-                const int col0 = sub * 32; // within the tile
-                float v[32];
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+
+            // 32-column groups of this tile that exist (col < N) ...
+            const int ncols = (N - n0) < BLOCK_N ? (N - n0) : BLOCK_N;
+            const int ngroups = (ncols + 31) >> 5;
+            // ... and the ones this half owns: group g belongs to chunk g / SUBS; chunk parity (or group parity when the
+            // tile is one chunk) selects the half
+            int my_last = -1;
+            for (int g = 0; g < ngroups; g++)
+            {
+                const int owner = (NCHUNK == 1) ? (SUBS == 2 ? (g & 1) : 0) : ((g / SUBS) & 1);
+                if (owner == half) my_last = g;
+            }
+            if (my_last < 0)
+            {
+                // nothing to read for this half: hand the accumulator stage back right away
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+                // single-chunk tiles count all eight warps as readers of the residual slot
+                if (has_res && NCHUNK == 1 && SUBS == 2 && lane == 0) mbar_arrive(smem_u32(&res_empty_bar[slots_seen % kResSlots]));
+            }
+#pragma unroll 1
+            for (int g = 0; g < ngroups; g++)
+            {
+                const int cc = g / SUBS;         // chunk = residual slot of the tile
+                const int slot_sub = g % SUBS;   // which 32-column half of the slot
+                const int owner = (NCHUNK == 1) ? (SUBS == 2 ? (g & 1) : 0) : (cc & 1);
+                if (owner != half) continue;
+                const int col0 = g * 32;
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + (uint32_t)col0, r);
+                // bias of the group while the TMEM load is in flight
+                float bv[32];
 #pragma unroll
                 for (int q = 0; q < 8; q++)
                 {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col0) + q);
-                    v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
-                    v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-                    v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-                    v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+                    const float4 b4 = *reinterpret_cast<const float4*>(brow + col0 + 4 * q);
+                    bv[4 * q + 0] = b4.x;
+                    bv[4 * q + 1] = b4.y;
+                    bv[4 * q + 2] = b4.z;
+                    bv[4 * q + 3] = b4.w;
                 }
+                const uint32_t slot_no = slots_seen + (uint32_t)cc;
+                const int rslot = (int)(slot_no % kResSlots);
+                if (has_res && (slot_sub == 0 || NCHUNK == 1)) mbar_wait(smem_u32(&res_full_bar[rslot]), (slot_no / kResSlots) & 1);
+                tmem_wait_ld_pin(r);
+                if (g == my_last)
+                {
+                    // every column group of this half sits in registers: the accumulator stage can be overwritten
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + bv[j];
                 if (has_res)
                 {
+                    const uint8_t* rbuf = smem_res + rslot * Plan::res_slot_bytes + row * EPI_ROW_BYTES;
 #pragma unroll
                     for (int u = 0; u < 4; u++)
                     {
                         const int unit = slot_sub * 4 + u; // 16-byte unit of the slot row
                         float rv[8];
-                        const uint4 ru = *reinterpret_cast<const uint4*>(rbuf + row * EPI_ROW_BYTES + ((unit ^ sw_row) * 16));
+                        const uint4 ru = *reinterpret_cast<const uint4*>(rbuf + ((unit ^ sw_row) * 16));
                         Pack8<T>::unpack(ru, rv);
 #pragma unroll
                         for (int j = 0; j < 8; j++) v[u * 8 + j] += rv[j];
+                    }
+                    // last read of the slot by this warp: after its final 32-column group (or the only one it owns)
+                    const bool slot_done = (NCHUNK == 1) || (slot_sub == SUBS - 1) || (g + 1 >= ngroups);
+                    if (slot_done)
+                    {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&res_empty_bar[rslot]));
                     }
                 }
                 // activation: one uniform branch per group, not per element
@@ -691,17 +762,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 else if (act == 3)
                 {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fminf(fmaxf(v[j], p.act_p0), p.act_p1);
+                    for (int j = 0; j < 32; j++) v[j] = fminf(fmaxf(v[j], act_p0), act_p1);
                 }
                 else if (act == 2)
                 {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * p.act_p0;
+                    for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * act_p0;
                 }
                 else if (act != 0)
                 {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = apply_activation_call(v[j], act, p.act_p0, p.act_p1);
+                    for (int j = 0; j < 32; j++) v[j] = apply_activation_call(v[j], act, act_p0, act_p1);
                 }
                 uint32_t o[16];
 #pragma unroll
@@ -713,7 +784,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     {
                         const int c = n0 + col0 + h * 16;
                         T* dst = orow + col0 + h * 16;
-                        if (p.v8_ok && c + 16 <= n8)
+                        if (v8ok && c + 16 <= n8)
                             st_global_v8(dst, &o[h * 8]);
                         else
                         {
@@ -722,58 +793,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                     }
                 }
-            };
-            // the accumulator stage goes back to the MMA warp as soon as its last column group sits in registers
-            auto release_tmem = [&]() {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-            };
-
-            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32b_x32(taddr, r0);
-#pragma unroll 1
-            for (int cc = 0; cc < NCHUNK; cc++)
-            {
-                const int c0 = n0 + cc * EPI_N;
-                if (c0 >= p.N) break;
-                const bool v1 = SUBS == 2 && (c0 + 32 < p.N);
-                const bool vnext = (cc + 1 < NCHUNK) && (c0 + EPI_N < p.N);
-                const uint8_t* rbuf = smem_res + rslot * Plan::res_slot_bytes;
-                if (has_res) mbar_wait(smem_u32(&res_full_bar[rslot]), rphase);
-
-                tmem_wait_ld_pin(r0);
-                if (v1)
-                    tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * EPI_N + 32), r1);
-                else if (vnext)
-                    tmem_ld_32x32b_x32(taddr + (uint32_t)((cc + 1) * EPI_N), r0);
-                else
-                    release_tmem();
-                process(cc * SUBS, r0, rbuf, 0);
-                if (SUBS == 2 && v1)
-                {
-                    tmem_wait_ld_pin(r1);
-                    if (vnext)
-                        tmem_ld_32x32b_x32(taddr + (uint32_t)((cc + 1) * EPI_N), r0);
-                    else
-                        release_tmem();
-                    process(cc * SUBS + 1, r1, rbuf, 1);
-                }
-                if (has_res)
-                {
-                    // this warp has read its rows of the slot
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&res_empty_bar[rslot]));
-                    if (++rslot == kResSlots)
-                    {
-                        rslot = 0;
-                        rphase ^= 1;
-                    }
-                }
             }
+            slots_seen += (uint32_t)((ngroups + SUBS - 1) / SUBS);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }

@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q -x --timeout 600 --tb=short > gpurun_out/pytest_kernels.log 2>&1; tail -15 gpurun_out/pytest_kernels.log
+timeout 600 python -m pytest tests/test_nets_gpu.py -q --timeout 500 --tb=short > gpurun_out/pytest_nets.log 2>&1; tail -8 gpurun_out/pytest_nets.log
+for wl in resnet50 mobilenet_v2; do
+ for st in fp16 bf16; do
+  timeout 300 python bench.py --workload $wl --storage $st --layers --no-cpu-baseline > gpurun_out/bench_${wl}_$st.json 2> gpurun_out/bench_${wl}_$st.layers; tail -1 gpurun_out/bench_${wl}_$st.json | cut -c1-120
+ done
+done
