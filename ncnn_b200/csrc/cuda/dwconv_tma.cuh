@@ -22,27 +22,9 @@ namespace dwt {
 constexpr int kConsumers = 256;
 constexpr int kThreads = kConsumers + 32;
 
-// n / d for 0 <= n < 2^31 as one multiply-high and a shift (d >= 1)
-struct FastDiv
-{
-    unsigned int d, m, s;
-};
-
-static inline FastDiv make_fastdiv(unsigned int d)
-{
-    FastDiv f;
-    f.d = d;
-    unsigned int s = 0;
-    while ((1ull << s) < d) s++;
-    f.s = s;
-    f.m = (unsigned int)((((1ull << s) - d) << 32) / d + 1);
-    return f;
-}
-
-__device__ __forceinline__ int fast_div(int n, const FastDiv& f)
-{
-    return (int)((__umulhi((unsigned int)n, f.m) + (unsigned int)n) >> f.s);
-}
+using ncnn_cuda::FastDiv;
+using ncnn_cuda::make_fastdiv;
+using ncnn_cuda::fast_div;
 
 struct Params
 {
@@ -150,16 +132,12 @@ struct Cfg
     static constexpr int cta_budget = 111 * 1024;
     static constexpr int fixed_bytes = 128 /*alignment*/ + 128 /*barriers*/;
     static_assert(CV * TW * TY == kConsumers, "one consumer thread per (channel vector, column, thread row)");
-    // ring depth once the filter bank (10 * cpad floats: 9 taps + bias) is resident
-    static int stages_for(int cpad)
-    {
-        int s = (cta_budget - fixed_bytes - 10 * cpad * 4) / stage_bytes;
-        return s > 4 ? 4 : s;
-    }
-    static int smem_for(int cpad)
-    {
-        return stages_for(cpad) * stage_bytes + 10 * cpad * 4 + fixed_bytes;
-    }
+    // this CTA's slice of the filter bank: 9 taps + bias for its CB channels
+    static constexpr int w_bytes = 10 * CB * 4;
+    static constexpr int stages_fit = (cta_budget - fixed_bytes - w_bytes) / stage_bytes;
+    static constexpr int kStages = stages_fit > 4 ? 4 : stages_fit;
+    static constexpr int smem_bytes = kStages * stage_bytes + w_bytes + fixed_bytes;
+    static_assert(kStages >= 2, "tile too large for a 2-stage ring");
 };
 
 template<typename T, int S, int CV, int TW, int TY, int R>
@@ -169,13 +147,13 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
     constexpr int VEC = C::VEC;
     constexpr int H2 = VEC / 2; // float2 per channel vector
     constexpr int NROWS = (R - 1) * S + 3; // input rows a thread walks
-    const int kStages = p.num_stages;
+    constexpr int kStages = C::kStages;
 
     extern __shared__ uint8_t dw_smem_raw[];
     // (pointer arithmetic, not an integer round trip: keeps the shared address space visible to the compiler -> LDS, not generic LD)
     uint8_t* smem = dw_smem_raw + ((128u - (tc::smem_u32(dw_smem_raw) & 127u)) & 127u);
-    float* smem_w = reinterpret_cast<float*>(smem + kStages * C::stage_bytes); // [9][cpad] taps, then [cpad] bias
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_w + 10 * p.cpad);
+    float* smem_w = reinterpret_cast<float*>(smem + kStages * C::stage_bytes); // [9][CB] taps, then [CB] bias, of this CTA's channel block
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_w + 10 * C::CB);
     uint64_t* empty_bar = full_bar + 4;
 
     const int tid = threadIdx.x;
@@ -189,9 +167,18 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
         }
         tc::fence_barrier_init();
     }
-    // the layer's filter bank and bias: resident for the whole kernel
-    for (int i = tid; i < 9 * p.cpad; i += kThreads) smem_w[i] = p.w[i];
-    for (int i = tid; i < p.cpad; i += kThreads) smem_w[9 * p.cpad + i] = (p.bias && i < p.C) ? p.bias[i] : 0.f;
+    // A CTA works on ONE channel block for its whole life (blockIdx.x % cblocks) and strides over the spatial tiles, so the
+    // CTAs that run side by side cover all channel blocks of the same pixels (shared DRAM pages / L2 lines) and each keeps
+    // just its own 9 x CB filter taps + bias resident.
+    const int cblocks = (int)p.div_cblocks.d;
+    const int cb = blockIdx.x % cblocks;
+    const int sp_first = blockIdx.x / cblocks;
+    const int sp_step = gridDim.x / cblocks;
+    for (int i = tid; i < 10 * C::CB; i += kThreads)
+    {
+        const int t = i / C::CB, c = cb * C::CB + (i - t * C::CB);
+        smem_w[i] = t < 9 ? p.w[(long long)t * p.cpad + c] : (p.bias ? p.bias[c] : 0.f);
+    }
     __syncthreads();
 
     if (tid >= kConsumers)
@@ -201,11 +188,8 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            for (int sp = sp_first; sp < p.n_spatial; sp += sp_step)
             {
-                // channel block fastest: the CTAs working on one spatial tile at the same time share its DRAM pages / L2 lines
-                const int sp = fast_div(tile, p.div_cblocks);
-                const int cb = tile - sp * (int)p.div_cblocks.d;
                 const int b = fast_div(sp, p.div_image);
                 const int t2 = sp - b * (int)p.div_image.d;
                 const int tyi = fast_div(t2, p.div_tiles_x);
@@ -236,17 +220,14 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
     const int thread_off = ((ty * R * S) * C::IW + tx * S) * (CV * 16) + cv * 16;
     const int act = p.act_type;
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+    const int c0 = cb * C::CB + cv * VEC;
+    const float* wc = smem_w + cv * VEC;
+    for (int sp = sp_first; sp < p.n_spatial; sp += sp_step)
     {
-        const int sp = fast_div(tile, p.div_cblocks);
-        const int cb = tile - sp * (int)p.div_cblocks.d;
         const int b = fast_div(sp, p.div_image);
         const int t2 = sp - b * (int)p.div_image.d;
         const int tyi = fast_div(t2, p.div_tiles_x);
         const int txi = t2 - tyi * p.tiles_x;
-        const int c0 = cb * C::CB + cv * VEC;
-        const float* wc = smem_w + c0;
-
         float2 acc[R][H2];
         {
             float2 bias2[H2];
@@ -254,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
             for (int i = 0; i < H2; i += 2)
             {
                 // cpad and c0 are multiples of 4 floats: 16-byte broadcast loads
-                const float4 t = *reinterpret_cast<const float4*>(wc + 9 * p.cpad + 2 * i);
+                const float4 t = *reinterpret_cast<const float4*>(wc + 9 * C::CB + 2 * i);
                 bias2[i] = make_float2(t.x, t.y);
                 bias2[i + 1] = make_float2(t.z, t.w);
             }
@@ -276,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < H2; i += 2)
                 {
-                    const float4 t = *reinterpret_cast<const float4*>(wc + (ky * 3 + kx) * p.cpad + 2 * i);
+                    const float4 t = *reinterpret_cast<const float4*>(wc + (ky * 3 + kx) * C::CB + 2 * i);
                     w[ky][i] = make_float2(t.x, t.y);
                     w[ky][i + 1] = make_float2(t.z, t.w);
                 }
@@ -353,24 +334,25 @@ static int launch_dw_tma(const CUtensorMap& tm, T* out, Params& p, cudaStream_t 
     static bool attr_set = false;
     if (!attr_set)
     {
-        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::cta_budget));
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
         attr_set = true;
     }
-    p.num_stages = C::stages_for(p.cpad);
-    if (p.num_stages < 2) return 1; // filter bank too large to keep resident: generic kernel
     p.tiles_x = (p.outw + TW - 1) / TW;
     p.tiles_y = (p.outh + C::TH - 1) / C::TH;
     const long long n_spatial = (long long)p.n * p.tiles_x * p.tiles_y;
-    const long long num_tiles = n_spatial * (p.C / C::CB);
-    if (num_tiles > 0x3fffffffLL) return 1; // caller falls back
+    const int cblocks = p.C / C::CB;
+    if (n_spatial > 0x3fffffffLL) return 1; // caller falls back
     p.n_spatial = (int)n_spatial;
-    p.num_tiles = (int)num_tiles;
-    p.div_cblocks = make_fastdiv((unsigned int)(p.C / C::CB));
+    p.num_tiles = 0;
+    p.div_cblocks = make_fastdiv((unsigned int)cblocks);
     p.div_image = make_fastdiv((unsigned int)(p.tiles_x * p.tiles_y));
     p.div_tiles_x = make_fastdiv((unsigned int)p.tiles_x);
-    const long long max_ctas = 2LL * sm_count();
-    const int grid = (int)(num_tiles < max_ctas ? num_tiles : max_ctas);
-    kern<<<grid, kThreads, C::smem_for(p.cpad), stream>>>(tm, out, p);
+    // two resident CTAs per SM; the grid is a whole number of channel-block groups
+    long long groups = (2LL * sm_count()) / cblocks;
+    if (groups < 1) groups = 1;
+    if (groups > n_spatial) groups = n_spatial;
+    const int grid = (int)(groups * cblocks);
+    kern<<<grid, kThreads, C::smem_bytes, stream>>>(tm, out, p);
     NC_LAUNCH_CHECK();
     return 0;
 }

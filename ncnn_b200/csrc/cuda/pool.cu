@@ -4,6 +4,9 @@
 // No padded copy is materialised (the reference's copy_make_border sweep disappears): out-of-image taps are
 // skipped for max, and contribute 0 / are excluded from the divisor for avg exactly as :255-343.
 #include "common.cuh"
+#include "pool_tma.cuh"
+
+#include <string.h>
 
 using namespace ncnn_cuda;
 
@@ -121,6 +124,30 @@ template<typename T>
 static int run_pool(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const PoolGeom& g, cudaStream_t stream)
 {
     constexpr int VEC = 16 / sizeof(T);
+    if (g.type == 0 && !g.global && !g.adaptive && g.kw == g.kh && g.sw == g.sh && g.n > 0)
+    {
+        // the bandwidth path: TMA-staged tiles with NaN out-of-bounds fill (pool_tma.cuh); what it declines runs below
+        plt::Call c;
+        c.in = bottom->data;
+        c.out = top->data;
+        c.elemtype = bottom->elemtype;
+        c.C = g.C;
+        c.inw = g.inw;
+        c.inh = g.inh;
+        c.outw = g.outw;
+        c.outh = g.outh;
+        c.n = g.n;
+        c.kernel = g.kw;
+        c.stride = g.sw;
+        c.pad_left = g.pad_left;
+        c.pad_top = g.pad_top;
+        c.in_cpitch = g.in_cpitch;
+        c.out_cpitch = g.out_cpitch;
+        c.in_nstep = g.in_nstep;
+        c.out_nstep = g.out_nstep;
+        int r = plt::forward<T>(c, stream);
+        if (r <= 0) return r;
+    }
     const int cround = ((g.C + VEC - 1) / VEC) * VEC;
     const bool vec_ok = (g.in_cpitch % VEC == 0) && (g.out_cpitch % VEC == 0) && (g.in_nstep % VEC == 0) && (g.out_nstep % VEC == 0)
                         && (((uintptr_t)bottom->data & 15) == 0) && (((uintptr_t)top->data & 15) == 0) && cround <= g.in_cpitch && cround <= g.out_cpitch;

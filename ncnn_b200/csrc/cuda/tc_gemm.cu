@@ -5,6 +5,7 @@
 #include "tc_gemm.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -90,7 +91,7 @@ static CUtensorMapDataType dtype_for(int elemtype)
 }
 
 int tma_encode_tiled_plain(CUtensorMap* map, int elemtype, int rank, const void* ptr, const unsigned long long* gdim, const unsigned long long* gstride_bytes,
-                           const unsigned int* box)
+                           const unsigned int* box, int oob_nan)
 {
     if (!tc_available() || rank < 1 || rank > 5) return -1;
     cuuint64_t gd[5], gs[4];
@@ -106,7 +107,7 @@ int tma_encode_tiled_plain(CUtensorMap* map, int elemtype, int rank, const void*
     // 128-byte promotion: a tile row can be as narrow as 32 bytes of a pixel's channel run; wider promotion only helps when
     // the neighbouring channel blocks are consumed soon after (they are: channel block is the fastest tile index)
     CUresult r = g_encodeTiled(map, dt, (cuuint32_t)rank, (void*)ptr, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, oob_nan ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -1;
 }
 
@@ -221,11 +222,31 @@ void tc_plan_destroy(TcPlan* plan)
 }
 
 // ---------------------------------------------------------------- A_ROWS geometry
+// The small-channel stem variant reads an "unfolded rows" copy of the input, U[n][Hp][outw][krow]: for every padded input
+// row and every OUTPUT column the kw' x Cp window that column needs from that row (krow = wp * cp 16-bit values = 32/64/128
+// bytes).  It is written once per call by rows_unfold_kernel (fully coalesced 16-byte stores) and makes every A tile of the
+// implicit GEMM one dense 128 x krow box -- a strided, overlapping-window TMA box over the raw image costs one L2 request per
+// 32..64-byte window and was the whole run time of the stems.
 struct RowsGeom
 {
-    int Lp, Hp, Wpitch; // physical left pad, padded rows, padded row pitch (pixels)
+    int Lp, Hp; // physical left pad (pixels), padded rows
+    int Wpitch; // row pitch (pixels) of the plain zero-padded copy (unfold = 0)
+    int unfold;
     size_t bytes;
 };
+
+// experiment switch: NCNN_B200_STEM_UNFOLD=0 keeps a plain zero-padded [n][Hp][Wpitch][Cp] copy and lets the TMA gather
+// the overlapping windows (strided box); default 1 = unfolded rows (dense boxes)
+static int stem_unfold()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* e = getenv("NCNN_B200_STEM_UNFOLD");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
 
 static bool rows_applicable(const TcPlan* plan, const TcConvCall* c, RowsGeom* g)
 {
@@ -234,15 +255,17 @@ static bool rows_applicable(const TcPlan* plan, const TcConvCall* c, RowsGeom* g
     const int cp = plan->rows_cp, wp = plan->rows_wp;
     if (cp == 4 && (((c->pad_left + plan->rows_shift) & 1) || (c->stride_w & 1))) return false;
     g->Lp = c->pad_left + plan->rows_shift;
+    int need_h = c->stride_h * (c->outh - 1) + (c->kernel_h - 1) * c->dil_h + 1;
+    int hp = c->pad_top + c->inh > need_h ? c->pad_top + c->inh : need_h;
+    g->Hp = hp;
+    g->unfold = stem_unfold();
     int need_w = c->stride_w * (c->outw - 1) + wp;
     int wpitch = g->Lp + c->inw > need_w ? g->Lp + c->inw : need_w;
     if (cp == 4) wpitch = (wpitch + 1) & ~1; // 16-byte row pitch
-    int need_h = c->stride_h * (c->outh - 1) + (c->kernel_h - 1) * c->dil_h + 1;
-    int hp = c->pad_top + c->inh > need_h ? c->pad_top + c->inh : need_h;
     g->Wpitch = wpitch;
-    g->Hp = hp;
-    g->bytes = (size_t)c->n * hp * wpitch * cp * 2;
+    g->bytes = g->unfold ? (size_t)c->n * hp * c->outw * wp * cp * 2 : (size_t)c->n * hp * wpitch * cp * 2;
     if ((long long)c->n * c->outh > 0x7fffffffLL) return false;
+    if ((long long)c->n * hp * c->outw * (wp * cp / 8) > 0x7fffffff00LL) return false;
     return true;
 }
 
@@ -280,6 +303,48 @@ __global__ void __launch_bounds__(256) rows_pack_kernel(const uint16_t* __restri
             *reinterpret_cast<uint2*>(out + i * CP) = *reinterpret_cast<const uint2*>(v);
         else
             *reinterpret_cast<uint4*>(out + i * CP) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+// NHWC blob (in_cpitch 16-bit channels per pixel, 16-byte aligned pixels) -> U[n][Hp][outw][wp*CP]; one thread per 16-byte
+// chunk of U = 8/CP consecutive window pixels.  Pixels outside the image are zeros (the layer's padding).
+template<int CP>
+__global__ void __launch_bounds__(256) rows_unfold_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int inh, int inw, int inch, int in_cpitch,
+                                                          int Hp, int outw, int wp, int stride_w, int Lp, int pad_top)
+{
+    constexpr int PPC = 8 / CP;          // pixels per 16-byte chunk
+    const int chunks = wp / PPC;         // chunks per window
+    const long long total = (long long)n * Hp * outw * chunks;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const int q = (int)(i % chunks);
+        long long r = i / chunks;
+        const int ox = (int)(r % outw);
+        r /= outw;
+        const int y = (int)(r % Hp);
+        const int b = (int)(r / Hp);
+        const int sy = y - pad_top;
+        uint16_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = 0;
+        if (sy >= 0 && sy < inh)
+        {
+#pragma unroll
+            for (int pp = 0; pp < PPC; pp++)
+            {
+                const int sx = ox * stride_w - Lp + q * PPC + pp;
+                if (sx >= 0 && sx < inw)
+                {
+                    // a pixel of the source blob is at least 16 bytes (cpitch >= 8): one vector load, keep the first CP lanes
+                    const uint4 px = *reinterpret_cast<const uint4*>(in + ((long long)b * inh * inw + (long long)sy * inw + sx) * in_cpitch);
+                    const uint16_t* ph = reinterpret_cast<const uint16_t*>(&px);
+#pragma unroll
+                    for (int k = 0; k < CP; k++)
+                        if (k < inch) v[pp * CP + k] = ph[k];
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(v);
     }
 }
 
@@ -381,23 +446,48 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     if (use_rows)
     {
         const int cp = plan->rows_cp;
-        // zero-padded small-channel copy of the input
-        const long long total = (long long)c->n * rg.Hp * rg.Wpitch;
-        int grid = grid_for(total, 256, 16);
-        if (cp == 4)
-            rows_pack_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
-                                                         c->pad_top);
+        const int krow = plan->rows_wp * cp;
+        CUresult r;
+        if (rg.unfold)
+        {
+            // unfolded-rows copy of the input
+            const long long total = (long long)c->n * rg.Hp * c->outw * (krow / 8);
+            int grid = grid_for(total, 256, 16);
+            if (cp == 4)
+                rows_unfold_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, c->outw,
+                                                               plan->rows_wp, c->stride_w, rg.Lp, c->pad_top);
+            else
+                rows_unfold_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, c->outw,
+                                                               plan->rows_wp, c->stride_w, rg.Lp, c->pad_top);
+            NC_LAUNCH_CHECK();
+            // dims: (window elements, output column, padded row, image), dense
+            cuuint64_t gdim[4] = {(cuuint64_t)krow, (cuuint64_t)c->outw, (cuuint64_t)rg.Hp, (cuuint64_t)c->n};
+            cuuint64_t gstride[3] = {(cuuint64_t)krow * 2, (cuuint64_t)c->outw * krow * 2, (cuuint64_t)rg.Hp * c->outw * krow * 2};
+            cuuint32_t box[4] = {(cuuint32_t)plan->rows_block_k, (cuuint32_t)tc::BLOCK_M, 1, 1};
+            cuuint32_t estride[4] = {1, 1, 1, 1};
+            r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, c->workspace, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_for(plan->rows_block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         else
-            rows_pack_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
-                                                         c->pad_top);
-        NC_LAUNCH_CHECK();
-        // dims: (window elements, output column, padded row, image); the column stride is the conv stride -> overlapping windows
-        cuuint64_t gdim[4] = {(cuuint64_t)(plan->rows_wp * cp), (cuuint64_t)c->outw, (cuuint64_t)rg.Hp, (cuuint64_t)c->n};
-        cuuint64_t gstride[3] = {(cuuint64_t)c->stride_w * cp * 2, (cuuint64_t)rg.Wpitch * cp * 2, (cuuint64_t)rg.Hp * rg.Wpitch * cp * 2};
-        cuuint32_t box[4] = {(cuuint32_t)plan->rows_block_k, (cuuint32_t)tc::BLOCK_M, 1, 1};
-        cuuint32_t estride[4] = {1, 1, 1, 1};
-        CUresult r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, c->workspace, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   swizzle_for(plan->rows_block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        {
+            // zero-padded small-channel copy of the input; the TMA box gathers the overlapping windows
+            const long long total = (long long)c->n * rg.Hp * rg.Wpitch;
+            int grid = grid_for(total, 256, 16);
+            if (cp == 4)
+                rows_pack_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch,
+                                                             rg.Lp, c->pad_top);
+            else
+                rows_pack_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch,
+                                                             rg.Lp, c->pad_top);
+            NC_LAUNCH_CHECK();
+            // dims: (window elements, output column, padded row, image); the column stride is the conv stride -> overlapping windows
+            cuuint64_t gdim[4] = {(cuuint64_t)krow, (cuuint64_t)c->outw, (cuuint64_t)rg.Hp, (cuuint64_t)c->n};
+            cuuint64_t gstride[3] = {(cuuint64_t)c->stride_w * cp * 2, (cuuint64_t)rg.Wpitch * cp * 2, (cuuint64_t)rg.Hp * rg.Wpitch * cp * 2};
+            cuuint32_t box[4] = {(cuuint32_t)plan->rows_block_k, (cuuint32_t)tc::BLOCK_M, 1, 1};
+            cuuint32_t estride[4] = {1, 1, 1, 1};
+            r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, c->workspace, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_for(plan->rows_block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (r == CUDA_SUCCESS)
         {
             amode = tc::A_ROWS;
@@ -486,6 +576,12 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     p.act_p0 = c->act_p0;
     p.act_p1 = c->act_p1;
     p.v8_ok = (c->out_cpitch % 16 == 0) && (((uintptr_t)c->out & 31) == 0);
+    p.taps_h = c->tiled ? 1 : c->kernel_h;
+    p.div_n_blocks = make_fastdiv((unsigned int)((plan->outch + plan->block_n - 1) / plan->block_n));
+    p.div_opix = make_fastdiv((unsigned int)(c->outw * c->outh > 0 ? c->outw * c->outh : 1));
+    p.div_outw = make_fastdiv((unsigned int)(c->outw > 0 ? c->outw : 1));
+    p.div_chunks = make_fastdiv((unsigned int)p.chunks_per_row);
+    p.div_outh = make_fastdiv((unsigned int)(c->outh > 0 ? c->outh : 1));
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row : (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
     const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);

@@ -22,6 +22,28 @@
 
 namespace ncnn_cuda {
 
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (d >= 1)
+struct FastDiv
+{
+    unsigned int d, m, s;
+};
+
+static inline FastDiv make_fastdiv(unsigned int d)
+{
+    FastDiv f;
+    f.d = d;
+    unsigned int s = 0;
+    while ((1ull << s) < d) s++;
+    f.s = s;
+    f.m = (unsigned int)((((1ull << s) - d) << 32) / d + 1);
+    return f;
+}
+
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f)
+{
+    return (int)((__umulhi((unsigned int)n, f.m) + (unsigned int)n) >> f.s);
+}
+
 namespace tc {
 
 constexpr int BLOCK_M = 128;
@@ -52,6 +74,9 @@ struct Params
     float act_p0, act_p1;
     int num_stages; // depth of the A/B ring (SmemPlan::stages_for(residual != NULL))
     int v8_ok;      // output rows are 32-byte aligned: 256-bit stores
+    int taps_h;     // kernel_h (A_IM2COL / A_ROWS k-block nest: filter row, filter column, channel slab)
+    // tile decode without integer division
+    FastDiv div_n_blocks, div_opix, div_outw, div_chunks, div_outh;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -98,6 +123,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             __trap();
         }
     }
+}
+
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void fence_barrier_init()
@@ -313,6 +352,10 @@ struct SmemPlan
     // the only epilogue staging is the fused residual: it arrives by TMA in EPI_N-column slots, a ring of kResSlots.
     static constexpr int EPI_N = BLOCK_N < 64 ? BLOCK_N : 64;
     static constexpr int kResSlots = 4;
+    static constexpr int kMaxStages = 16;
+    // accumulator stages in TMEM: as many as 512 columns hold (the MMA -> epilogue -> MMA round trip is a latency chain;
+    // with few k-blocks per tile it needs more than two tiles in flight)
+    static constexpr int kAccStages = (512 / BLOCK_N) > 8 ? 8 : (512 / BLOCK_N);
     static constexpr int res_slot_bytes = BLOCK_M * EPI_N * 2;
     static constexpr int barrier_bytes = 512;
     static constexpr int bias_bytes = kBiasSmemFloats * 4;
@@ -320,7 +363,7 @@ struct SmemPlan
     static constexpr int stages_for(bool has_res)
     {
         int s = (budget - (has_res ? kResSlots * res_slot_bytes : 0)) / stage_bytes;
-        return s > 8 ? 8 : s;
+        return s > kMaxStages ? kMaxStages : s;
     }
     static constexpr int total_for(bool has_res)
     {
@@ -415,7 +458,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     constexpr int NCHUNK = BLOCK_N / EPI_N;    // residual slots per tile
     constexpr int SUBS = EPI_N / 32;           // 32-column TMEM loads per slot (1 or 2)
     constexpr int kResSlots = Plan::kResSlots;
-    constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N; // power of two for BLOCK_N in {16..256}
+    constexpr int kAccStages = Plan::kAccStages;
+    constexpr uint32_t kTmemCols = kAccStages * BLOCK_N; // 512 (256 for BLOCK_N = 32): a power of two
     // swizzle of the residual staging tiles: rows of EPI_N 16-bit values = 128 / 64 bytes
     constexpr int EPI_ROW_BYTES = EPI_N * 2;
     constexpr int EPI_CHUNKS16 = EPI_ROW_BYTES / 16; // 16-byte units per row: 8 / 4
@@ -430,13 +474,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* smem_res = smem + kStages * Plan::stage_bytes; // [kResSlots][BLOCK_M][EPI_N], only when has_res
     float* smem_bias = reinterpret_cast<float*>(smem_res + (has_res ? kResSlots * Plan::res_slot_bytes : 0)); // [kBiasSmemFloats]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + Plan::bias_bytes);
-    uint64_t* full_bar = bars;                  // [8]
-    uint64_t* empty_bar = bars + 8;             // [8]
-    uint64_t* tmem_full_bar = bars + 16;        // [2]
-    uint64_t* tmem_empty_bar = bars + 18;       // [2]
-    uint64_t* res_full_bar = bars + 20;         // [kResSlots]
-    uint64_t* res_empty_bar = bars + 24;        // [kResSlots]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    uint64_t* full_bar = bars;                  // [16]
+    uint64_t* empty_bar = bars + 16;            // [16]
+    uint64_t* tmem_full_bar = bars + 32;        // [8]
+    uint64_t* tmem_empty_bar = bars + 40;       // [8]
+    uint64_t* res_full_bar = bars + 48;         // [kResSlots]
+    uint64_t* res_empty_bar = bars + 52;        // [kResSlots]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 56);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -462,7 +506,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(smem_u32(&full_bar[i]), 1);
             mbar_init(smem_u32(&empty_bar[i]), 1);
         }
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < kAccStages; i++)
         {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[i]), kEpilogueWarps);
@@ -495,63 +539,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0)
         {
             // ===================== TMA producer =====================
+            // One lane issues every load of the CTA.  Its instruction stream is the critical path of small-K tiles, so the
+            // loop carries no integer division: tiles are decoded with multiply-shift, k-blocks by nested counters.
             int stage = 0;
             uint32_t phase = 0;
             int rslot = 0;
             uint32_t rphase = 0;
+            const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
+            const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
             {
-                const int n_blk = tile % num_n_blocks;
-                const int m_blk = tile / num_n_blocks;
-                const long long m0 = (long long)m_blk * BLOCK_M;
+                const int m_blk = fast_div(tile, p.div_n_blocks);
+                const int n_blk = tile - m_blk * num_n_blocks;
+                const int n_coord = n_blk * BLOCK_N;
                 int base_w = 0, base_h = 0, base_n = 0;
+                int m0 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
                 if (AMODE == A_IM2COL)
                 {
-                    const int opix = p.outw * p.outh;
-                    base_n = (int)(m0 / opix);
-                    int rem = (int)(m0 - (long long)base_n * opix);
-                    int oy = rem / p.outw;
-                    int ox = rem - oy * p.outw;
+                    base_n = fast_div(m0, p.div_opix);
+                    const int rem = m0 - base_n * (int)p.div_opix.d;
+                    const int oy = fast_div(rem, p.div_outw);
+                    const int ox = rem - oy * p.outw;
                     base_w = ox * p.stride_w - p.pad_left;
                     base_h = oy * p.stride_h - p.pad_top;
                 }
                 else if (AMODE == A_ROWS)
                 {
-                    const int chunk = m_blk % p.chunks_per_row;
-                    const int row = m_blk / p.chunks_per_row; // img * outh + oy
-                    base_n = row / p.outh;
+                    const int row = fast_div(m_blk, p.div_chunks); // img * outh + oy
+                    const int chunk = m_blk - row * p.chunks_per_row;
+                    base_n = fast_div(row, p.div_outh);
                     base_h = (row - base_n * p.outh) * p.stride_h; // physical row of filter row 0 (top padding is materialised)
                     base_w = chunk * BLOCK_M;                      // first output column of the chunk
                 }
-                for (int kb = 0; kb < p.num_k_blocks; kb++)
-                {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                auto load_kblock = [&](int kcoord_b, auto&& issue_a) {
+                    mbar_wait(empty0 + stage * 8, phase ^ 1);
+                    const uint32_t fb = full0 + stage * 8;
                     mbar_expect_tx(fb, Plan::stage_bytes);
-                    const int tap = kb / p.cblocks;
-                    const int cb = kb - tap * p.cblocks;
-                    if (AMODE == A_IM2COL)
-                    {
-                        const int ky = tap / p.taps_w;
-                        const int kx = tap - ky * p.taps_w;
-                        tma_load_im2col_4d(smem_u32(smem_a + stage * Plan::a_bytes), &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n,
-                                           (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
-                    }
-                    else if (AMODE == A_ROWS)
-                    {
-                        // tap = filter row; the K slab of that row is cb * BLOCK_K .. +BLOCK_K of the (pixels x Cp) window
-                        tma_load_4d(smem_u32(smem_a + stage * Plan::a_bytes), &tmap_a, fb, cb * BLOCK_K, base_w, base_h + tap * p.dil_h, base_n);
-                    }
-                    else
-                    {
-                        tma_load_2d(smem_u32(smem_a + stage * Plan::a_bytes), &tmap_a, fb, kb * BLOCK_K, (int)m0);
-                    }
-                    tma_load_2d(smem_u32(smem_b + stage * Plan::b_bytes), &tmap_b, fb, kb * BLOCK_K, n_blk * BLOCK_N);
+                    issue_a(smem_a0 + stage * Plan::a_bytes, fb);
+                    tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord_b, n_coord);
                     if (++stage == kStages)
                     {
                         stage = 0;
                         phase ^= 1;
                     }
+                };
+                if (AMODE == A_IM2COL)
+                {
+                    int kcoord = 0;
+                    for (int ky = 0; ky < p.taps_h; ky++)
+                        for (int kx = 0; kx < p.taps_w; kx++)
+                            for (int cb = 0; cb < p.cblocks; cb++, kcoord += BLOCK_K)
+                                load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) {
+                                    tma_load_im2col_4d(dst, &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
+                                });
+                }
+                else if (AMODE == A_ROWS)
+                {
+                    // k-block = (filter row, K slab of that row's kw' x Cp window)
+                    int kcoord = 0;
+                    for (int ky = 0; ky < p.taps_h; ky++)
+                        for (int cb = 0; cb < p.cblocks; cb++, kcoord += BLOCK_K)
+                            load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) { tma_load_4d(dst, &tmap_a, fb, cb * BLOCK_K, base_w, base_h + ky * p.dil_h, base_n); });
+                }
+                else
+                {
+                    for (int kb = 0, kcoord = 0; kb < p.num_k_blocks; kb++, kcoord += BLOCK_K)
+                        load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) { tma_load_2d(dst, &tmap_a, fb, kcoord, m0); });
                 }
                 if (has_res)
                 {
@@ -560,8 +613,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     int c1, c2;
                     if (AMODE == A_ROWS)
                     {
-                        c1 = (m_blk % p.chunks_per_row) * BLOCK_M;
-                        c2 = m_blk / p.chunks_per_row;
+                        c2 = fast_div(m_blk, p.div_chunks);
+                        c1 = (m_blk - c2 * p.chunks_per_row) * BLOCK_M;
                     }
                     else
                     {
@@ -588,41 +641,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     else if (warp == 1)
     {
-        if (lane == 0)
+        // ===================== MMA issuer =====================
+        // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform registers); one elected
+        // lane issues tcgen05.mma / tcgen05.commit.
+        constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M, BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
+        const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M, BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < p.num_k_blocks; kb++)
             {
-                mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+                mbar_wait(full0 + stage * 8, phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < p.num_k_blocks; kb++)
+                if (elect_one())
                 {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase);
-                    tc_fence_after();
-                    const uint64_t adesc = make_smem_desc<BLOCK_K>(smem_u32(smem_a + stage * Plan::a_bytes));
-                    const uint64_t bdesc = make_smem_desc<BLOCK_K>(smem_u32(smem_b + stage * Plan::b_bytes));
+                    const uint64_t adesc = make_smem_desc<BLOCK_K>(smem_a0 + stage * Plan::a_bytes);
+                    const uint64_t bdesc = make_smem_desc<BLOCK_K>(smem_b0 + stage * Plan::b_bytes);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; k++)
                     {
                         // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
                         umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
                     }
-                    umma_commit(smem_u32(&empty_bar[stage])); // frees the smem slot when these MMAs retire
+                    umma_commit(empty0 + stage * 8); // frees the smem slot when these MMAs retire
                     if (kb == p.num_k_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
-                    if (++stage == kStages)
-                    {
-                        stage = 0;
-                        phase ^= 1;
-                    }
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == kStages)
+                {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == kAccStages)
+            {
+                acc = 0;
+                acc_phase ^= 1;
             }
         }
     }
@@ -649,16 +710,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
-            const int n_blk = tile % num_n_blocks;
-            const int m_blk = tile / num_n_blocks;
+            const int m_blk = fast_div(tile, p.div_n_blocks);
+            const int n_blk = tile - m_blk * num_n_blocks;
             const int n0 = n_blk * BLOCK_N;
             long long pix;
             bool row_ok;
             if (AMODE == A_ROWS)
             {
-                const int col = (m_blk % p.chunks_per_row) * BLOCK_M + row;
+                const int orow_idx = fast_div(m_blk, p.div_chunks);
+                const int col = (m_blk - orow_idx * p.chunks_per_row) * BLOCK_M + row;
                 row_ok = col < p.outw;
-                pix = (long long)(m_blk / p.chunks_per_row) * p.outw + col;
+                pix = (long long)orow_idx * p.outw + col;
             }
             else
             {
@@ -795,8 +857,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
             slots_seen += (uint32_t)((ngroups + SUBS - 1) / SUBS);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == kAccStages)
+            {
+                acc = 0;
+                acc_phase ^= 1;
+            }
         }
     }
 
@@ -836,8 +901,9 @@ struct TcPlan
 int tc_available(); // 1 when the driver exposes cuTensorMapEncode* and the device is sm_100
 // cuTensorMapEncodeTiled for the bandwidth kernels (depthwise, pooling): channel-innermost blob, no swizzle, zero OOB fill.
 // rank <= 5; gstride has rank-1 entries (bytes, multiples of 16).  Returns 0 / -1.
+// oob_nan: out-of-bounds elements read as NaN instead of zero (max pooling: NaN never wins a NaN-ignoring maximum)
 int tma_encode_tiled_plain(CUtensorMap* map, int elemtype, int rank, const void* ptr, const unsigned long long* gdim, const unsigned long long* gstride_bytes,
-                           const unsigned int* box);
+                           const unsigned int* box, int oob_nan = 0);
 int tc_pick_block_k(int inch);
 int tc_pick_block_n(int outch);
 struct ncnn_cuda_conv2d_desc_fwd; // (documentation only)

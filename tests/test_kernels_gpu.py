@@ -319,6 +319,18 @@ def test_pooling_grid(ref, elemtype):
     run_pool(ref, rng, elemtype, 2, 20, 20, 256, 0, 5, 1, 2, 1)
 
 
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_pooling_max_tma_shapes(ref, elemtype):
+    """max pooling on the TMA-staged tile kernel (pool_tma.cuh): every channel-block width, maps that are not a multiple of
+    the tile, windows hanging over every edge (NaN out-of-bounds fill must never win), more tiles than ring stages"""
+    rng = np.random.default_rng(22)
+    for (w, h, c, k, s, pad, mode) in [(112, 112, 64, 3, 2, 0, 0), (57, 33, 128, 2, 2, 0, 0), (56, 56, 96, 3, 2, 1, 0), (27, 27, 256, 3, 2, 0, 0),
+                                       (20, 20, 256, 5, 1, 2, 1), (40, 23, 48, 5, 1, 2, 1), (14, 14, 512, 2, 2, 0, 0), (31, 29, 16, 3, 1, 1, 1),
+                                       (13, 13, 64, 3, 2, 0, 2), (15, 15, 32, 2, 1, 0, 3)]:
+        run_pool(ref, rng, elemtype, 3, w, h, c, 0, k, s, pad, mode)
+    run_pool(ref, rng, elemtype, 24, 112, 112, 64, 0, 3, 2, 0, 0)
+
+
 # ------------------------------------------------------------------------------------------ InnerProduct
 def run_fc(ref, rng, elemtype, n, in_shape, num_output, bias, act_type):
     L = cabi.lib()
