@@ -222,50 +222,37 @@ void tc_plan_destroy(TcPlan* plan)
 }
 
 // ---------------------------------------------------------------- A_ROWS geometry
-// The small-channel stem variant reads an "unfolded rows" copy of the input, U[n][Hp][outw][krow]: for every padded input
-// row and every OUTPUT column the kw' x Cp window that column needs from that row (krow = wp * cp 16-bit values = 32/64/128
-// bytes).  It is written once per call by rows_unfold_kernel (fully coalesced 16-byte stores) and makes every A tile of the
-// implicit GEMM one dense 128 x krow box -- a strided, overlapping-window TMA box over the raw image costs one L2 request per
-// 32..64-byte window and was the whole run time of the stems.
+// The small-channel stem variant (tc_gemm.cuh, A_ROWS) reads a zero-padded copy of the input, [n][Hp][Wpitch][Cp] with
+// Cp = 4 (stride 2) or 8 (stride 1) 16-bit channels per pixel so that the windows of consecutive output columns start 16
+// bytes apart; rows_pack_kernel writes it once per call.
 struct RowsGeom
 {
-    int Lp, Hp; // physical left pad (pixels), padded rows
-    int Wpitch; // row pitch (pixels) of the plain zero-padded copy (unfold = 0)
-    int unfold;
+    int Lp, Hp, Wpitch; // physical left pad, padded rows, padded row pitch (pixels)
+    int seg_bytes;      // one tile's row segment: 127 windows' starts + one window
     size_t bytes;
 };
-
-// experiment switch: NCNN_B200_STEM_UNFOLD=0 keeps a plain zero-padded [n][Hp][Wpitch][Cp] copy and lets the TMA gather
-// the overlapping windows (strided box); default 1 = unfolded rows (dense boxes)
-static int stem_unfold()
-{
-    static int v = -1;
-    if (v < 0)
-    {
-        const char* e = getenv("NCNN_B200_STEM_UNFOLD");
-        v = e ? atoi(e) : 1;
-    }
-    return v;
-}
 
 static bool rows_applicable(const TcPlan* plan, const TcConvCall* c, RowsGeom* g)
 {
     if (!plan->rows_ok || c->tiled || c->residual) return false;
-    if (c->dil_w != 1) return false;
+    if (c->dil_w != 1 || plan->rows_cblocks != 1) return false;
     const int cp = plan->rows_cp, wp = plan->rows_wp;
-    if (cp == 4 && (((c->pad_left + plan->rows_shift) & 1) || (c->stride_w & 1))) return false;
+    if (c->stride_w * cp * 2 != 16) return false;       // consecutive windows exactly one 16-byte core-matrix row apart
+    if (plan->outch > plan->block_n) return false;      // one n-block: the weights stay resident
+    if (cp == 4 && ((c->pad_left + plan->rows_shift) & 1)) return false;
     g->Lp = c->pad_left + plan->rows_shift;
-    int need_h = c->stride_h * (c->outh - 1) + (c->kernel_h - 1) * c->dil_h + 1;
-    int hp = c->pad_top + c->inh > need_h ? c->pad_top + c->inh : need_h;
-    g->Hp = hp;
-    g->unfold = stem_unfold();
     int need_w = c->stride_w * (c->outw - 1) + wp;
     int wpitch = g->Lp + c->inw > need_w ? g->Lp + c->inw : need_w;
     if (cp == 4) wpitch = (wpitch + 1) & ~1; // 16-byte row pitch
+    int need_h = c->stride_h * (c->outh - 1) + (c->kernel_h - 1) * c->dil_h + 1;
+    int hp = c->pad_top + c->inh > need_h ? c->pad_top + c->inh : need_h;
     g->Wpitch = wpitch;
-    g->bytes = g->unfold ? (size_t)c->n * hp * c->outw * wp * cp * 2 : (size_t)c->n * hp * wpitch * cp * 2;
+    g->Hp = hp;
+    g->seg_bytes = 16 * (tc::BLOCK_M - 1) + wp * cp * 2;
+    // the last chunk of a row reads up to one segment past its first column: slack behind the last row
+    g->bytes = (size_t)c->n * hp * wpitch * cp * 2 + (size_t)g->seg_bytes + 16 * tc::BLOCK_M;
     if ((long long)c->n * c->outh > 0x7fffffffLL) return false;
-    if ((long long)c->n * hp * c->outw * (wp * cp / 8) > 0x7fffffff00LL) return false;
+    if ((long long)hp * wpitch * cp * 2 > 0x7fffffffLL) return false;
     return true;
 }
 
@@ -306,48 +293,6 @@ __global__ void __launch_bounds__(256) rows_pack_kernel(const uint16_t* __restri
     }
 }
 
-// NHWC blob (in_cpitch 16-bit channels per pixel, 16-byte aligned pixels) -> U[n][Hp][outw][wp*CP]; one thread per 16-byte
-// chunk of U = 8/CP consecutive window pixels.  Pixels outside the image are zeros (the layer's padding).
-template<int CP>
-__global__ void __launch_bounds__(256) rows_unfold_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int inh, int inw, int inch, int in_cpitch,
-                                                          int Hp, int outw, int wp, int stride_w, int Lp, int pad_top)
-{
-    constexpr int PPC = 8 / CP;          // pixels per 16-byte chunk
-    const int chunks = wp / PPC;         // chunks per window
-    const long long total = (long long)n * Hp * outw * chunks;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    {
-        const int q = (int)(i % chunks);
-        long long r = i / chunks;
-        const int ox = (int)(r % outw);
-        r /= outw;
-        const int y = (int)(r % Hp);
-        const int b = (int)(r / Hp);
-        const int sy = y - pad_top;
-        uint16_t v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = 0;
-        if (sy >= 0 && sy < inh)
-        {
-#pragma unroll
-            for (int pp = 0; pp < PPC; pp++)
-            {
-                const int sx = ox * stride_w - Lp + q * PPC + pp;
-                if (sx >= 0 && sx < inw)
-                {
-                    // a pixel of the source blob is at least 16 bytes (cpitch >= 8): one vector load, keep the first CP lanes
-                    const uint4 px = *reinterpret_cast<const uint4*>(in + ((long long)b * inh * inw + (long long)sy * inw + sx) * in_cpitch);
-                    const uint16_t* ph = reinterpret_cast<const uint16_t*>(&px);
-#pragma unroll
-                    for (int k = 0; k < CP; k++)
-                        if (k < inch) v[pp * CP + k] = ph[k];
-                }
-            }
-        }
-        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(v);
-    }
-}
-
 int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
 {
     if (!plan->w_packed) return 0;
@@ -380,14 +325,29 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     static bool attr_set = false;
     if (!attr_set)
     {
-        constexpr int max_smem = Plan::total_for(false) > Plan::total_for(true) ? Plan::total_for(false) : Plan::total_for(true);
-        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const bool has_res = p.residual != 0;
-    p.num_stages = Plan::stages_for(has_res);
+    int smem_bytes;
+    if (AMODE == tc::A_ROWS)
+    {
+        const int aux = p.taps_h * Plan::b_bytes; // resident weights
+        p.num_stages = Plan::stages_with_aux(aux);
+        smem_bytes = Plan::total_with_aux(aux);
+        if (p.num_stages < 2)
+        {
+            set_last_error_msg("tc_gemm: stem weights do not fit in shared memory");
+            return -1;
+        }
+    }
+    else
+    {
+        p.num_stages = Plan::stages_for(has_res);
+        smem_bytes = Plan::total_for(has_res);
+    }
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, tc::kNumThreads, Plan::total_for(has_res), stream>>>(ta, tb, tr, p);
+    kern<<<grid, tc::kNumThreads, smem_bytes, stream>>>(ta, tb, tr, p);
     NC_LAUNCH_CHECK();
     return 0;
 }
@@ -446,57 +406,27 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     if (use_rows)
     {
         const int cp = plan->rows_cp;
-        const int krow = plan->rows_wp * cp;
-        CUresult r;
-        if (rg.unfold)
-        {
-            // unfolded-rows copy of the input
-            const long long total = (long long)c->n * rg.Hp * c->outw * (krow / 8);
-            int grid = grid_for(total, 256, 16);
-            if (cp == 4)
-                rows_unfold_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, c->outw,
-                                                               plan->rows_wp, c->stride_w, rg.Lp, c->pad_top);
-            else
-                rows_unfold_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, c->outw,
-                                                               plan->rows_wp, c->stride_w, rg.Lp, c->pad_top);
-            NC_LAUNCH_CHECK();
-            // dims: (window elements, output column, padded row, image), dense
-            cuuint64_t gdim[4] = {(cuuint64_t)krow, (cuuint64_t)c->outw, (cuuint64_t)rg.Hp, (cuuint64_t)c->n};
-            cuuint64_t gstride[3] = {(cuuint64_t)krow * 2, (cuuint64_t)c->outw * krow * 2, (cuuint64_t)rg.Hp * c->outw * krow * 2};
-            cuuint32_t box[4] = {(cuuint32_t)plan->rows_block_k, (cuuint32_t)tc::BLOCK_M, 1, 1};
-            cuuint32_t estride[4] = {1, 1, 1, 1};
-            r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, c->workspace, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              swizzle_for(plan->rows_block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        }
+        // zero-padded small-channel copy of the input
+        const long long total = (long long)c->n * rg.Hp * rg.Wpitch;
+        int grid = grid_for(total, 256, 16);
+        if (cp == 4)
+            rows_pack_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
+                                                         c->pad_top);
         else
-        {
-            // zero-padded small-channel copy of the input; the TMA box gathers the overlapping windows
-            const long long total = (long long)c->n * rg.Hp * rg.Wpitch;
-            int grid = grid_for(total, 256, 16);
-            if (cp == 4)
-                rows_pack_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch,
-                                                             rg.Lp, c->pad_top);
-            else
-                rows_pack_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch,
-                                                             rg.Lp, c->pad_top);
-            NC_LAUNCH_CHECK();
-            // dims: (window elements, output column, padded row, image); the column stride is the conv stride -> overlapping windows
-            cuuint64_t gdim[4] = {(cuuint64_t)krow, (cuuint64_t)c->outw, (cuuint64_t)rg.Hp, (cuuint64_t)c->n};
-            cuuint64_t gstride[3] = {(cuuint64_t)c->stride_w * cp * 2, (cuuint64_t)rg.Wpitch * cp * 2, (cuuint64_t)rg.Hp * rg.Wpitch * cp * 2};
-            cuuint32_t box[4] = {(cuuint32_t)plan->rows_block_k, (cuuint32_t)tc::BLOCK_M, 1, 1};
-            cuuint32_t estride[4] = {1, 1, 1, 1};
-            r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, c->workspace, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              swizzle_for(plan->rows_block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        }
-        if (r == CUDA_SUCCESS)
-        {
-            amode = tc::A_ROWS;
-            block_k = plan->rows_block_k;
-            tb = &plan->tmap_b_rows;
-            p.cblocks = plan->rows_cblocks;
-            p.num_k_blocks = c->kernel_h * plan->rows_cblocks;
-            p.chunks_per_row = (c->outw + tc::BLOCK_M - 1) / tc::BLOCK_M;
-        }
+            rows_pack_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
+                                                         c->pad_top);
+        NC_LAUNCH_CHECK();
+        amode = tc::A_ROWS;
+        block_k = plan->rows_block_k;
+        tb = &plan->tmap_b_rows;
+        ta = plan->tmap_b_rows; // unused by this mode (the A operand is a plain bulk copy)
+        p.cblocks = 1;
+        p.num_k_blocks = c->kernel_h;
+        p.chunks_per_row = (c->outw + tc::BLOCK_M - 1) / tc::BLOCK_M;
+        p.rows_src = (const unsigned char*)c->workspace;
+        p.rows_row_bytes = rg.Wpitch * cp * 2;
+        p.rows_img_bytes = (long long)rg.Hp * rg.Wpitch * cp * 2;
+        p.rows_seg_bytes = rg.seg_bytes;
     }
     if (amode == tc::A_TILED)
     {

@@ -75,6 +75,11 @@ struct Params
     int num_stages; // depth of the A/B ring (SmemPlan::stages_for(residual != NULL))
     int v8_ok;      // output rows are 32-byte aligned: 256-bit stores
     int taps_h;     // kernel_h (A_IM2COL / A_ROWS k-block nest: filter row, filter column, channel slab)
+    // A_ROWS: the zero-padded small-channel copy and its pitches (bytes)
+    const unsigned char* rows_src;
+    long long rows_img_bytes;
+    int rows_row_bytes;
+    int rows_seg_bytes; // bytes of one tile's row segment (multiple of 16)
     // tile decode without integer division
     FastDiv div_n_blocks, div_opix, div_outw, div_chunks, div_outh;
 };
@@ -180,6 +185,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                  "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+
+// contiguous global -> shared bulk copy (16-byte granularity), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // shared -> global tensor store (bulk async group); out-of-range rows / columns are clipped by the TMA unit
@@ -321,6 +332,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     return d;
 }
 
+// No-swizzle ("interleaved") K-major operand: element (row m, 16-byte K chunk j) at start + (m % 8) * 16 + (m / 8) * SBO + j * LBO.
+// With LBO = 16 and SBO = 128 the 8x16-byte core matrices overlap: row m begins 16 * m bytes after the start.
+__device__ __forceinline__ uint64_t make_smem_desc_overlap16(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(16 >> 4) << 16;  // LBO
+    d |= (uint64_t)(128 >> 4) << 32; // SBO
+    d |= (uint64_t)1 << 46;          // version
+    return d;                        // layout_type 0 = no swizzle
+}
+
 // Instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accumulate, A/B K-major.
 __host__ __device__ constexpr uint32_t make_idesc(int ab_format /*0 f16, 1 bf16*/, int M, int N)
 {
@@ -330,11 +353,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format /*0 f16, 1 bf16*
 // A-operand addressing modes
 //   A_TILED  : A is a plain [M][C] matrix (1x1 stride-1 unpadded conv, InnerProduct, Gemm): 2-D TMA tiles
 //   A_IM2COL : TMA im2col mode over the NHWC blob, one (tap, 64-channel slab) per k-block
-//   A_ROWS   : small-channel stems (cin <= 8): the input is re-packed once per call into a zero-padded
-//              [n][Hp][Wp][Cp] image (Cp = 4 or 8) and a k-block is one filter ROW: kw' consecutive pixels x Cp channels
-//              are contiguous in memory, so a 4-D *tiled* TMA whose pixel stride is the conv stride (overlapping
-//              windows) delivers, for 128 consecutive output columns of one output row, their kw'*Cp-wide K slab.
-//              One tile = one (image, output row, 128-column chunk).
+//   A_ROWS   : small-channel stems (cin <= 8, e.g. 7x7 s2 / 3x3 s2 / 3x3 s1 on RGB).  The input is re-packed once per call
+//              into a zero-padded [n][Hp][Wpitch][Cp] image with Cp = 4 (stride 2) or 8 (stride 1) channels per pixel, so
+//              that consecutive OUTPUT columns' windows start exactly 16 bytes apart.  A k-block is one filter row.  The A
+//              operand of a tile (128 consecutive output columns of one output row) is then just the raw row segment
+//              (16*127 + krow*2 bytes, ONE cp.async.bulk copy): a no-swizzle K-major UMMA descriptor with LBO = 16 B and
+//              SBO = 128 B addresses overlapping 8x16-byte core matrices, i.e. row m of the MMA starts 16*m bytes into the
+//              segment -- the im2col expansion happens inside the tensor core's operand fetch, not in memory.
+//              The layer's whole weight matrix (all filter rows) stays resident in shared memory.
 enum
 {
     A_TILED = 0,
@@ -368,6 +394,16 @@ struct SmemPlan
     static constexpr int total_for(bool has_res)
     {
         return stages_for(has_res) * stage_bytes + (has_res ? kResSlots * res_slot_bytes : 0) + bias_bytes + barrier_bytes + 1024;
+    }
+    // A_ROWS: `aux` bytes of resident weights behind the ring
+    static int stages_with_aux(int aux)
+    {
+        int s = (budget - aux) / stage_bytes;
+        return s > kMaxStages ? kMaxStages : s;
+    }
+    static int total_with_aux(int aux)
+    {
+        return stages_with_aux(aux) * stage_bytes + aux + bias_bytes + barrier_bytes + 1024;
     }
 };
 
@@ -472,7 +508,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Plan::a_bytes;
     uint8_t* smem_res = smem + kStages * Plan::stage_bytes; // [kResSlots][BLOCK_M][EPI_N], only when has_res
-    float* smem_bias = reinterpret_cast<float*>(smem_res + (has_res ? kResSlots * Plan::res_slot_bytes : 0)); // [kBiasSmemFloats]
+    // (A_ROWS keeps the resident weights where the residual slots would be; the two never coexist)
+    const int aux_bytes = AMODE == A_ROWS ? p.taps_h * Plan::b_bytes : (has_res ? kResSlots * Plan::res_slot_bytes : 0);
+    float* smem_bias = reinterpret_cast<float*>(smem_res + aux_bytes); // [kBiasSmemFloats]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + Plan::bias_bytes);
     uint64_t* full_bar = bars;                  // [16]
     uint64_t* empty_bar = bars + 16;            // [16]
@@ -480,7 +518,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* tmem_empty_bar = bars + 40;       // [8]
     uint64_t* res_full_bar = bars + 48;         // [kResSlots]
     uint64_t* res_empty_bar = bars + 52;        // [kResSlots]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 56);
+    uint64_t* bres_bar = bars + 56;             // A_ROWS: resident weights landed
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 57);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -511,6 +550,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[i]), kEpilogueWarps);
         }
+        mbar_init(smem_u32(bres_bar), 1);
         for (int i = 0; i < kResSlots; i++)
         {
             mbar_init(smem_u32(&res_full_bar[i]), 1);
@@ -547,6 +587,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t rphase = 0;
             const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
             const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            if (AMODE == A_ROWS)
+            {
+                // the layer's weights (one n-block, every filter row): resident behind the A ring for the whole kernel
+                const uint32_t bb = smem_u32(bres_bar);
+                mbar_expect_tx(bb, (uint32_t)(p.taps_h * Plan::b_bytes));
+                for (int ky = 0; ky < p.taps_h; ky++) tma_load_2d(smem_u32(smem_res) + ky * Plan::b_bytes, &tmap_b, bb, ky * BLOCK_K, 0);
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
             {
                 const int m_blk = fast_div(tile, p.div_n_blocks);
@@ -595,11 +642,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 else if (AMODE == A_ROWS)
                 {
-                    // k-block = (filter row, K slab of that row's kw' x Cp window)
-                    int kcoord = 0;
-                    for (int ky = 0; ky < p.taps_h; ky++)
-                        for (int cb = 0; cb < p.cblocks; cb++, kcoord += BLOCK_K)
-                            load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) { tma_load_4d(dst, &tmap_a, fb, cb * BLOCK_K, base_w, base_h + ky * p.dil_h, base_n); });
+                    // k-block = filter row: one contiguous segment of the padded row (output column j's window starts 16*j bytes in)
+                    const unsigned char* src = p.rows_src + (long long)base_n * p.rows_img_bytes + (long long)base_h * p.rows_row_bytes + (long long)base_w * 16;
+                    for (int ky = 0; ky < p.taps_h; ky++, src += (long long)p.dil_h * p.rows_row_bytes)
+                    {
+                        mbar_wait(empty0 + stage * 8, phase ^ 1);
+                        const uint32_t fb = full0 + stage * 8;
+                        mbar_expect_tx(fb, (uint32_t)p.rows_seg_bytes);
+                        bulk_load(smem_a0 + stage * Plan::a_bytes, src, (uint32_t)p.rows_seg_bytes, fb);
+                        if (++stage == kStages)
+                        {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
                 }
                 else
                 {
@@ -651,6 +707,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t acc_phase = 0;
         const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
         const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        if (AMODE == A_ROWS) mbar_wait(smem_u32(bres_bar), 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
@@ -662,8 +719,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tc_fence_after();
                 if (elect_one())
                 {
-                    const uint64_t adesc = make_smem_desc<BLOCK_K>(smem_a0 + stage * Plan::a_bytes);
-                    const uint64_t bdesc = make_smem_desc<BLOCK_K>(smem_b0 + stage * Plan::b_bytes);
+                    const uint64_t adesc = AMODE == A_ROWS ? make_smem_desc_overlap16(smem_a0 + stage * Plan::a_bytes) : make_smem_desc<BLOCK_K>(smem_a0 + stage * Plan::a_bytes);
+                    const uint64_t bdesc = make_smem_desc<BLOCK_K>(AMODE == A_ROWS ? smem_u32(smem_res) + kb * Plan::b_bytes : smem_b0 + stage * Plan::b_bytes);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / 16; k++)
                     {

@@ -7,5 +7,3 @@ for wl in resnet50 mobilenet_v2 vgg16 yolov8s; do
   timeout 300 python bench.py --workload $wl --storage $st --layers --no-cpu-baseline > gpurun_out/bench_${wl}_$st.json 2> gpurun_out/bench_${wl}_$st.layers; tail -1 gpurun_out/bench_${wl}_$st.json | cut -c1-120
  done
 done
-NCNN_B200_STEM_UNFOLD=0 timeout 300 python bench.py --workload resnet50 --storage bf16 --layers --no-cpu-baseline > gpurun_out/bench_resnet50_nounfold.json 2> gpurun_out/bench_resnet50_nounfold.layers; head -1 gpurun_out/bench_resnet50_nounfold.layers
-NCNN_B200_STEM_UNFOLD=0 timeout 300 python bench.py --workload vgg16 --storage bf16 --layers --no-cpu-baseline > gpurun_out/bench_vgg16_nounfold.json 2> gpurun_out/bench_vgg16_nounfold.layers; head -1 gpurun_out/bench_vgg16_nounfold.layers
