@@ -143,7 +143,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="resnet50", choices=sorted(WORKLOADS))
-    ap.add_argument("--storage", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--storage", default="bf16", choices=["fp16", "bf16", "fp32"],
+                    help="element type of device blobs; bf16 is the north-star dtype (fp32 in, bf16 tensor cores, fp32 accumulate)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-fusion", action="store_true")

@@ -293,6 +293,68 @@ __global__ void __launch_bounds__(256) rows_pack_kernel(const uint16_t* __restri
     }
 }
 
+// ---------------------------------------------------------------- A_SHIFT geometry (tc_gemm.cuh)
+struct ShiftGeom
+{
+    int bw, rows, colstep, chunks_x, tiles_y;
+    int stage_bytes, box_bytes, aux_bytes;
+};
+
+static int shift_mode()
+{
+    // NCNN_B200_CONV_SHIFT=0 forces the im2col path (A/B comparisons)
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* e = getenv("NCNN_B200_CONV_SHIFT");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+static bool shift_applicable(const TcPlan* plan, const TcConvCall* c, ShiftGeom* g)
+{
+    if (!shift_mode() || c->tiled || c->residual) return false;
+    if (c->stride_w != 1 || c->stride_h != 1 || c->dil_w != 1 || c->dil_h != 1) return false;
+    if (c->kernel_w * c->kernel_h < 2 || c->kernel_w > 8 || c->kernel_h > 8) return false;
+    if (plan->block_k != 64 || plan->outch > plan->block_n) return false; // 128-byte pixel rows; one n-block (resident weights)
+    if (c->pad_left < 0 || c->pad_top < 0 || c->pad_right < 0 || c->pad_bottom < 0) return false;
+    const int pw = c->inw + c->pad_left + c->pad_right;
+    if (c->outw != pw - (c->kernel_w - 1) || c->outh != c->inh + c->pad_top + c->pad_bottom - (c->kernel_h - 1)) return false;
+    if (pw <= 128)
+    {
+        g->bw = pw;
+        g->colstep = pw - (c->kernel_w - 1); // = outw
+        g->chunks_x = 1;
+        g->rows = 128 / pw;
+    }
+    else
+    {
+        g->bw = 128;
+        g->colstep = 128 - (c->kernel_w - 1);
+        g->chunks_x = (c->outw + g->colstep - 1) / g->colstep;
+        g->rows = 1;
+    }
+    if (g->rows > c->outh) g->rows = c->outh;
+    if (g->rows + c->kernel_h - 1 > 256) return false;
+    g->tiles_y = (c->outh + g->rows - 1) / g->rows;
+    g->box_bytes = g->bw * (g->rows + c->kernel_h - 1) * 128;
+    // the MMA reads 128 rows from the last tap's start: (kh-1)*bw + (kw-1) + 128 pixels
+    int px = (c->kernel_h - 1) * g->bw + (c->kernel_w - 1) + 128;
+    int need = px * 128 > g->box_bytes ? px * 128 : g->box_bytes;
+    g->stage_bytes = (need + 1023) / 1024 * 1024;
+    g->aux_bytes = plan->num_k_blocks * plan->block_n * 64 * 2;
+    // at least 3 stages next to the resident weights (and the layer's bias vector)
+    const int bias_need = (plan->outch_pad * 4 + 1023) / 1024 * 1024;
+    const int budget = 227 * 1024 - 512 - bias_need - 1024;
+    if ((budget - g->aux_bytes) / g->stage_bytes < 3) return false;
+    // utilisation of the 128 MMA rows: below ~60 % the im2col path wins
+    const long long useful = (long long)g->rows * g->colstep;
+    if (useful * 100 < 128 * 55) return false;
+    if ((long long)c->n * g->tiles_y * g->chunks_x > 0x3fffffffLL) return false;
+    return true;
+}
+
 int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
 {
     if (!plan->w_packed) return 0;
@@ -330,16 +392,27 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     }
     const bool has_res = p.residual != 0;
     int smem_bytes;
+    const int bias_count = ((p.N + BLOCK_N - 1) / BLOCK_N) * BLOCK_N;
+    const int bias_need = (bias_count * 4 + 1023) / 1024 * 1024;
+    p.bias_smem_bytes = Plan::bias_bytes; // the general modes reserve the worst case
     if (AMODE == tc::A_ROWS)
     {
         const int aux = p.taps_h * Plan::b_bytes; // resident weights
-        p.num_stages = Plan::stages_with_aux(aux);
-        smem_bytes = Plan::total_with_aux(aux);
+        p.bias_smem_bytes = bias_need <= Plan::bias_bytes ? bias_need : 0;
+        p.num_stages = Plan::stages_with_aux(aux, p.rows_stage_bytes, p.bias_smem_bytes);
+        smem_bytes = Plan::total_with_aux(aux, p.rows_stage_bytes, p.bias_smem_bytes);
         if (p.num_stages < 2)
         {
             set_last_error_msg("tc_gemm: stem weights do not fit in shared memory");
             return -1;
         }
+    }
+    else if (AMODE == tc::A_SHIFT)
+    {
+        const int aux = p.num_k_blocks * Plan::b_bytes; // resident weights
+        p.bias_smem_bytes = bias_need <= Plan::bias_bytes ? bias_need : 0;
+        p.num_stages = Plan::stages_with_aux(aux, p.sh_stage_bytes, p.bias_smem_bytes);
+        smem_bytes = Plan::total_with_aux(aux, p.sh_stage_bytes, p.bias_smem_bytes);
     }
     else
     {
@@ -362,6 +435,8 @@ static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CU
     NC_TC(128, 64);
     NC_TC(64, 64);
     NC_TC(32, 64);
+    if constexpr (AMODE != tc::A_SHIFT)
+    {
     NC_TC(256, 32);
     NC_TC(128, 32);
     NC_TC(64, 32);
@@ -370,6 +445,7 @@ static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CU
     NC_TC(128, 16);
     NC_TC(64, 16);
     NC_TC(32, 16);
+    }
 #undef NC_TC
     set_last_error_msg("tc_gemm: no kernel instance for this tile shape");
     return -1;
@@ -403,6 +479,31 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
 
     tc::Params p;
     memset(&p, 0, sizeof(p));
+    ShiftGeom sg;
+    const bool use_shift = !use_rows && shift_applicable(plan, c, &sg);
+    if (use_shift)
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)c->inch, (cuuint64_t)c->inw, (cuuint64_t)c->inh, (cuuint64_t)c->n};
+        cuuint64_t gstride[3] = {(cuuint64_t)c->in_cpitch * 2, (cuuint64_t)c->in_cpitch * 2 * c->inw, (cuuint64_t)c->in_cpitch * 2 * c->inw * c->inh};
+        cuuint32_t box[4] = {64u, (cuuint32_t)sg.bw, (cuuint32_t)(sg.rows + c->kernel_h - 1), 1u};
+        cuuint32_t estride[4] = {1, 1, 1, 1};
+        CUresult r = g_encodeTiled(&ta, dtype_for(plan->elemtype), 4, (void*)c->in, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+        {
+            amode = tc::A_SHIFT;
+            p.sh_bw = sg.bw;
+            p.sh_rows = sg.rows;
+            p.sh_colstep = sg.colstep;
+            p.sh_chunks_x = sg.chunks_x;
+            p.sh_tiles_y = sg.tiles_y;
+            p.sh_stage_bytes = sg.stage_bytes;
+            p.sh_box_bytes = sg.box_bytes;
+            p.div_sh_chunks_x = make_fastdiv((unsigned int)sg.chunks_x);
+            p.div_sh_tiles_y = make_fastdiv((unsigned int)sg.tiles_y);
+            p.div_sh_bw = make_fastdiv((unsigned int)sg.bw);
+        }
+    }
     if (use_rows)
     {
         const int cp = plan->rows_cp;
@@ -427,8 +528,14 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
         p.rows_row_bytes = rg.Wpitch * cp * 2;
         p.rows_img_bytes = (long long)rg.Hp * rg.Wpitch * cp * 2;
         p.rows_seg_bytes = rg.seg_bytes;
+        p.rows_seg_pitch = (rg.seg_bytes + 127) / 128 * 128;
+        p.rows_stage_bytes = ((c->kernel_h * p.rows_seg_pitch + 1023) / 1024) * 1024;
     }
-    if (amode == tc::A_TILED)
+    if (amode == tc::A_SHIFT)
+    {
+        // (descriptor encoded above)
+    }
+    else if (amode == tc::A_TILED)
     {
         cuuint64_t gdim[2] = {(cuuint64_t)c->inch, (cuuint64_t)M};
         cuuint64_t gstride[1] = {(cuuint64_t)c->in_cpitch * 2};
@@ -513,10 +620,12 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     p.div_chunks = make_fastdiv((unsigned int)p.chunks_per_row);
     p.div_outh = make_fastdiv((unsigned int)(c->outh > 0 ? c->outh : 1));
 
-    const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row : (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+    const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row
+                               : (amode == tc::A_SHIFT ? (long long)c->n * p.sh_tiles_y * p.sh_chunks_x : (M + tc::BLOCK_M - 1) / tc::BLOCK_M);
     const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);
 
 #define NC_MODE(T)                                                                                                            \
+    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream);  \
     if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream);  \
     if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream); \
     return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream)

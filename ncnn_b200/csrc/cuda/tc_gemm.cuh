@@ -73,6 +73,7 @@ struct Params
     int act_type;
     float act_p0, act_p1;
     int num_stages; // depth of the A/B ring (SmemPlan::stages_for(residual != NULL))
+    int bias_smem_bytes; // shared memory reserved for the bias vector (multiple of 1024; 0 = read it from global memory)
     int v8_ok;      // output rows are 32-byte aligned: 256-bit stores
     int taps_h;     // kernel_h (A_IM2COL / A_ROWS k-block nest: filter row, filter column, channel slab)
     // A_ROWS: the zero-padded small-channel copy and its pitches (bytes)
@@ -80,6 +81,13 @@ struct Params
     long long rows_img_bytes;
     int rows_row_bytes;
     int rows_seg_bytes; // bytes of one tile's row segment (multiple of 16)
+    int rows_seg_pitch; // shared-memory pitch of the segments of one stage (multiple of 128)
+    int rows_stage_bytes; // taps_h * rows_seg_pitch: one stage holds every filter row of a tile
+    // A_SHIFT geometry
+    int sh_bw, sh_rows, sh_colstep; // buffer row pitch (pixels), output rows per tile, output columns per column chunk
+    int sh_chunks_x, sh_tiles_y;    // column chunks per row, row groups per image
+    int sh_stage_bytes, sh_box_bytes;
+    FastDiv div_sh_chunks_x, div_sh_tiles_y, div_sh_bw;
     // tile decode without integer division
     FastDiv div_n_blocks, div_opix, div_outw, div_chunks, div_outh;
 };
@@ -361,11 +369,20 @@ __host__ __device__ constexpr uint32_t make_idesc(int ab_format /*0 f16, 1 bf16*
 //              SBO = 128 B addresses overlapping 8x16-byte core matrices, i.e. row m of the MMA starts 16*m bytes into the
 //              segment -- the im2col expansion happens inside the tensor core's operand fetch, not in memory.
 //              The layer's whole weight matrix (all filter rows) stays resident in shared memory.
+//   A_SHIFT  : stride-1 k x k convolutions whose weights fit in shared memory (64 -> 64 3x3 and the like; with im2col
+//              loads these are bound by the kh*kw-fold re-read of the input through L2).  A tile is R output rows x BW
+//              positions of ONE image, BW = padded width (or a 128-wide column chunk); per 64-channel slab ONE 4-D tiled TMA
+//              box brings the (R + kh - 1) x BW input pixels (zero OOB fill = the padding) into a 128B-swizzled [pixel][64ch]
+//              buffer, and the A operand of tap (ky, kx) is that same buffer read from pixel ky * BW + kx on: the UMMA
+//              descriptor's start address moves by whole 128-byte rows (the swizzle is a function of the shared-memory
+//              address, so the TMA-written pattern stays consistent).  Accumulator row i is output (i / BW, i % BW); the
+//              kw - 1 positions per row that wrap into the next row are computed and dropped.  kh*kw-fold less L2 traffic.
 enum
 {
     A_TILED = 0,
     A_IM2COL = 1,
-    A_ROWS = 2
+    A_ROWS = 2,
+    A_SHIFT = 3
 };
 
 template<int BLOCK_N, int BLOCK_K>
@@ -384,7 +401,7 @@ struct SmemPlan
     static constexpr int kAccStages = (512 / BLOCK_N) > 8 ? 8 : (512 / BLOCK_N);
     static constexpr int res_slot_bytes = BLOCK_M * EPI_N * 2;
     static constexpr int barrier_bytes = 512;
-    static constexpr int bias_bytes = kBiasSmemFloats * 4;
+    static constexpr int bias_bytes = kBiasSmemFloats * 4; // worst case; A_ROWS / A_SHIFT reserve only what the layer needs
     static constexpr int budget = 227 * 1024 - barrier_bytes - bias_bytes - 1024; // - alignment slack
     static constexpr int stages_for(bool has_res)
     {
@@ -396,14 +413,14 @@ struct SmemPlan
         return stages_for(has_res) * stage_bytes + (has_res ? kResSlots * res_slot_bytes : 0) + bias_bytes + barrier_bytes + 1024;
     }
     // A_ROWS: `aux` bytes of resident weights behind the ring
-    static int stages_with_aux(int aux)
+    static int stages_with_aux(int aux, int stage_sz, int bias_sz)
     {
-        int s = (budget - aux) / stage_bytes;
+        int s = (budget + bias_bytes - bias_sz - aux) / stage_sz;
         return s > kMaxStages ? kMaxStages : s;
     }
-    static int total_with_aux(int aux)
+    static int total_with_aux(int aux, int stage_sz, int bias_sz)
     {
-        return stages_with_aux(aux) * stage_bytes + aux + bias_bytes + barrier_bytes + 1024;
+        return stages_with_aux(aux, stage_sz, bias_sz) * stage_sz + aux + bias_sz + barrier_bytes + 1024;
     }
 };
 
@@ -507,11 +524,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool has_res = p.residual != nullptr;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Plan::a_bytes;
-    uint8_t* smem_res = smem + kStages * Plan::stage_bytes; // [kResSlots][BLOCK_M][EPI_N], only when has_res
+    // behind the ring: residual slots [kResSlots][BLOCK_M][EPI_N] (has_res) or the resident stem weights (A_ROWS, whose
+    // stages hold a whole tile's row segments instead of A/B k-block pairs)
+    uint8_t* smem_res = smem + kStages * (AMODE == A_ROWS ? p.rows_stage_bytes : (AMODE == A_SHIFT ? p.sh_stage_bytes : Plan::stage_bytes));
     // (A_ROWS keeps the resident weights where the residual slots would be; the two never coexist)
-    const int aux_bytes = AMODE == A_ROWS ? p.taps_h * Plan::b_bytes : (has_res ? kResSlots * Plan::res_slot_bytes : 0);
+    const int aux_bytes = AMODE == A_ROWS ? p.taps_h * Plan::b_bytes : (AMODE == A_SHIFT ? p.num_k_blocks * Plan::b_bytes : (has_res ? kResSlots * Plan::res_slot_bytes : 0));
     float* smem_bias = reinterpret_cast<float*>(smem_res + aux_bytes); // [kBiasSmemFloats]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + Plan::bias_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + p.bias_smem_bytes);
     uint64_t* full_bar = bars;                  // [16]
     uint64_t* empty_bar = bars + 16;            // [16]
     uint64_t* tmem_full_bar = bars + 32;        // [8]
@@ -528,6 +547,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int num_m_blocks;
     if (AMODE == A_ROWS)
         num_m_blocks = (int)(p.M / p.outw) * p.chunks_per_row; // rows * chunks
+    else if (AMODE == A_SHIFT)
+        num_m_blocks = (int)(p.M / ((long long)p.outw * p.outh)) * p.sh_tiles_y * p.sh_chunks_x; // images * row groups * column chunks
     else
         num_m_blocks = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     const int num_tiles = num_m_blocks * num_n_blocks;
@@ -566,7 +587,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     // the layer's (padded) bias vector: resident in shared memory when it fits
     const int bias_count = ((p.N + BLOCK_N - 1) / BLOCK_N) * BLOCK_N;
-    const bool bias_in_smem = bias_count <= kBiasSmemFloats;
+    const bool bias_in_smem = bias_count * 4 <= p.bias_smem_bytes;
     if (bias_in_smem)
         for (int i = threadIdx.x; i < bias_count; i += kNumThreads) smem_bias[i] = __ldg(p.bias + i);
     tc_fence_before();
@@ -587,12 +608,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t rphase = 0;
             const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
             const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-            if (AMODE == A_ROWS)
+            if (AMODE == A_ROWS || AMODE == A_SHIFT)
             {
-                // the layer's weights (one n-block, every filter row): resident behind the A ring for the whole kernel
+                // the layer's weights (one n-block, every k-block): resident behind the A ring for the whole kernel
+                const int nres = AMODE == A_ROWS ? p.taps_h : p.num_k_blocks;
                 const uint32_t bb = smem_u32(bres_bar);
-                mbar_expect_tx(bb, (uint32_t)(p.taps_h * Plan::b_bytes));
-                for (int ky = 0; ky < p.taps_h; ky++) tma_load_2d(smem_u32(smem_res) + ky * Plan::b_bytes, &tmap_b, bb, ky * BLOCK_K, 0);
+                mbar_expect_tx(bb, (uint32_t)(nres * Plan::b_bytes));
+                for (int kb = 0; kb < nres; kb++) tma_load_2d(smem_u32(smem_res) + kb * Plan::b_bytes, &tmap_b, bb, kb * BLOCK_K, 0);
             }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
             {
@@ -630,7 +652,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         phase ^= 1;
                     }
                 };
-                if (AMODE == A_IM2COL)
+                if (AMODE == A_SHIFT)
+                {
+                    // tile = (image, row group, column chunk); one box per 64-channel slab
+                    const int t1 = fast_div(m_blk, p.div_sh_chunks_x);
+                    const int cx = m_blk - t1 * p.sh_chunks_x;
+                    const int img = fast_div(t1, p.div_sh_tiles_y);
+                    const int ty = t1 - img * p.sh_tiles_y;
+                    const int w0 = cx * p.sh_colstep - p.pad_left, h0 = ty * p.sh_rows - p.pad_top;
+                    for (int cb = 0; cb < p.cblocks; cb++)
+                    {
+                        mbar_wait(empty0 + stage * 8, phase ^ 1);
+                        const uint32_t fb = full0 + stage * 8;
+                        mbar_expect_tx(fb, (uint32_t)p.sh_box_bytes);
+                        tma_load_4d(smem_a0 + stage * p.sh_stage_bytes, &tmap_a, fb, cb * BLOCK_K, w0, h0, img);
+                        if (++stage == kStages)
+                        {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                else if (AMODE == A_IM2COL)
                 {
                     int kcoord = 0;
                     for (int ky = 0; ky < p.taps_h; ky++)
@@ -642,19 +685,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 else if (AMODE == A_ROWS)
                 {
-                    // k-block = filter row: one contiguous segment of the padded row (output column j's window starts 16*j bytes in)
+                    // one stage = the tile's kh row segments (output column j's window starts 16*j bytes into each): one barrier
+                    // round trip per tile, kh contiguous bulk copies
                     const unsigned char* src = p.rows_src + (long long)base_n * p.rows_img_bytes + (long long)base_h * p.rows_row_bytes + (long long)base_w * 16;
-                    for (int ky = 0; ky < p.taps_h; ky++, src += (long long)p.dil_h * p.rows_row_bytes)
+                    mbar_wait(empty0 + stage * 8, phase ^ 1);
+                    const uint32_t fb = full0 + stage * 8;
+                    mbar_expect_tx(fb, (uint32_t)(p.taps_h * p.rows_seg_bytes));
+                    uint32_t dst = smem_a0 + stage * p.rows_stage_bytes;
+                    for (int ky = 0; ky < p.taps_h; ky++, src += (long long)p.dil_h * p.rows_row_bytes, dst += p.rows_seg_pitch)
+                        bulk_load(dst, src, (uint32_t)p.rows_seg_bytes, fb);
+                    if (++stage == kStages)
                     {
-                        mbar_wait(empty0 + stage * 8, phase ^ 1);
-                        const uint32_t fb = full0 + stage * 8;
-                        mbar_expect_tx(fb, (uint32_t)p.rows_seg_bytes);
-                        bulk_load(smem_a0 + stage * Plan::a_bytes, src, (uint32_t)p.rows_seg_bytes, fb);
-                        if (++stage == kStages)
-                        {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
                 else
@@ -707,34 +750,99 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t acc_phase = 0;
         const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
         const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-        if (AMODE == A_ROWS) mbar_wait(smem_u32(bres_bar), 0);
+        if (AMODE == A_ROWS || AMODE == A_SHIFT) mbar_wait(smem_u32(bres_bar), 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int kb = 0; kb < p.num_k_blocks; kb++)
+            if (AMODE == A_ROWS)
             {
+                // the whole tile sits in one stage: kh filter rows x (BLOCK_K / 16) MMAs, one commit
                 mbar_wait(full0 + stage * 8, phase);
                 tc_fence_after();
                 if (elect_one())
                 {
-                    const uint64_t adesc = AMODE == A_ROWS ? make_smem_desc_overlap16(smem_a0 + stage * Plan::a_bytes) : make_smem_desc<BLOCK_K>(smem_a0 + stage * Plan::a_bytes);
-                    const uint64_t bdesc = make_smem_desc<BLOCK_K>(AMODE == A_ROWS ? smem_u32(smem_res) + kb * Plan::b_bytes : smem_b0 + stage * Plan::b_bytes);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; k++)
+                    const uint32_t a_base = smem_a0 + stage * p.rows_stage_bytes;
+                    const uint32_t b_base = smem_u32(smem_res);
+                    for (int ky = 0; ky < p.taps_h; ky++)
                     {
-                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
-                        umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                        const uint64_t adesc = make_smem_desc_overlap16(a_base + ky * p.rows_seg_pitch);
+                        const uint64_t bdesc = make_smem_desc<BLOCK_K>(b_base + ky * Plan::b_bytes);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; k++) umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((ky | k) != 0));
                     }
-                    umma_commit(empty0 + stage * 8); // frees the smem slot when these MMAs retire
-                    if (kb == p.num_k_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                    umma_commit(empty0 + stage * 8);
+                    umma_commit(smem_u32(&tmem_full_bar[acc]));
                 }
                 __syncwarp();
                 if (++stage == kStages)
                 {
                     stage = 0;
                     phase ^= 1;
+                }
+            }
+            else if (AMODE == A_SHIFT)
+            {
+                // per 64-channel slab: every tap reads the same staged pixels, shifted by ky * BW + kx rows of 128 bytes
+                const uint32_t b_base = smem_u32(smem_res);
+                for (int cb = 0; cb < p.cblocks; cb++)
+                {
+                    mbar_wait(full0 + stage * 8, phase);
+                    tc_fence_after();
+                    if (elect_one())
+                    {
+                        const uint32_t a_base = smem_a0 + stage * p.sh_stage_bytes;
+                        int tap = 0;
+                        for (int ky = 0; ky < p.taps_h; ky++)
+                            for (int kx = 0; kx < p.taps_w; kx++, tap++)
+                            {
+                                const uint32_t shift_px = (uint32_t)(ky * p.sh_bw + kx);
+                                // (the descriptor's base-offset field stays 0: measured on B200, the 128B swizzle is applied to the
+                                // absolute shared-memory address, so a start that is not 1024-byte aligned needs no correction --
+                                // setting the field to (start >> 7) & 7 produces wrong results)
+                                const uint64_t adesc = make_smem_desc<BLOCK_K>(a_base + shift_px * 128u);
+                                const uint64_t bdesc = make_smem_desc<BLOCK_K>(b_base + (tap * p.cblocks + cb) * Plan::b_bytes);
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; k++)
+                                    umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
+                            }
+                        umma_commit(empty0 + stage * 8);
+                        if (cb == p.cblocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                    }
+                    __syncwarp();
+                    if (++stage == kStages)
+                    {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            else
+            {
+                for (int kb = 0; kb < p.num_k_blocks; kb++)
+                {
+                    mbar_wait(full0 + stage * 8, phase);
+                    tc_fence_after();
+                    if (elect_one())
+                    {
+                        const uint64_t adesc = make_smem_desc<BLOCK_K>(smem_a0 + stage * Plan::a_bytes);
+                        const uint64_t bdesc = make_smem_desc<BLOCK_K>(smem_b0 + stage * Plan::b_bytes);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; k++)
+                        {
+                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
+                            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        umma_commit(empty0 + stage * 8); // frees the smem slot when these MMAs retire
+                        if (kb == p.num_k_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                    }
+                    __syncwarp();
+                    if (++stage == kStages)
+                    {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
             if (++acc == kAccStages)
@@ -778,6 +886,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int col = (m_blk - orow_idx * p.chunks_per_row) * BLOCK_M + row;
                 row_ok = col < p.outw;
                 pix = (long long)orow_idx * p.outw + col;
+            }
+            else if (AMODE == A_SHIFT)
+            {
+                const int t1 = fast_div(m_blk, p.div_sh_chunks_x);
+                const int cx = m_blk - t1 * p.sh_chunks_x;
+                const int img = fast_div(t1, p.div_sh_tiles_y);
+                const int ty = t1 - img * p.sh_tiles_y;
+                const int r = fast_div(row, p.div_sh_bw); // accumulator row -> (tile row, position in the buffer row)
+                const int x = row - r * p.sh_bw;
+                const int oy = ty * p.sh_rows + r, ox = cx * p.sh_colstep + x;
+                row_ok = r < p.sh_rows && x < p.sh_colstep && oy < p.outh && ox < p.outw;
+                pix = ((long long)img * p.outh + oy) * p.outw + ox;
             }
             else
             {

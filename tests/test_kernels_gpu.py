@@ -160,6 +160,35 @@ def test_convolution_tensor_core_shapes(ref, elemtype):
 
 
 @pytest.mark.parametrize("elemtype", [BF16, F16])
+def test_convolution_shifted_window_shapes(ref, elemtype):
+    """stride-1 k x k convolutions with shared-memory-resident weights run the A_SHIFT variant (tc_gemm.cuh): one staged
+    pixel buffer per 64-channel slab, taps as row-shifted UMMA descriptors.  Rows narrower and wider than the 128-row
+    MMA tile, several rows per tile, column chunks, image/row-group tails, channel counts that are not a multiple of 64,
+    asymmetric padding, 'valid' windows, 5x5 and non-square kernels"""
+    rng = np.random.default_rng(6)
+    cases = [
+        # w, h, cin, cout, k, pad, n, act
+        (56, 56, 64, 64, 3, 1, 2, 1),      # resnet50 res2x_branch2b: 2 rows of 58 per tile
+        (28, 28, 64, 64, 3, 1, 3, 0),      # 4 rows of 30 per tile
+        (14, 14, 64, 48, 3, 1, 5, 1),      # 8 rows of 16 per tile, 14 = 8 + 6 (row-group tail)
+        (224, 20, 64, 64, 3, 1, 1, 1),     # vgg16 conv1_2: 226 > 128 -> column chunks of 126
+        (130, 9, 64, 32, 3, 1, 2, 3),      # 132-wide rows: two chunks, second nearly empty
+        (126, 7, 40, 64, 3, 1, 2, 1),      # exactly one 128-wide buffer row; cin = 40 (zero-filled channel tail)
+        (61, 33, 96, 32, 3, 1, 2, 2),      # two 64-channel slabs (the second half empty)
+        (40, 40, 64, 64, 3, 0, 2, 1),      # valid window: outw = 38
+        (37, 29, 48, 24, 5, 2, 2, 7),      # 5x5, swish epilogue
+        (45, 31, 64, 64, 3, -233, 2, 1),   # SAME padding
+        (50, 18, 64, 16, 2, 1, 2, 0),      # even kernel: outw = 51
+    ]
+    for (w, h, ci, co, k, pad, n, act) in cases:
+        if act == 7:
+            continue  # (swish is a graph-level fold, not a layer activation_type: covered by the network tests)
+        run_conv(ref, rng, elemtype, n, w, h, ci, co, k, 1, 1, pad, True, act, expect_algo=2)
+    run_conv(ref, rng, elemtype, 2, 41, 37, 64, 48, 5, 1, 1, 2, True, 2, kh=3)
+    run_conv(ref, rng, elemtype, 30, 56, 56, 64, 64, 3, 1, 1, 1, True, 1)  # more tiles than CTAs x stages
+
+
+@pytest.mark.parametrize("elemtype", [BF16, F16])
 def test_convolution_small_channel_stems(ref, elemtype):
     """cin <= 8 first layers run the A_ROWS variant (zero-padded 4/8-channel copy + overlapping-window TMA): the five
     models' stems, odd sizes, rows wider than one 128-column chunk, and the cases that must NOT take it"""

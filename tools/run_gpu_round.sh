@@ -24,6 +24,6 @@ prof() { # name regex skip count workload
   ncu -i /tmp/prof_$1.ncu-rep --page details --csv > gpurun_out/prof_$1.details.csv 2>/dev/null
   sz=$(stat -c %s /tmp/prof_$1.ncu-rep); [ "$sz" -lt 12000000 ] && cp /tmp/prof_$1.ncu-rep gpurun_out/
 }
-prof tc_gemm tc_gemm 53 53 resnet50
-prof dwconv dwconv 0 17 mobilenet_v2
+prof tc_gemm tc_gemm 159 53 resnet50
+prof dwconv dwconv 51 17 mobilenet_v2
 du -sh gpurun_out; ls -la gpurun_out
