@@ -150,6 +150,9 @@ def main():
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer table to stderr")
+    ap.add_argument("--e2e-threads", type=int, default=2,
+                    help="host threads feeding the end-to-end path, one Extractor (own stream, own device pool) per call: with 2 the H2D "
+                         "copy of one step overlaps the kernels of the previous one (the reference's one-extractor-per-thread rule)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,15 +226,45 @@ def main():
     value = replicas.throughput(batch, args.steps, world, ms)
 
     # ---- end to end through the reference-facing call (host Mat in, host Mat out)
+    # every step = ncnn_extractor_input(pinned host Mat) + ncnn_extractor_extract(host Mat): H2D of the fp32 batch, the
+    # kernels, D2H of the result, all inside the timed region.  Steps are dealt to --e2e-threads host threads, each with
+    # its own input Mat and its own Extractor per step (ctypes releases the GIL), so consecutive steps overlap on the GPU's
+    # copy and compute engines; with 1 thread the steps run strictly one after the other.
+    def e2e_run(n_threads, steps):
+        inputs = [host_in] + [sess.pinned_input(x) for _ in range(n_threads - 1)]
+        per = [steps // n_threads + (1 if i < steps % n_threads else 0) for i in range(n_threads)]
+        errs = []
+
+        def worker(i):
+            try:
+                lib.ncnn_cuda_set_device(local_rank)
+                for _ in range(per[i]):
+                    lib.ncnn_mat_destroy(sess.extract_host(inputs[i]))
+            except Exception as e:  # surfaced below: a failed step must fail the bench
+                errs.append(e)
+
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(n_threads)]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        for m in inputs[1:]:
+            lib.ncnn_mat_destroy(m)
+        if errs:
+            raise errs[0]
+        return dt
+
     for _ in range(3):
         lib.ncnn_mat_destroy(sess.extract_host(host_in))
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lib.ncnn_mat_destroy(sess.extract_host(host_in))
-    e2e_s = time.perf_counter() - t0
-    e2e_s = max_over_ranks(e2e_s)
+    e2e_serial_s = max_over_ranks(e2e_run(1, args.steps))
+    barrier()
+    nthreads = max(1, args.e2e_threads)
+    e2e_s = max_over_ranks(e2e_run(nthreads, args.steps)) if nthreads > 1 else e2e_serial_s
     e2e_value = replicas.throughput(batch, args.steps, world, e2e_s * 1000.0)
+    e2e_serial_value = replicas.throughput(batch, args.steps, world, e2e_serial_s * 1000.0)
     h2d, d2h = int(sess.last_h2d), int(sess.last_d2h)
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
     if rank == 0:
@@ -268,15 +301,24 @@ def main():
                                                           ("%7.1f TFLOP/s" % r["tflops"]) if r.get("tflops") else (("%7.1f GB/s" % r["gbs"]) if r.get("gbs") else "")))
         sys.stderr.write("layers total %.3f ms (conv %.3f, dw %.3f, fc %.3f); step %.3f ms\n" % (total_ms, conv_ms, dw_ms, fc_ms, ms / args.steps))
 
-    if dw_ms > conv_ms and dw_bytes > 0:
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1b", "traffic.json")
+    if os.path.exists(tpath) and batch == WORKLOADS[args.workload][1]:
+        t = json.load(open(tpath)).get(args.workload)
+        if t and t.get("storage") == args.storage:
+            # DRAM bytes of the dominant kernel family over one step, from the committed ncu --set full capture of this command
+            traffic = {"dram_bytes_per_step": t["dram_read_bytes"] + t["dram_write_bytes"], "launches": t["launches"], "source": "profiles/r1b/traffic.json (ncu)"}
+    # MobileNetV2 is the depthwise (bandwidth) configuration of BASELINE.json: its roofline line is the depthwise family
+    if dw_bytes > 0 and (dw_ms > conv_ms or args.workload == "mobilenet_v2"):
         achieved = dw_bytes / (dw_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "dwconv_kernel (ConvolutionDepthWise)", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["source"] + " copy bandwidth",
+        roofline = {"bound": "hbm", "kernel": "dwconv3x3_tma_kernel (ConvolutionDepthWise, TMA halo tiles)", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm"], "traffic": traffic, "peak_source": peaks["source"] + " copy bandwidth",
+                    "algorithmic_bytes_per_step": dw_bytes, "dw_ms_per_step": dw_ms,
                     "share_of_step": dw_ms / total_ms if total_ms else None}
     else:
         achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel (Convolution, tcgen05 implicit GEMM)" if args.storage != "fp32" else "conv_simt_kernel (fp32 CUDA cores)",
-                    "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": None,
+                    "achieved": achieved, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": traffic,
                     "peak_source": peaks["source"] + " sustained dense bf16 (kernel timed inside a long step)",
                     "share_of_step": conv_ms / total_ms if total_ms else None,
                     "algorithmic_flop_per_step": conv_flop, "conv_ms_per_step": conv_ms}
@@ -286,7 +328,9 @@ def main():
     line = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.storage], "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads": nthreads,
+                    "serial_value": e2e_serial_value,
+                    "mode": "each step = extractor.input(pinned host Mat) + extract(host Mat); steps dealt to %d host thread(s), one Extractor/stream per step" % nthreads},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "fused_layers": sess.fused_layers}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

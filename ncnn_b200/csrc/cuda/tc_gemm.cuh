@@ -911,18 +911,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 
-            // 32-column groups of this tile that exist (col < N) ...
+            // 32-column groups of this tile that exist (col < N), and the ones this half owns: chunk parity selects the half
+            // (group parity when the tile is a single 64-column chunk)
             const int ncols = (N - n0) < BLOCK_N ? (N - n0) : BLOCK_N;
             const int ngroups = (ncols + 31) >> 5;
-            // ... and the ones this half owns: group g belongs to chunk g / SUBS; chunk parity (or group parity when the
-            // tile is one chunk) selects the half
-            int my_last = -1;
-            for (int g = 0; g < ngroups; g++)
+            int g_begin, g_last; // first / last owned group (g_last < g_begin: none)
+            if (NCHUNK == 1)
             {
-                const int owner = (NCHUNK == 1) ? (SUBS == 2 ? (g & 1) : 0) : ((g / SUBS) & 1);
-                if (owner == half) my_last = g;
+                g_begin = g_last = half;
+                if (half >= ngroups) g_last = -1;
             }
-            if (my_last < 0)
+            else
+            {
+                const int nchunks = (ngroups + SUBS - 1) / SUBS;
+                g_begin = half * SUBS;
+                if (half >= nchunks)
+                    g_last = -1;
+                else
+                {
+                    const int last_cc = half + ((nchunks - 1 - half) & ~1);
+                    const int e = last_cc * SUBS + SUBS - 1;
+                    g_last = e < ngroups ? e : ngroups - 1;
+                }
+            }
+            if (g_last < 0)
             {
                 // nothing to read for this half: hand the accumulator stage back right away
                 tc_fence_before();
@@ -931,13 +943,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // single-chunk tiles count all eight warps as readers of the residual slot
                 if (has_res && NCHUNK == 1 && SUBS == 2 && lane == 0) mbar_arrive(smem_u32(&res_empty_bar[slots_seen % kResSlots]));
             }
+            // owned groups: g_begin, +1 within a chunk, then the chunk after next
 #pragma unroll 1
-            for (int g = 0; g < ngroups; g++)
+            for (int g = g_begin; g <= g_last; g = (NCHUNK == 1 || (g % SUBS) != SUBS - 1) ? g + 1 : g + 1 + SUBS)
             {
                 const int cc = g / SUBS;         // chunk = residual slot of the tile
                 const int slot_sub = g % SUBS;   // which 32-column half of the slot
-                const int owner = (NCHUNK == 1) ? (SUBS == 2 ? (g & 1) : 0) : (cc & 1);
-                if (owner != half) continue;
                 const int col0 = g * 32;
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)col0, r);
@@ -956,7 +967,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int rslot = (int)(slot_no % kResSlots);
                 if (has_res && (slot_sub == 0 || NCHUNK == 1)) mbar_wait(smem_u32(&res_full_bar[rslot]), (slot_no / kResSlots) & 1);
                 tmem_wait_ld_pin(r);
-                if (g == my_last)
+                if (g == g_last)
                 {
                     // every column group of this half sits in registers: the accumulator stage can be overwritten
                     tc_fence_before();
