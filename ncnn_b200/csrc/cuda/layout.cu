@@ -195,6 +195,49 @@ __global__ void gather_kernel(const TS* __restrict__ src, DShape ss, TD* __restr
     }
 }
 
+// Batched 2-D transpose dst[b][j][i] = src[b][i][j] (rows x cols -> cols x rows), 32x32 shared-memory tiles: both sides
+// coalesced.  In the channel-innermost device layout a Reshape (w,h,c) -> (w*h, c) and a 2-D Permute are exactly this
+// (YOLOv8's detection head does both on its largest blobs).
+template<typename T>
+__global__ void __launch_bounds__(256) transpose2d_kernel(const T* __restrict__ src, int rows, int cols, int spitch, long long snstep, T* __restrict__ dst, int dpitch,
+                                                          long long dnstep)
+{
+    __shared__ T tile[32][33];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const T* s = src + (long long)b * snstep;
+    T* d = dst + (long long)b * dnstep;
+    const int tx = threadIdx.x, ty = threadIdx.y; // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8)
+    {
+        const int r = r0 + ty + k, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + k][tx] = s[(long long)r * spitch + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8)
+    {
+        const int c = c0 + ty + k, r = r0 + tx;
+        if (r < rows && c < cols) d[(long long)c * dpitch + r] = tile[tx][ty + k];
+    }
+}
+
+// src viewed as [n][rows][cols] (pitch spitch) -> dst [n][cols][rows] (pitch dpitch); same element type
+static int launch_transpose2d(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, int rows, int cols, int spitch, int dpitch, cudaStream_t stream)
+{
+    const int n = dst->n < 1 ? 1 : dst->n;
+    if (rows == 0 || cols == 0) return 0;
+    dim3 block(32, 8), grid(ceil_div(cols, 32), ceil_div(rows, 32), n);
+    if (grid.y > 65535 || grid.z > 65535) return 1;
+    if (src->elemtype == NCNN_CUDA_F32)
+        transpose2d_kernel<float><<<grid, block, 0, stream>>>((const float*)src->data, rows, cols, spitch, src->nstep, (float*)dst->data, dpitch, dst->nstep);
+    else
+        transpose2d_kernel<uint16_t><<<grid, block, 0, stream>>>((const uint16_t*)src->data, rows, cols, spitch, src->nstep, (uint16_t*)dst->data, dpitch, dst->nstep);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
 template<typename TS, typename TD>
 static int launch_gather(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, bool permute, const PermuteMap& pm, cudaStream_t stream)
 {
@@ -260,6 +303,21 @@ int ncnn_cuda_reshape(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, 
     NC_REQUIRE(ss.logical_count() == ds.logical_count(), "reshape: element counts differ");
     NC_REQUIRE((src->n < 1 ? 1 : src->n) == (dst->n < 1 ? 1 : dst->n), "reshape: batch differs");
     PermuteMap pm = {{0, 1, 2, 3}};
+    if (src->elemtype == dst->elemtype)
+    {
+        // (w,h,c) -> (w*h, c): rows = pixels, cols = channels of the source; the 2-D top is [c][w*h]
+        if (src->dims == 3 && dst->dims == 2 && dst->w == src->w * src->h && dst->h == src->c)
+        {
+            int r = launch_transpose2d(src, dst, src->w * src->h, src->c, src->cpitch, dst->cpitch, as_stream(stream));
+            if (r <= 0) return r;
+        }
+        // (w2, h2) -> (w, h, c) with w*h = w2, c = h2: the inverse
+        if (src->dims == 2 && dst->dims == 3 && src->w == dst->w * dst->h && src->h == dst->c)
+        {
+            int r = launch_transpose2d(src, dst, src->h, src->w, src->cpitch, dst->cpitch, as_stream(stream));
+            if (r <= 0) return r;
+        }
+    }
     return dispatch_gather(src, dst, false, pm, as_stream(stream));
 }
 
@@ -279,6 +337,12 @@ int ncnn_cuda_permute(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, 
     if (src->dims == 2)
     {
         NC_REQUIRE(order_type >= 0 && order_type < 2, "permute: bad order_type");
+        if (order_type == 1 && src->elemtype == dst->elemtype && dst->w == src->h && dst->h == src->w)
+        {
+            // 2-D blobs are [h rows][w innermost]: swapping w and h is a plain transpose
+            int r = launch_transpose2d(src, dst, src->h, src->w, src->cpitch, dst->cpitch, as_stream(stream));
+            if (r <= 0) return r;
+        }
         pm.src_of[0] = t2[order_type][0];
         pm.src_of[1] = t2[order_type][1];
     }

@@ -750,6 +750,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t acc_phase = 0;
         const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
         const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        const uint64_t adesc0 = make_smem_desc<BLOCK_K>(smem_a0), bdesc0 = make_smem_desc<BLOCK_K>(smem_b0);
         if (AMODE == A_ROWS || AMODE == A_SHIFT) mbar_wait(smem_u32(bres_bar), 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         {
@@ -826,14 +827,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tc_fence_after();
                     if (elect_one())
                     {
-                        const uint64_t adesc = make_smem_desc<BLOCK_K>(smem_a0 + stage * Plan::a_bytes);
-                        const uint64_t bdesc = make_smem_desc<BLOCK_K>(smem_b0 + stage * Plan::b_bytes);
+                        // descriptors of stage 0 are built once; a stage (and a 16-element K step inside the swizzle atom:
+                        // 32 bytes) only moves the 14-bit (address >> 4) field, which cannot carry out below 256 KB
+                        const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(stage * Plan::a_bytes) >> 4);
+                        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(stage * Plan::b_bytes) >> 4);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; k++)
-                        {
-                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr>>4) field
-                            umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
-                        }
+                        for (int k = 0; k < BLOCK_K / 16; k++) umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
                         umma_commit(empty0 + stage * 8); // frees the smem slot when these MMAs retire
                         if (kb == p.num_k_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
                     }

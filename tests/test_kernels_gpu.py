@@ -402,3 +402,43 @@ def test_innerproduct(ref, elemtype):
     run_fc(ref, rng, elemtype, 2, (5, 24), 13, True, 4)         # 2-D bottom: row-wise gemm (innerproduct.cpp:102-134)
     run_fc(ref, rng, elemtype, 1, (15,), 7, False, 2)
     run_fc(ref, rng, elemtype, 130, (1280,), 1000, True, 0)
+
+
+# ------------------------------------------------------------------------------------------ Reshape / Permute
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_reshape_permute_layout(elemtype):
+    """Reshape and Permute are pure data movement; the reference works on the planar (c,h,w) order
+    (src/layer/reshape.cpp, permute.cpp:38-73), so numpy's reshape / transpose of the planar array IS the reference
+    result.  Covers the tiled-transpose fast paths (3-D -> 2-D reshape, 2-D permute: YOLOv8's head) and the generic gather."""
+    L = cabi.lib()
+    L.ncnn_cuda_reshape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ncnn_cuda_permute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(41)
+    for (n, c, h, w) in [(2, 144, 20, 20), (3, 65, 7, 9), (1, 8, 33, 31), (2, 33, 1, 70)]:
+        x = quant(rand(rng, (n, c, h, w)), elemtype)
+        src = cabi.Blob.from_numpy(x, elemtype)
+        # (w,h,c) -> (w*h, c): planar reshape to (c, h*w)
+        dst = cabi.Blob((c, h * w), n, elemtype, fill=float("nan"))
+        sd, dd = src.desc(), dst.desc()
+        cabi.check(L.ncnn_cuda_reshape(C.byref(sd), C.byref(dd), None), "reshape 3d->2d")
+        sync()
+        assert np.array_equal(dst.numpy(), x.reshape(n, c, h * w))
+        # 2-D permute order 1: (w,h) -> (h,w)
+        per = cabi.Blob((h * w, c), n, elemtype, fill=float("nan"))
+        pd = per.desc()
+        cabi.check(L.ncnn_cuda_permute(C.byref(dd), C.byref(pd), 1, None), "permute 2d")
+        sync()
+        assert np.array_equal(per.numpy(), x.reshape(n, c, h * w).transpose(0, 2, 1))
+        # back: 2-D (w*h, c) -> 3-D
+        back = cabi.Blob((c, h, w), n, elemtype, fill=float("nan"))
+        bd = back.desc()
+        cabi.check(L.ncnn_cuda_reshape(C.byref(dd), C.byref(bd), None), "reshape 2d->3d")
+        sync()
+        assert np.array_equal(back.numpy(), x)
+        # a reshape the fast path must decline: (w,h,c) -> (w*c, h) style regrouping goes through the generic gather
+        if (c * h) % 2 == 0:
+            g = cabi.Blob((2, c * h // 2, w), n, elemtype, fill=float("nan"))
+            gd = g.desc()
+            cabi.check(L.ncnn_cuda_reshape(C.byref(sd), C.byref(gd), None), "reshape generic")
+            sync()
+            assert np.array_equal(g.numpy(), x.reshape(n, 2, c * h // 2, w))
