@@ -172,7 +172,7 @@ def main():
         cpu_batch = 8 if model != "squeezenet_v1_1" else 16
         reps = max(1, min(args.steps, 3))
         r = cpu_reference_run(model, size, cpu_batch, reps)
-        line = {"impl": "reference", "metric": "images/sec", "value": r["images_per_s"], "unit": "images/s", "n_gpus": 0, "steps": reps, "warmup": 1,
+        line = {"impl": "reference", "metric": "images/sec", "value": r["images_per_s"], "unit": "images/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": reps, "warmup": 1,
                 "ms_per_step": 1000.0 * float(np.mean(r["seconds"])), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": dict(config, workload="%s %dx%d, reference CPU path, bounded sample of %d images per step" % (model, size, size, cpu_batch)),
                 "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": r["threads"], "kind": "reference",
