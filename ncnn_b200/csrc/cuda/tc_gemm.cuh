@@ -904,7 +904,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 row_ok = pix < p.M;
             }
             T* const orow = reinterpret_cast<T*>(p.out) + pix * p.out_cpitch + n0;
-            const float* const brow = bias_in_smem ? (smem_bias + n0) : (p.bias + n0);
 
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
@@ -951,16 +950,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int col0 = g * 32;
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)col0, r);
-                // bias of the group while the TMEM load is in flight
+                // bias of the group while the TMEM load is in flight (LDS broadcast; layers whose bias vector does not fit in shared
+                // memory read it through the read-only path -- kept as two explicit branches so that the common one is LDS, not
+                // a generic load with its descriptor set-up)
                 float bv[32];
-#pragma unroll
-                for (int q = 0; q < 8; q++)
+                if (bias_in_smem)
                 {
-                    const float4 b4 = *reinterpret_cast<const float4*>(brow + col0 + 4 * q);
-                    bv[4 * q + 0] = b4.x;
-                    bv[4 * q + 1] = b4.y;
-                    bv[4 * q + 2] = b4.z;
-                    bv[4 * q + 3] = b4.w;
+                    const float* bs = smem_bias + n0 + col0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                    {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * q);
+                        bv[4 * q + 0] = b4.x;
+                        bv[4 * q + 1] = b4.y;
+                        bv[4 * q + 2] = b4.z;
+                        bv[4 * q + 3] = b4.w;
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                    {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col0) + q);
+                        bv[4 * q + 0] = b4.x;
+                        bv[4 * q + 1] = b4.y;
+                        bv[4 * q + 2] = b4.z;
+                        bv[4 * q + 3] = b4.w;
+                    }
                 }
                 const uint32_t slot_no = slots_seen + (uint32_t)cc;
                 const int rslot = (int)(slot_no % kResSlots);
