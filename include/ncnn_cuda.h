@@ -255,6 +255,15 @@ NCNN_CUDA_API int ncnn_cuda_gemm_strided(const ncnn_cuda_gemm_args* args, void* 
 #define NCNN_CUDA_UNARY_HARDSIGMOID 10 /* p0 = alpha, p1 = beta */
 NCNN_CUDA_API int ncnn_cuda_unary(int op, float p0, float p1, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
 
+/* BatchNorm (src/layer/batchnorm.cpp:57-120: value = b * value + a) and Scale (src/layer/scale.cpp:44-168: value * s + bias):
+ * top = bottom * scale[i] + shift[i], i = channel for 1-D/3-D/4-D blobs, i = row (h) for 2-D blobs.  scale/shift are DEVICE
+ * fp32 arrays (shift may be NULL = 0); bottom == top (in place) is allowed. */
+NCNN_CUDA_API int ncnn_cuda_channel_affine(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const float* scale_dev, const float* shift_dev, void* stream);
+
+/* ShuffleChannel (src/layer/shufflechannel.cpp:22-60): top channel group*j + i = bottom channel (c/group)*i + j.
+ * `group` is the effective group count (the caller resolves the layer's `reverse` flag: group = c / group). */
+NCNN_CUDA_API int ncnn_cuda_shuffle_channel(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group, void* stream);
+
 /* Eltwise src/layer/eltwise.cpp:22-178: op 0 PROD, 1 SUM (optional coeffs), 2 MAX over `count` same-shape
  * bottoms; `relu` fuses a following ReLU layer (graph-level fold). */
 NCNN_CUDA_API int ncnn_cuda_eltwise(int op, const ncnn_cuda_tensor* bottoms, int count, const float* coeffs, int relu, const ncnn_cuda_tensor* top, void* stream);

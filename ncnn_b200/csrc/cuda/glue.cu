@@ -742,6 +742,108 @@ static int run_padding(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* t
     return 0;
 }
 
+// ---------------------------------------------------------------- BatchNorm / Scale / ShuffleChannel
+namespace {
+
+// y = x * scale[i] + shift[i] with i = channel (dims 1, 3, 4: the innermost index) or i = row (dims 2); src/layer/batchnorm.cpp:57-120
+// (value = b * value + a) and src/layer/scale.cpp:44-168.  One thread per 16-byte channel vector when the channel count allows.
+template<typename T, int VEC>
+__global__ void __launch_bounds__(256) channel_affine_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             int P, int C, int in_cpitch, int out_cpitch, long long in_nstep, long long out_nstep, int n, int per_row)
+{
+    const int CV = (C + VEC - 1) / VEC;
+    const long long total = (long long)n * P * CV;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        const int cv = (int)(idx % CV);
+        long long r = idx / CV;
+        const int pix = (int)(r % P);
+        const int b = (int)(r / P);
+        const int c0 = cv * VEC;
+        float x[VEC];
+        load_vec_f32<T, VEC>(in + (long long)b * in_nstep + (long long)pix * in_cpitch + c0, x);
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+        {
+            const int i = per_row ? pix : (c0 + v < C ? c0 + v : C - 1);
+            x[v] = fmaf(x[v], scale[i], shift ? shift[i] : 0.f);
+        }
+        store_vec_f32<T, VEC>(out + (long long)b * out_nstep + (long long)pix * out_cpitch + c0, x);
+    }
+}
+
+template<typename T>
+static int run_channel_affine(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const float* scale, const float* shift, int per_row, cudaStream_t stream)
+{
+    TView bv = make_view(bottom), tv = make_view(top);
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int cround = ((bv.C + VEC - 1) / VEC) * VEC;
+    const bool vec_ok = (bv.cpitch % VEC == 0) && (tv.cpitch % VEC == 0) && (bv.nstep % VEC == 0) && (tv.nstep % VEC == 0) && (((uintptr_t)bottom->data & 15) == 0)
+                        && (((uintptr_t)top->data & 15) == 0) && cround <= bv.cpitch && cround <= tv.cpitch;
+    if (vec_ok)
+    {
+        const long long total = (long long)bv.n * bv.P * (cround / VEC);
+        channel_affine_kernel<T, VEC><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, scale, shift, bv.P, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
+                                                                               tv.nstep, bv.n, per_row);
+    }
+    else
+    {
+        const long long total = (long long)bv.n * bv.P * bv.C;
+        channel_affine_kernel<T, 1><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, scale, shift, bv.P, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
+                                                                             tv.nstep, bv.n, per_row);
+    }
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+// out[pixel][group * j + i] = in[pixel][cpg * i + j]  (src/layer/shufflechannel.cpp:30-57); consecutive threads write consecutive channels
+template<typename T>
+__global__ void __launch_bounds__(256) shuffle_channel_kernel(const T* __restrict__ in, T* __restrict__ out, int P, int C, int group, int in_cpitch, int out_cpitch,
+                                                              long long in_nstep, long long out_nstep, int n)
+{
+    const int cpg = C / group;
+    const long long total = (long long)n * P * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        const int dq = (int)(idx % C);
+        long long r = idx / C;
+        const int pix = (int)(r % P);
+        const int b = (int)(r / P);
+        const int j = dq / group, i = dq - j * group;
+        out[(long long)b * out_nstep + (long long)pix * out_cpitch + dq] = in[(long long)b * in_nstep + (long long)pix * in_cpitch + cpg * i + j];
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int ncnn_cuda_channel_affine(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const float* scale_dev, const float* shift_dev, void* stream)
+{
+    NC_REQUIRE(bottom && top && scale_dev && same_shape(bottom, top) && bottom->elemtype == top->elemtype, "channel_affine: shape/type mismatch");
+    const int per_row = bottom->dims == 2;
+    NC_DISPATCH_T(bottom->elemtype, run_channel_affine<T>(bottom, top, scale_dev, shift_dev, per_row, as_stream(stream)));
+}
+
+int ncnn_cuda_shuffle_channel(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group, void* stream)
+{
+    NC_REQUIRE(bottom && top && same_shape(bottom, top) && bottom->elemtype == top->elemtype && bottom->dims >= 3, "shuffle_channel: a 3-D/4-D blob pair of one type is required");
+    NC_REQUIRE(group > 0 && bottom->c % group == 0, "shuffle_channel: channels not divisible by group");
+    TView bv = make_view(bottom), tv = make_view(top);
+    const long long total = (long long)bv.n * bv.P * bv.C;
+    if (total == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (bottom->elemtype == NCNN_CUDA_F32)
+        shuffle_channel_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)bottom->data, (float*)top->data, bv.P, bv.C, group, bv.cpitch, tv.cpitch, bv.nstep, tv.nstep, bv.n);
+    else
+        shuffle_channel_kernel<uint16_t><<<grid_for(total, 256), 256, 0, st>>>((const uint16_t*)bottom->data, (uint16_t*)top->data, bv.P, bv.C, group, bv.cpitch, tv.cpitch, bv.nstep,
+                                                                              tv.nstep, bv.n);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+} // extern "C"
+
 extern "C" {
 
 int ncnn_cuda_unary(int op, float p0, float p1, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream)

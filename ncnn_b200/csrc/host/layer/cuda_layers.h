@@ -192,6 +192,50 @@ public:
     virtual int load_param(const ParamDict& pd);
 };
 
+// a constant host Mat (1-D / 2-D) as a device blob of the same logical shape, allocated from the weight allocator (gemm_layer.cpp)
+int upload_const(const Mat& src, int elemtype, CudaMat& dst);
+
+// src/layer/batchnorm.cpp -- inference form: value = b * value + a per channel (per row for 2-D blobs)
+class BatchNorm : public Layer
+{
+public:
+    BatchNorm();
+    virtual int load_param(const ParamDict& pd);
+    virtual int load_model(const ModelBin& mb);
+    virtual int create_pipeline(const Option& opt);
+    virtual int destroy_pipeline(const Option& opt);
+    virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
+    int channels;
+    float eps;
+    Mat a_data, b_data;
+    CudaMat a_dev, b_dev;
+};
+
+// src/layer/scale.cpp -- value * scale (+ bias) per channel; the two-input form (scale_data_size = -233) is not on the device path
+class Scale : public Layer
+{
+public:
+    Scale();
+    virtual int load_param(const ParamDict& pd);
+    virtual int load_model(const ModelBin& mb);
+    virtual int create_pipeline(const Option& opt);
+    virtual int destroy_pipeline(const Option& opt);
+    virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
+    int scale_data_size, bias_term;
+    Mat scale_data, bias_data;
+    CudaMat scale_dev, bias_dev;
+};
+
+// src/layer/shufflechannel.cpp
+class ShuffleChannel : public Layer
+{
+public:
+    ShuffleChannel();
+    virtual int load_param(const ParamDict& pd);
+    virtual int forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const;
+    int group, reverse;
+};
+
 class Eltwise : public Layer
 {
 public:

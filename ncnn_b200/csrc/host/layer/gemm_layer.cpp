@@ -75,7 +75,7 @@ int Gemm::load_model(const ModelBin& mb)
     return 0;
 }
 
-static int upload_const(const Mat& src, int elemtype, CudaMat& dst)
+int upload_const(const Mat& src, int elemtype, CudaMat& dst)
 {
     // constants are 1-D/2-D host Mats; keep them as device blobs of the same logical shape
     CudaContext* ctx = acquire_cuda_context(-1);

@@ -35,6 +35,9 @@ DEFINE_LAYER_CREATOR(Reshape)
 DEFINE_LAYER_CREATOR(Flatten)
 DEFINE_LAYER_CREATOR(Permute)
 DEFINE_LAYER_CREATOR(Padding)
+DEFINE_LAYER_CREATOR(BatchNorm)
+DEFINE_LAYER_CREATOR(Scale)
+DEFINE_LAYER_CREATOR(ShuffleChannel)
 
 static const layer_registry_entry cuda_layer_registry[] = {
     {"Input", Input_layer_creator},
@@ -63,6 +66,9 @@ static const layer_registry_entry cuda_layer_registry[] = {
     {"Flatten", Flatten_layer_creator},
     {"Permute", Permute_layer_creator},
     {"Padding", Padding_layer_creator},
+    {"BatchNorm", BatchNorm_layer_creator},
+    {"Scale", Scale_layer_creator},
+    {"ShuffleChannel", ShuffleChannel_layer_creator},
 };
 
 static const int layer_type_count = (int)(sizeof(layer_type_names) / sizeof(layer_type_names[0]));

@@ -442,3 +442,54 @@ def test_reshape_permute_layout(elemtype):
             cabi.check(L.ncnn_cuda_reshape(C.byref(sd), C.byref(gd), None), "reshape generic")
             sync()
             assert np.array_equal(g.numpy(), x.reshape(n, 2, c * h // 2, w))
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm / Scale / ShuffleChannel
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_batchnorm_scale_shufflechannel(ref, elemtype):
+    """per-channel affine (BatchNorm: b*x + a, Scale: x*s + bias) and the ShuffleChannel permutation against the reference's
+    naive layers (src/layer/batchnorm.cpp, scale.cpp, shufflechannel.cpp); 1-D, 2-D (per-row) and 3-D blobs, channel counts
+    that are not a multiple of the vector width"""
+    import torch
+    L = cabi.lib()
+    L.ncnn_cuda_channel_affine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ncnn_cuda_shuffle_channel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(51)
+    tol = 1e-5 if elemtype == F32 else 1e-4
+    for shape in [(24, 9, 11), (7, 5, 6), (64, 14, 14), (13, 40), (37,)]:
+        n = 3
+        ch = shape[0]
+        x = quant(rand(rng, (n,) + shape), elemtype)
+        slope, mean = rand(rng, (ch,), 0.5, 1.5), rand(rng, (ch,), -0.3, 0.3)
+        var, bias = rand(rng, (ch,), 0.4, 1.6), rand(rng, (ch,), -0.2, 0.2)
+        eps = np.float32(1e-5)
+        # BatchNorm
+        want = ref.layer_forward("BatchNorm", {0: ch, 1: float(eps)}, [slope, mean, var, bias], [x], batched=True)[0]
+        sq = np.sqrt(var + eps, dtype=np.float32)
+        a = (bias - slope * mean / sq).astype(np.float32)
+        b = (slope / sq).astype(np.float32)
+        ad, bdv = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        blob = cabi.Blob.from_numpy(x, elemtype, pad_fill=0.0)
+        d = blob.desc()
+        cabi.check(L.ncnn_cuda_channel_affine(C.byref(d), C.byref(d), C.c_void_p(bdv.data_ptr()), C.c_void_p(ad.data_ptr()), None), "batchnorm")
+        sync()
+        assert nerr(blob.numpy(), want, elemtype) <= tol, ("batchnorm", shape)
+        # Scale with and without bias
+        for bias_term in (1, 0):
+            want = ref.layer_forward("Scale", {0: ch, 1: bias_term}, [slope] + ([bias] if bias_term else []), [x], batched=True)[0]
+            sd, bd = torch.from_numpy(slope).cuda(), torch.from_numpy(bias).cuda()
+            blob = cabi.Blob.from_numpy(x, elemtype, pad_fill=0.0)
+            d = blob.desc()
+            cabi.check(L.ncnn_cuda_channel_affine(C.byref(d), C.byref(d), C.c_void_p(sd.data_ptr()), C.c_void_p(bd.data_ptr()) if bias_term else None, None), "scale")
+            sync()
+            assert nerr(blob.numpy(), want, elemtype) <= tol, ("scale", shape, bias_term)
+    for (ch, h, w, group, reverse) in [(24, 9, 11, 3, 0), (24, 9, 11, 3, 1), (116, 7, 7, 2, 0), (30, 5, 4, 5, 0), (8, 3, 3, 1, 0)]:
+        x = quant(rand(rng, (2, ch, h, w)), elemtype)
+        want = ref.layer_forward("ShuffleChannel", {0: group, 1: reverse}, [], [x], batched=True)[0]
+        src = cabi.Blob.from_numpy(x, elemtype)
+        dst = cabi.Blob((ch, h, w), 2, elemtype, fill=float("nan"))
+        sd, dd = src.desc(), dst.desc()
+        g = ch // group if reverse else group
+        cabi.check(L.ncnn_cuda_shuffle_channel(C.byref(sd), C.byref(dd), g, None), "shuffle_channel")
+        sync()
+        assert np.array_equal(dst.numpy(), want), ("shufflechannel", ch, group, reverse)

@@ -165,3 +165,33 @@ def test_unknown_layer_fails_loudly():
     text = "7767517\n2 2\nInput data 0 1 data 0=4 1=4 2=1\nLSTM l 1 1 data out 0=4\n"
     assert L.lib.ncnn_net_load_param_memory(net, text.encode()) != 0
     L.lib.ncnn_net_destroy(net)
+
+
+UNFUSED_PARAM = """7767517
+12 13
+Input            data      0 1 data 0=24 1=24 2=3
+Convolution      conv1     1 1 data conv1 0=24 1=3 3=1 4=1 5=0 6=648
+BatchNorm        bn1       1 1 conv1 bn1 0=24 1=0.00001
+Scale            scale1    1 1 bn1 scale1 0=24 1=1
+ReLU             relu1     1 1 scale1 relu1
+Split            split1    1 2 relu1 relu1_a relu1_b
+Convolution      conv2     1 1 relu1_a conv2 0=24 1=1 5=0 6=576
+BatchNorm        bn2       1 1 conv2 bn2 0=24 1=0.001
+ShuffleChannel   shuf      1 1 relu1_b shuf 0=3
+Concat           cat       2 1 bn2 shuf cat 0=0
+ShuffleChannel   shuf2     1 1 cat shuf2 0=2 1=1
+InnerProduct     fc        1 1 shuf2 fc 0=10 1=1 2=276480
+"""
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_unfused_batchnorm_scale_shufflechannel_graph(ref, mode):
+    """BatchNorm / Scale / ShuffleChannel as they appear in un-fused and ShuffleNet-style graphs, through
+    Net.load_param / load_model / Extractor against the reference CPU path on the same bytes"""
+    text = UNFUSED_PARAM
+    weights = modelzoo.random_model_bytes(text, seed=11)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (3, 3, 24, 24)).astype(np.float32)
+    want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=["fc"])["fc"]
+    got = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=["fc"])["fc"]
+    assert nerr(got, want) <= TOL[mode], nerr(got, want)

@@ -378,7 +378,20 @@ def random_model_bytes(text, seed=7767517, bias_scale=0.1, dtype=np.float32):
             chunks.append(w.tobytes())
             if bias_term:
                 chunks.append(rng.uniform(-bias_scale, bias_scale, num_output).astype(np.float32).tobytes())
-        elif t in ("BatchNorm", "Scale", "PReLU", "Gemm", "Deconvolution"):
+        elif t == "BatchNorm":
+            # src/layer/batchnorm.cpp:22-38: slope, mean, var, bias -- raw fp32, no tag (ModelBin type 1)
+            c = p[0]
+            chunks.append(rng.uniform(0.5, 1.5, c).astype(np.float32).tobytes())
+            chunks.append(rng.uniform(-0.3, 0.3, c).astype(np.float32).tobytes())
+            chunks.append(rng.uniform(0.4, 1.6, c).astype(np.float32).tobytes())
+            chunks.append(rng.uniform(-0.2, 0.2, c).astype(np.float32).tobytes())
+        elif t == "Scale":
+            # src/layer/scale.cpp:25-42: scale (+ bias), raw fp32
+            c = p[0]
+            chunks.append(rng.uniform(0.5, 1.5, c).astype(np.float32).tobytes())
+            if p.get(1, 0):
+                chunks.append(rng.uniform(-0.2, 0.2, c).astype(np.float32).tobytes())
+        elif t in ("PReLU", "Gemm", "Deconvolution"):
             raise NotImplementedError("random weights for " + t)
     return b"".join(chunks)
 
