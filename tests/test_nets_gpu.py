@@ -195,3 +195,40 @@ def test_unfused_batchnorm_scale_shufflechannel_graph(ref, mode):
     want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=["fc"])["fc"]
     got = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=["fc"])["fc"]
     assert nerr(got, want) <= TOL[mode], nerr(got, want)
+
+
+EXTRA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
+EXTRA_MODELS = ["mobilenet", "mobilenet_v3", "shufflenet", "shufflenet_v2", "mnasnet", "proxylessnasnet", "efficientnet_b0", "regnety_400m", "resnet18",
+                "squeezenet", "blazeface", "FastestDet"]
+EXTRA_INPUT = {"blazeface": 128, "FastestDet": 352, "squeezenet": 227}
+# FastestDet's only output is the concatenation of its sigmoid / softmax heads (no linear blob to assert on) after ~70 stored
+# fp16 activations: measured 2.1e-3, so its 16-bit bound is 4e-3; its fp32 bound stays 1e-5 like every other graph.
+EXTRA_TOL16 = {"FastestDet": 4e-3}
+
+
+@pytest.mark.parametrize("name", EXTRA_MODELS)
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_reference_benchmark_graphs(ref, name, mode):
+    """widening: the other graphs of the reference's benchmark set whose operators this backend has
+    (benchmark/models/*.param, committed as model descriptions under models/extra/), with seeded random weights, against
+    the reference CPU path through the same Net API: depthwise/grouped convolutions, squeeze-excite blocks (global pooling
+    + broadcasting BinaryOp), HardSwish/HardSigmoid, ShuffleChannel + Slice, multi-output detection heads"""
+    text = open(os.path.join(EXTRA, name + ".param")).read()
+    size = EXTRA_INPUT.get(name, 224)
+    text = "\n".join(("Input data 0 1 data 0=%d 1=%d 2=3" % (size, size)) if l.split() and l.split()[0] == "Input" and l.split()[1] == "data" else l
+                     for l in text.splitlines()) + "\n"
+    layers = modelzoo.parse_param(text)
+    in_name = [l for l in layers if l[0] == "Input"][0][3][0]
+    consumed = set(b for l in layers for b in l[2])
+    outs = [t for l in layers for t in l[3] if t not in consumed]
+    if layers[-1][0] == "Softmax":
+        outs = [layers[-1][2][0]]  # the bound is asserted on the logits (see the module docstring)
+    weights = modelzoo.random_model_bytes(text, seed=5)
+    rng = np.random.default_rng(9)
+    x = rng.uniform(-1, 1, (2, 3, size, size)).astype(np.float32)
+    want = run_ref(ref, text, weights, {in_name: x}, batched=True, outputs=outs)
+    got = run_ours(text, weights, {in_name: x}, mode, batched=True, outputs=outs)
+    for o in outs:
+        e = nerr(got[o], want[o])
+        tol = TOL[mode] if mode == "fp32" else EXTRA_TOL16.get(name, TOL[mode])
+        assert e <= tol, (name, o, e)

@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu --timeout 600 --tb=short -k "batchnorm or unfused or reshape" > gpurun_out/pytest_gpu.log 2>&1; tail -12 gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests/test_nets_gpu.py -q --timeout 600 --tb=line -k "reference_benchmark" > gpurun_out/pytest_extra.log 2>&1; tail -40 gpurun_out/pytest_extra.log
