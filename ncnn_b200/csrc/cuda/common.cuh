@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "ncnn_cuda.h"
 
@@ -227,6 +228,25 @@ __device__ __forceinline__ float apply_activation(float v, int type, float p0, f
         break;
     }
     return v;
+}
+
+// launch with the programmatic-stream-serialization attribute (see tc::pdl_wait in tc_gemm.cuh); the kernel MUST call
+// griddepcontrol.wait before it touches memory the previous kernel of the stream reads or writes
+template<typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 static inline int ceil_div(long long a, long long b)

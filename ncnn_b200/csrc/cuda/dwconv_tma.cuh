@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
     uint64_t* empty_bar = full_bar + 4;
 
     const int tid = threadIdx.x;
+    tc::pdl_launch_dependents();
     if (tid == 0)
     {
         tc::prefetch_tmap(&tmap_in);
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
         smem_w[i] = t < 9 ? p.w[(long long)t * p.cpad + c] : (p.bias ? p.bias[c] : 0.f);
     }
     __syncthreads();
+    tc::pdl_wait(); // the filter slice above is a constant; the previous layer's blob is touched only from here on
 
     if (tid >= kConsumers)
     {
@@ -352,7 +354,7 @@ static int launch_dw_tma(const CUtensorMap& tm, T* out, Params& p, cudaStream_t 
     if (groups < 1) groups = 1;
     if (groups > n_spatial) groups = n_spatial;
     const int grid = (int)(groups * cblocks);
-    kern<<<grid, kThreads, C::smem_bytes, stream>>>(tm, out, p);
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)C::smem_bytes, stream, tm, out, p));
     NC_LAUNCH_CHECK();
     return 0;
 }

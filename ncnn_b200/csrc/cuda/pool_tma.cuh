@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 2) maxpool_tma_kernel(const __grid_c
     uint64_t* empty_bar = full_bar + 4;
 
     const int tid = threadIdx.x;
+    tc::pdl_launch_dependents();
     if (tid == 0)
     {
         tc::prefetch_tmap(&tmap_in);
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kThreads, 2) maxpool_tma_kernel(const __grid_c
         tc::fence_barrier_init();
     }
     __syncthreads();
+    tc::pdl_wait();
 
     // one channel block per CTA, striding over the spatial tiles (see dwconv_tma.cuh)
     const int cb = blockIdx.x % p.cblocks;
@@ -239,7 +241,7 @@ static int launch_pool_tma(const void* in, int elemtype, const unsigned long lon
     long long groups = (2LL * sm_count()) / p.cblocks;
     if (groups < 1) groups = 1;
     if (groups > n_spatial) groups = n_spatial;
-    kern<<<(int)(groups * p.cblocks), kThreads, C::smem_bytes, stream>>>(tm, out, p);
+    NC_CHECK(launch_pdl(kern, dim3((unsigned int)(groups * p.cblocks)), dim3(kThreads), (size_t)C::smem_bytes, stream, tm, out, p));
     NC_LAUNCH_CHECK();
     return 0;
 }

@@ -420,7 +420,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
         smem_bytes = Plan::total_for(has_res);
     }
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, tc::kNumThreads, smem_bytes, stream>>>(ta, tb, tr, p);
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, p));
     NC_LAUNCH_CHECK();
     return 0;
 }

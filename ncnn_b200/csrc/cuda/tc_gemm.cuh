@@ -138,6 +138,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still draining; everything before pdl_wait() (barrier / TMEM set-up, constant loads)
+// overlaps that tail, pdl_wait() returns once the predecessor has completed and its writes are visible.
+// pdl_launch_dependents() lets the successor start its own prologue as soon as SM resources free up.
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // true in exactly one lane of a converged warp
 __device__ __forceinline__ bool elect_one()
 {
@@ -542,6 +555,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     const int num_n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
     int num_m_blocks;
@@ -594,6 +608,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // everything above touched only constants (bias, descriptors) and on-chip state; activations of the previous layer are
+    // read -- and recycled pool blocks written -- only from here on
+    pdl_wait();
 
     if (warp == 0)
     {
