@@ -249,6 +249,27 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// every kernel of the backend starts with NC_PDL_PROLOGUE() and is launched with NC_PDL_LAUNCH: the next kernel of the stream
+// may be scheduled while this one drains (its launch latency disappears), and no kernel touches memory before its
+// predecessor has completed.  The TMA kernels place the wait after their on-chip set-up instead (tc::pdl_wait).
+#define NC_PDL_PROLOGUE()                                                  \
+    do                                                                     \
+    {                                                                      \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                 \
+    } while (0)
+
+#define NC_PDL_LAUNCH(kernel, grid, block, smem, stream, ...)                                                                   \
+    do                                                                                                                          \
+    {                                                                                                                           \
+        cudaError_t _le = ncnn_cuda::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__);          \
+        if (_le != cudaSuccess)                                                                                                 \
+        {                                                                                                                       \
+            ncnn_cuda::set_last_error("kernel launch", _le, __FILE__, __LINE__);                                               \
+            return -100;                                                                                                        \
+        }                                                                                                                       \
+    } while (0)
+
 static inline int ceil_div(long long a, long long b)
 {
     return (int)((a + b - 1) / b);

@@ -41,6 +41,7 @@ struct DwGeom
 template<typename T, int VEC, int OWT>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, DwGeom g)
 {
+    NC_PDL_PROLOGUE();
     const int CV = (g.C + VEC - 1) / VEC;
     const int OWB = (g.outw + OWT - 1) / OWT;
     const long long total = (long long)g.n * g.outh * OWB * CV;
@@ -139,6 +140,7 @@ struct GroupGeom
 template<typename T>
 __global__ void grouped_conv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, GroupGeom g)
 {
+    NC_PDL_PROLOGUE();
     const int outch = g.outch_g * g.group;
     const long long total = (long long)g.n * g.outh * g.outw * outch;
     const int taps = g.kw * g.kh;
@@ -217,18 +219,18 @@ static int run_depthwise(const ncnn_cuda_dwconv2d* conv, const ncnn_cuda_tensor*
         {
             constexpr int OWT = 4;
             long long total = (long long)g.n * g.outh * ((g.outw + OWT - 1) / OWT) * CV;
-            dwconv_kernel<T, VEC, OWT><<<grid_for(total, 256, 16), 256, 0, stream>>>(in, conv->w_dev, conv->bias_dev, out, g);
+            NC_PDL_LAUNCH((dwconv_kernel<T, VEC, OWT>), grid_for(total, 256, 16), 256, 0, stream, in, conv->w_dev, conv->bias_dev, out, g);
         }
         else
         {
             long long total = (long long)g.n * g.outh * g.outw * CV;
-            dwconv_kernel<T, VEC, 1><<<grid_for(total, 256, 16), 256, 0, stream>>>(in, conv->w_dev, conv->bias_dev, out, g);
+            NC_PDL_LAUNCH((dwconv_kernel<T, VEC, 1>), grid_for(total, 256, 16), 256, 0, stream, in, conv->w_dev, conv->bias_dev, out, g);
         }
     }
     else
     {
         long long total = (long long)g.n * g.outh * g.outw * g.C;
-        dwconv_kernel<T, 1, 1><<<grid_for(total, 256, 16), 256, 0, stream>>>(in, conv->w_dev, conv->bias_dev, out, g);
+        NC_PDL_LAUNCH((dwconv_kernel<T, 1, 1>), grid_for(total, 256, 16), 256, 0, stream, in, conv->w_dev, conv->bias_dev, out, g);
     }
     NC_LAUNCH_CHECK();
     return 0;
@@ -238,7 +240,7 @@ template<typename T>
 static int run_grouped(const ncnn_cuda_dwconv2d* conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const GroupGeom& g, cudaStream_t stream)
 {
     long long total = (long long)g.n * g.outh * g.outw * g.outch_g * g.group;
-    grouped_conv_kernel<T><<<grid_for(total, 256, 16), 256, 0, stream>>>((const T*)bottom->data, conv->w_dev, conv->bias_dev, (T*)top->data, g);
+    NC_PDL_LAUNCH((grouped_conv_kernel<T>), grid_for(total, 256, 16), 256, 0, stream, (const T*)bottom->data, conv->w_dev, conv->bias_dev, (T*)top->data, g);
     NC_LAUNCH_CHECK();
     return 0;
 }

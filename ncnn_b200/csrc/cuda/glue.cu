@@ -63,6 +63,7 @@ __device__ __forceinline__ float unary_apply(int op, float v, float p0, float p1
 template<typename T, int VEC>
 __global__ void __launch_bounds__(256) unary_flat_kernel(const T* __restrict__ in, T* __restrict__ out, long long count, int op, float p0, float p1)
 {
+    NC_PDL_PROLOGUE();
     const long long nvec = count / VEC;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
     {
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) unary_flat_kernel(const T* __restrict__ i
 template<typename T>
 __global__ void unary_strided_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int P, int C, int icp, long long ins, int ocp, long long ons, int op, float p0, float p1)
 {
+    NC_PDL_PROLOGUE();
     const long long total = (long long)n * P * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     {
@@ -99,14 +101,14 @@ static int run_unary(int op, float p0, float p1, const ncnn_cuda_tensor* bottom,
     {
         long long count = flat_count(bottom);
         if (count == 0) return 0;
-        unary_flat_kernel<T, VEC><<<grid_for(count / VEC + 1, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, count, op, p0, p1);
+        NC_PDL_LAUNCH((unary_flat_kernel<T, VEC>), grid_for(count / VEC + 1, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, count, op, p0, p1);
     }
     else
     {
         TView b = make_view(bottom), t = make_view(top);
         long long total = (long long)b.n * b.P * b.C;
         if (total == 0) return 0;
-        unary_strided_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, b.n, b.P, b.C, b.cpitch, b.nstep, t.cpitch, t.nstep, op, p0, p1);
+        NC_PDL_LAUNCH((unary_strided_kernel<T>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, b.n, b.P, b.C, b.cpitch, b.nstep, t.cpitch, t.nstep, op, p0, p1);
     }
     NC_LAUNCH_CHECK();
     return 0;
@@ -126,6 +128,7 @@ struct EltArgs
 template<typename T, int VEC>
 __global__ void __launch_bounds__(256) eltwise_flat_kernel(EltArgs a, T* __restrict__ out, long long count)
 {
+    NC_PDL_PROLOGUE();
     const long long nvec = (count + VEC - 1) / VEC; // buffers are padded to VEC multiples (cpitch % VEC == 0)
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
     {
@@ -169,6 +172,7 @@ struct EltStrided
 template<typename T>
 __global__ void eltwise_strided_kernel(EltArgs a, EltStrided s, T* __restrict__ out, int n, int P, int C, int ocp, long long ons)
 {
+    NC_PDL_PROLOGUE();
     const long long total = (long long)n * P * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     {
@@ -203,7 +207,7 @@ static int run_eltwise(EltArgs& a, const ncnn_cuda_tensor* bottoms, const ncnn_c
     {
         long long count = flat_count(top);
         if (count == 0) return 0;
-        eltwise_flat_kernel<T, VEC><<<grid_for(count / VEC, 256), 256, 0, stream>>>(a, (T*)top->data, count);
+        NC_PDL_LAUNCH((eltwise_flat_kernel<T, VEC>), grid_for(count / VEC, 256), 256, 0, stream, a, (T*)top->data, count);
     }
     else
     {
@@ -216,7 +220,7 @@ static int run_eltwise(EltArgs& a, const ncnn_cuda_tensor* bottoms, const ncnn_c
         TView t = make_view(top);
         long long total = (long long)t.n * t.P * t.C;
         if (total == 0) return 0;
-        eltwise_strided_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(a, s, (T*)top->data, t.n, t.P, t.C, t.cpitch, t.nstep);
+        NC_PDL_LAUNCH((eltwise_strided_kernel<T>), grid_for(total, 256), 256, 0, stream, a, s, (T*)top->data, t.n, t.P, t.C, t.cpitch, t.nstep);
     }
     NC_LAUNCH_CHECK();
     return 0;
@@ -273,6 +277,7 @@ template<typename T>
 __global__ void binary_broadcast_kernel(const T* __restrict__ a, BShape sa, const T* __restrict__ b, BShape sb, float scalar, int use_scalar, T* __restrict__ out,
                                         BShape so, int n, int op)
 {
+    NC_PDL_PROLOGUE();
     const long long total = (long long)n * so.d * so.h * so.w * so.c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     {
@@ -302,6 +307,7 @@ __global__ void binary_broadcast_kernel(const T* __restrict__ a, BShape sa, cons
 template<typename T, int VEC>
 __global__ void __launch_bounds__(256) binary_flat_kernel(const T* __restrict__ a, const T* __restrict__ b, float scalar, int use_scalar, T* __restrict__ out, long long count, int op)
 {
+    NC_PDL_PROLOGUE();
     const long long nvec = count / VEC;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x)
     {
@@ -356,7 +362,7 @@ static int run_binary(int op, const ncnn_cuda_tensor* a, const ncnn_cuda_tensor*
     {
         long long count = flat_count(top);
         if (count == 0) return 0;
-        binary_flat_kernel<T, VEC><<<grid_for(count / VEC, 256), 256, 0, stream>>>((const T*)a->data, b ? (const T*)b->data : 0, scalar, use_scalar, (T*)top->data, count, op);
+        NC_PDL_LAUNCH((binary_flat_kernel<T, VEC>), grid_for(count / VEC, 256), 256, 0, stream, (const T*)a->data, b ? (const T*)b->data : 0, scalar, use_scalar, (T*)top->data, count, op);
         NC_LAUNCH_CHECK();
         return 0;
     }
@@ -366,7 +372,7 @@ static int run_binary(int op, const ncnn_cuda_tensor* a, const ncnn_cuda_tensor*
     so.nstep = top->nstep;
     long long total = (long long)n * so.d * so.h * so.w * so.c;
     if (total == 0) return 0;
-    binary_broadcast_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>((const T*)a->data, sa, b ? (const T*)b->data : 0, sb, scalar, use_scalar, (T*)top->data, so, n, op);
+    NC_PDL_LAUNCH((binary_broadcast_kernel<T>), grid_for(total, 256), 256, 0, stream, (const T*)a->data, sa, b ? (const T*)b->data : 0, sb, scalar, use_scalar, (T*)top->data, so, n, op);
     NC_LAUNCH_CHECK();
     return 0;
 }
@@ -386,6 +392,7 @@ struct AxisCopy
 template<typename T, int VEC>
 __global__ void __launch_bounds__(256) axis_copy_kernel(const T* __restrict__ src, T* __restrict__ dst, AxisCopy a, int n)
 {
+    NC_PDL_PROLOGUE();
     const int CV = (a.sc + VEC - 1) / VEC;
     const long long total = (long long)n * a.sd * a.sh * a.sw * CV;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -459,13 +466,13 @@ static int run_axis_copy(const ncnn_cuda_tensor* small_t, const ncnn_cuda_tensor
     {
         long long total = (long long)n * a.sd * a.sh * a.sw * (ss.c / VEC);
         if (total == 0) return 0;
-        axis_copy_kernel<T, VEC><<<grid_for(total, 256), 256, 0, stream>>>(src, dst, a, n);
+        NC_PDL_LAUNCH((axis_copy_kernel<T, VEC>), grid_for(total, 256), 256, 0, stream, src, dst, a, n);
     }
     else
     {
         long long total = (long long)n * a.sd * a.sh * a.sw * ss.c;
         if (total == 0) return 0;
-        axis_copy_kernel<T, 1><<<grid_for(total, 256), 256, 0, stream>>>(src, dst, a, n);
+        NC_PDL_LAUNCH((axis_copy_kernel<T, 1>), grid_for(total, 256), 256, 0, stream, src, dst, a, n);
     }
     NC_LAUNCH_CHECK();
     return 0;
@@ -476,6 +483,7 @@ template<typename T, int VEC>
 __global__ void __launch_bounds__(256) interp_nearest_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int C, int inw, int inh, int outw, int outh, float hs, float ws,
                                                             int icp, long long ins, int ocp, long long ons)
 {
+    NC_PDL_PROLOGUE();
     const int CV = (C + VEC - 1) / VEC;
     const long long total = (long long)n * outh * outw * CV;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -525,6 +533,7 @@ template<typename T>
 __global__ void interp_bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int C, int inw, int inh, int outw, int outh, int align_corner, int icp,
                                        long long ins, int ocp, long long ons)
 {
+    NC_PDL_PROLOGUE();
     const long long total = (long long)n * outh * outw * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     {
@@ -560,6 +569,7 @@ struct SoftmaxGeom
 template<typename T>
 __global__ void __launch_bounds__(256) softmax_kernel(const T* __restrict__ in, T* __restrict__ out, SoftmaxGeom g, long long lines)
 {
+    NC_PDL_PROLOGUE();
     __shared__ float red[32];
     for (long long line = blockIdx.x; line < lines; line += gridDim.x)
     {
@@ -616,6 +626,7 @@ template<typename T>
 __global__ void padding_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int inw, int inh, int inc, int outw, int outh, int outc, int top_pad, int left_pad, int front_pad,
                                int type, float value, int icp, long long ins, int ocp, long long ons)
 {
+    NC_PDL_PROLOGUE();
     const long long total = (long long)n * outh * outw * outc;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     {
@@ -679,20 +690,20 @@ static int run_interp(int resize_type, int align_corner, float hs, float ws, con
         if (vec_ok)
         {
             long long total = (long long)n * top->h * top->w * ((C + VEC - 1) / VEC);
-            interp_nearest_kernel<T, VEC><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, n, C, bottom->w, bottom->h, top->w, top->h, hs, ws,
+            NC_PDL_LAUNCH((interp_nearest_kernel<T, VEC>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, n, C, bottom->w, bottom->h, top->w, top->h, hs, ws,
                                                                                   bottom->cpitch, bottom->nstep, top->cpitch, top->nstep);
         }
         else
         {
             long long total = (long long)n * top->h * top->w * C;
-            interp_nearest_kernel<T, 1><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, n, C, bottom->w, bottom->h, top->w, top->h, hs, ws,
+            NC_PDL_LAUNCH((interp_nearest_kernel<T, 1>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, n, C, bottom->w, bottom->h, top->w, top->h, hs, ws,
                                                                                 bottom->cpitch, bottom->nstep, top->cpitch, top->nstep);
         }
     }
     else
     {
         long long total = (long long)n * top->h * top->w * C;
-        interp_bilinear_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, n, C, bottom->w, bottom->h, top->w, top->h, align_corner,
+        NC_PDL_LAUNCH((interp_bilinear_kernel<T>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, n, C, bottom->w, bottom->h, top->w, top->h, align_corner,
                                                                           bottom->cpitch, bottom->nstep, top->cpitch, top->nstep);
     }
     NC_LAUNCH_CHECK();
@@ -725,7 +736,7 @@ static int run_softmax(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* t
     if (lines == 0 || g.L == 0) return 0;
     int block = g.L >= 256 ? 256 : (g.L >= 128 ? 128 : (g.L >= 64 ? 64 : 32));
     long long grid = lines < (long long)sm_count() * 16 ? lines : (long long)sm_count() * 16;
-    softmax_kernel<T><<<(int)grid, block, 0, stream>>>((const T*)bottom->data, (T*)top->data, g, lines);
+    NC_PDL_LAUNCH((softmax_kernel<T>), (int)grid, block, 0, stream, (const T*)bottom->data, (T*)top->data, g, lines);
     NC_LAUNCH_CHECK();
     return 0;
 }
@@ -736,7 +747,7 @@ static int run_padding(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* t
     int n = top->n < 1 ? 1 : top->n;
     long long total = (long long)n * top->h * top->w * top->c;
     if (total == 0) return 0;
-    padding_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, n, bottom->w, bottom->h, bottom->c, top->w, top->h, top->c, top_pad, left_pad,
+    NC_PDL_LAUNCH((padding_kernel<T>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, n, bottom->w, bottom->h, bottom->c, top->w, top->h, top->c, top_pad, left_pad,
                                                               front_pad, type, value, bottom->cpitch, bottom->nstep, top->cpitch, top->nstep);
     NC_LAUNCH_CHECK();
     return 0;
@@ -751,6 +762,7 @@ template<typename T, int VEC>
 __global__ void __launch_bounds__(256) channel_affine_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
                                                              int P, int C, int in_cpitch, int out_cpitch, long long in_nstep, long long out_nstep, int n, int per_row)
 {
+    NC_PDL_PROLOGUE();
     const int CV = (C + VEC - 1) / VEC;
     const long long total = (long long)n * P * CV;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
@@ -783,13 +795,13 @@ static int run_channel_affine(const ncnn_cuda_tensor* bottom, const ncnn_cuda_te
     if (vec_ok)
     {
         const long long total = (long long)bv.n * bv.P * (cround / VEC);
-        channel_affine_kernel<T, VEC><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, scale, shift, bv.P, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
+        NC_PDL_LAUNCH((channel_affine_kernel<T, VEC>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, scale, shift, bv.P, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
                                                                                tv.nstep, bv.n, per_row);
     }
     else
     {
         const long long total = (long long)bv.n * bv.P * bv.C;
-        channel_affine_kernel<T, 1><<<grid_for(total, 256), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, scale, shift, bv.P, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
+        NC_PDL_LAUNCH((channel_affine_kernel<T, 1>), grid_for(total, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, scale, shift, bv.P, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
                                                                              tv.nstep, bv.n, per_row);
     }
     NC_LAUNCH_CHECK();
@@ -801,6 +813,7 @@ template<typename T>
 __global__ void __launch_bounds__(256) shuffle_channel_kernel(const T* __restrict__ in, T* __restrict__ out, int P, int C, int group, int in_cpitch, int out_cpitch,
                                                               long long in_nstep, long long out_nstep, int n)
 {
+    NC_PDL_PROLOGUE();
     const int cpg = C / group;
     const long long total = (long long)n * P * C;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
@@ -834,9 +847,9 @@ int ncnn_cuda_shuffle_channel(const ncnn_cuda_tensor* bottom, const ncnn_cuda_te
     if (total == 0) return 0;
     cudaStream_t st = as_stream(stream);
     if (bottom->elemtype == NCNN_CUDA_F32)
-        shuffle_channel_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)bottom->data, (float*)top->data, bv.P, bv.C, group, bv.cpitch, tv.cpitch, bv.nstep, tv.nstep, bv.n);
+        NC_PDL_LAUNCH((shuffle_channel_kernel<float>), grid_for(total, 256), 256, 0, st, (const float*)bottom->data, (float*)top->data, bv.P, bv.C, group, bv.cpitch, tv.cpitch, bv.nstep, tv.nstep, bv.n);
     else
-        shuffle_channel_kernel<uint16_t><<<grid_for(total, 256), 256, 0, st>>>((const uint16_t*)bottom->data, (uint16_t*)top->data, bv.P, bv.C, group, bv.cpitch, tv.cpitch, bv.nstep,
+        NC_PDL_LAUNCH((shuffle_channel_kernel<uint16_t>), grid_for(total, 256), 256, 0, st, (const uint16_t*)bottom->data, (uint16_t*)top->data, bv.P, bv.C, group, bv.cpitch, tv.cpitch, bv.nstep,
                                                                               tv.nstep, bv.n);
     NC_LAUNCH_CHECK();
     return 0;

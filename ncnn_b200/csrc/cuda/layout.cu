@@ -53,6 +53,7 @@ template<typename TD, bool PACK>
 __global__ void planar_transpose_kernel(float* __restrict__ planar, long long cstep, long long pl_nstep,
                                         TD* __restrict__ dev, int cpitch, long long dv_nstep, int P, int C)
 {
+    NC_PDL_PROLOGUE();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int p0 = blockIdx.x * 32;
@@ -96,6 +97,7 @@ template<typename TD, bool PACK>
 __global__ void planar_rows_kernel(float* __restrict__ planar, long long pl_nstep, TD* __restrict__ dev, int cpitch,
                                    long long dv_nstep, int P, int C, int n)
 {
+    NC_PDL_PROLOGUE();
     long long total = (long long)n * P * cpitch;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     {
@@ -122,14 +124,14 @@ static int planar_convert(const ncnn_cuda_hostmat* hm, const ncnn_cuda_tensor* t
     if (t->dims <= 2)
     {
         long long total = (long long)n * v.P * v.cpitch;
-        planar_rows_kernel<TD, PACK><<<grid_for(total, 256), 256, 0, stream>>>((float*)hm->data, hm->nstep, (TD*)t->data, v.cpitch, v.nstep, v.P, v.C, n);
+        NC_PDL_LAUNCH((planar_rows_kernel<TD, PACK>), grid_for(total, 256), 256, 0, stream, (float*)hm->data, hm->nstep, (TD*)t->data, v.cpitch, v.nstep, v.P, v.C, n);
         NC_LAUNCH_CHECK();
         return 0;
     }
     dim3 block(32, 8);
     int cspan = PACK ? v.cpitch : v.C;
     dim3 grid(ceil_div(v.P, 32), ceil_div(cspan, 32), n);
-    planar_transpose_kernel<TD, PACK><<<grid, block, 0, stream>>>((float*)hm->data, hm->cstep, hm->nstep, (TD*)t->data, v.cpitch, v.nstep, v.P, v.C);
+    NC_PDL_LAUNCH((planar_transpose_kernel<TD, PACK>), grid, block, 0, stream, (float*)hm->data, hm->cstep, hm->nstep, (TD*)t->data, v.cpitch, v.nstep, v.P, v.C);
     NC_LAUNCH_CHECK();
     return 0;
 }
@@ -143,6 +145,7 @@ struct PermuteMap
 template<typename TS, typename TD, bool PERMUTE>
 __global__ void gather_kernel(const TS* __restrict__ src, DShape ss, TD* __restrict__ dst, DShape ds, int n, PermuteMap pm)
 {
+    NC_PDL_PROLOGUE();
     const int dP = ds.dims == 1 ? 1 : (ds.dims == 2 ? ds.h : ds.w * ds.h * ds.d);
     const int dC = ds.dims == 1 ? ds.w : (ds.dims == 2 ? ds.w : ds.c);
     long long total = (long long)n * dP * dC;
@@ -202,6 +205,7 @@ template<typename T>
 __global__ void __launch_bounds__(256) transpose2d_kernel(const T* __restrict__ src, int rows, int cols, int spitch, long long snstep, T* __restrict__ dst, int dpitch,
                                                           long long dnstep)
 {
+    NC_PDL_PROLOGUE();
     __shared__ T tile[32][33];
     const int b = blockIdx.z;
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -231,9 +235,9 @@ static int launch_transpose2d(const ncnn_cuda_tensor* src, const ncnn_cuda_tenso
     dim3 block(32, 8), grid(ceil_div(cols, 32), ceil_div(rows, 32), n);
     if (grid.y > 65535 || grid.z > 65535) return 1;
     if (src->elemtype == NCNN_CUDA_F32)
-        transpose2d_kernel<float><<<grid, block, 0, stream>>>((const float*)src->data, rows, cols, spitch, src->nstep, (float*)dst->data, dpitch, dst->nstep);
+        NC_PDL_LAUNCH((transpose2d_kernel<float>), grid, block, 0, stream, (const float*)src->data, rows, cols, spitch, src->nstep, (float*)dst->data, dpitch, dst->nstep);
     else
-        transpose2d_kernel<uint16_t><<<grid, block, 0, stream>>>((const uint16_t*)src->data, rows, cols, spitch, src->nstep, (uint16_t*)dst->data, dpitch, dst->nstep);
+        NC_PDL_LAUNCH((transpose2d_kernel<uint16_t>), grid, block, 0, stream, (const uint16_t*)src->data, rows, cols, spitch, src->nstep, (uint16_t*)dst->data, dpitch, dst->nstep);
     NC_LAUNCH_CHECK();
     return 0;
 }
@@ -246,9 +250,9 @@ static int launch_gather(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* ds
     long long total = (long long)n * ds.logical_count();
     if (total == 0) return 0;
     if (permute)
-        gather_kernel<TS, TD, true><<<grid_for(total, 256), 256, 0, stream>>>((const TS*)src->data, ss, (TD*)dst->data, ds, n, pm);
+        NC_PDL_LAUNCH((gather_kernel<TS, TD, true>), grid_for(total, 256), 256, 0, stream, (const TS*)src->data, ss, (TD*)dst->data, ds, n, pm);
     else
-        gather_kernel<TS, TD, false><<<grid_for(total, 256), 256, 0, stream>>>((const TS*)src->data, ss, (TD*)dst->data, ds, n, pm);
+        NC_PDL_LAUNCH((gather_kernel<TS, TD, false>), grid_for(total, 256), 256, 0, stream, (const TS*)src->data, ss, (TD*)dst->data, ds, n, pm);
     NC_LAUNCH_CHECK();
     return 0;
 }

@@ -25,6 +25,7 @@ struct PoolGeom
 template<typename T, int VEC>
 __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* __restrict__ out, PoolGeom g)
 {
+    NC_PDL_PROLOGUE();
     const int CV = (g.C + VEC - 1) / VEC;
     const long long total = (long long)g.n * g.outh * g.outw * CV;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
@@ -154,12 +155,12 @@ static int run_pool(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top,
     if (vec_ok)
     {
         long long total = (long long)g.n * g.outh * g.outw * (cround / VEC);
-        pool_kernel<T, VEC><<<grid_for(total, 256, 16), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, g);
+        NC_PDL_LAUNCH((pool_kernel<T, VEC>), grid_for(total, 256, 16), 256, 0, stream, (const T*)bottom->data, (T*)top->data, g);
     }
     else
     {
         long long total = (long long)g.n * g.outh * g.outw * g.C;
-        pool_kernel<T, 1><<<grid_for(total, 256, 16), 256, 0, stream>>>((const T*)bottom->data, (T*)top->data, g);
+        NC_PDL_LAUNCH((pool_kernel<T, 1>), grid_for(total, 256, 16), 256, 0, stream, (const T*)bottom->data, (T*)top->data, g);
     }
     NC_LAUNCH_CHECK();
     return 0;
