@@ -309,12 +309,12 @@ def main():
         sys.stderr.write("layers total %.3f ms (conv %.3f, dw %.3f, fc %.3f); step %.3f ms\n" % (total_ms, conv_ms, dw_ms, fc_ms, ms / args.steps))
 
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1b", "traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c", "traffic.json")
     if os.path.exists(tpath) and batch == WORKLOADS[args.workload][1]:
         t = json.load(open(tpath)).get(args.workload)
         if t and t.get("storage") == args.storage:
             # DRAM bytes of the dominant kernel family over one step, from the committed ncu --set full capture of this command
-            traffic = {"dram_bytes_per_step": t["dram_read_bytes"] + t["dram_write_bytes"], "launches": t["launches"], "source": "profiles/r1b/traffic.json (ncu)"}
+            traffic = {"dram_bytes_per_step": t["dram_read_bytes"] + t["dram_write_bytes"], "launches": t["launches"], "source": "profiles/r1c/traffic.json (ncu)"}
     # MobileNetV2 is the depthwise (bandwidth) configuration of BASELINE.json: its roofline line is the depthwise family
     if dw_bytes > 0 and (dw_ms > conv_ms or args.workload == "mobilenet_v2"):
         achieved = dw_bytes / (dw_ms * 1e-3) / 1e9

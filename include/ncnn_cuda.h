@@ -260,6 +260,11 @@ NCNN_CUDA_API int ncnn_cuda_unary(int op, float p0, float p1, const ncnn_cuda_te
  * fp32 arrays (shift may be NULL = 0); bottom == top (in place) is allowed. */
 NCNN_CUDA_API int ncnn_cuda_channel_affine(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const float* scale_dev, const float* shift_dev, void* stream);
 
+/* LRN (src/layer/lrn.cpp:26-170): top = bottom * (bias + alpha/size * sum of squares over the window)^-beta, window =
+ * local_size channels (region_type 0) or local_size x local_size pixels (region_type 1) around each element, zeros outside.
+ * bottom and top must be distinct blobs (the window reads neighbours). */
+NCNN_CUDA_API int ncnn_cuda_lrn(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int region_type, int local_size, float alpha, float beta, float bias, void* stream);
+
 /* ShuffleChannel (src/layer/shufflechannel.cpp:22-60): top channel group*j + i = bottom channel (c/group)*i + j.
  * `group` is the effective group count (the caller resolves the layer's `reverse` flag: group = c / group). */
 NCNN_CUDA_API int ncnn_cuda_shuffle_channel(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group, void* stream);

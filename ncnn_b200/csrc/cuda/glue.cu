@@ -753,6 +753,89 @@ static int run_padding(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* t
     return 0;
 }
 
+// ---------------------------------------------------------------- LRN (src/layer/lrn.cpp:26-170)
+namespace {
+
+// y = x * (bias + alpha_div_size * sum_{window} x^2) ^ -beta; window = local_size channels around the element
+// (region 0, zero outside [0, C)) or local_size x local_size pixels around it (region 1, zero padding)
+template<typename T>
+__global__ void __launch_bounds__(256) lrn_kernel(const T* __restrict__ in, T* __restrict__ out, int w, int h, int C, int cpitch_in, int cpitch_out, long long nstep_in,
+                                                  long long nstep_out, int n, int region, int local_size, float alpha_div_size, float beta, float bias)
+{
+    NC_PDL_PROLOGUE();
+    const int P = w * h;
+    const long long total = (long long)n * P * C;
+    const int lo = local_size / 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        const int q = (int)(idx % C);
+        long long r = idx / C;
+        const int pix = (int)(r % P);
+        const int b = (int)(r / P);
+        const T* ib = in + (long long)b * nstep_in;
+        float ss = 0.f;
+        if (region == 0)
+        {
+            const T* px = ib + (long long)pix * cpitch_in;
+            for (int c = q - lo; c <= q + lo; c++)
+                if (c >= 0 && c < C)
+                {
+                    const float v = to_f32(px[c]);
+                    ss += v * v;
+                }
+        }
+        else
+        {
+            const int y = pix / w, x = pix - y * w;
+            // the reference pads lo before and local_size - lo - 1 after (lrn.cpp:94-100)
+            for (int dy = -lo; dy < local_size - lo; dy++)
+                for (int dx = -lo; dx < local_size - lo; dx++)
+                {
+                    const int yy = y + dy, xx = x + dx;
+                    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+                    {
+                        const float v = to_f32(ib[((long long)yy * w + xx) * cpitch_in + q]);
+                        ss += v * v;
+                    }
+                }
+        }
+        const float x0 = to_f32(ib[(long long)pix * cpitch_in + q]);
+        out[(long long)b * nstep_out + (long long)pix * cpitch_out + q] = from_f32<T>(x0 * powf(bias + alpha_div_size * ss, -beta));
+    }
+}
+
+} // namespace
+
+extern "C" int ncnn_cuda_lrn(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int region_type, int local_size, float alpha, float beta, float bias, void* stream)
+{
+    NC_REQUIRE(bottom && top && bottom->dims == 3 && same_shape(bottom, top) && bottom->elemtype == top->elemtype && bottom->data != top->data,
+               "lrn: a distinct pair of 3-D blobs of one type is required");
+    NC_REQUIRE((region_type == 0 || region_type == 1) && local_size > 0, "lrn: bad region_type / local_size");
+    TView bv = make_view(bottom), tv = make_view(top);
+    const long long total = (long long)bv.n * bv.P * bv.C;
+    if (total == 0) return 0;
+    const float ads = region_type == 0 ? alpha / local_size : alpha / (local_size * local_size);
+    cudaStream_t st = as_stream(stream);
+    switch (bottom->elemtype)
+    {
+    case NCNN_CUDA_F32:
+        NC_PDL_LAUNCH((lrn_kernel<float>), grid_for(total, 256), 256, 0, st, (const float*)bottom->data, (float*)top->data, bottom->w, bottom->h, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
+                      tv.nstep, bv.n, region_type, local_size, ads, beta, bias);
+        break;
+    case NCNN_CUDA_BF16:
+        NC_PDL_LAUNCH((lrn_kernel<__nv_bfloat16>), grid_for(total, 256), 256, 0, st, (const __nv_bfloat16*)bottom->data, (__nv_bfloat16*)top->data, bottom->w, bottom->h, bv.C, bv.cpitch,
+                      tv.cpitch, bv.nstep, tv.nstep, bv.n, region_type, local_size, ads, beta, bias);
+        break;
+    case NCNN_CUDA_F16:
+        NC_PDL_LAUNCH((lrn_kernel<__half>), grid_for(total, 256), 256, 0, st, (const __half*)bottom->data, (__half*)top->data, bottom->w, bottom->h, bv.C, bv.cpitch, tv.cpitch, bv.nstep,
+                      tv.nstep, bv.n, region_type, local_size, ads, beta, bias);
+        break;
+    default: return -1;
+    }
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---------------------------------------------------------------- BatchNorm / Scale / ShuffleChannel
 namespace {
 

@@ -236,6 +236,37 @@ public:
     int group, reverse;
 };
 
+// src/layer/lrn.cpp
+class LRN : public Layer
+{
+public:
+    LRN();
+    virtual int load_param(const ParamDict& pd);
+    virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
+    int region_type, local_size;
+    float alpha, beta, bias;
+};
+
+// src/layer/noop.cpp -- passes its blobs through
+class Noop : public Layer
+{
+public:
+    Noop();
+    virtual int forward_inplace(std::vector<CudaMat>& bottom_top_blobs, CudaCompute& cmd, const Option& opt) const;
+    virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
+};
+
+// src/layer/crop.cpp -- single-input forms: offsets (+ sizes / trailing offsets) and numpy-style starts / ends / axes
+class Crop : public Layer
+{
+public:
+    Crop();
+    virtual int load_param(const ParamDict& pd);
+    virtual int forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const;
+    int woffset, hoffset, doffset, coffset, outw, outh, outd, outc, woffset2, hoffset2, doffset2, coffset2;
+    Mat starts, ends, axes;
+};
+
 class Eltwise : public Layer
 {
 public:

@@ -155,4 +155,217 @@ int ShuffleChannel::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaC
     return ncnn_cuda_shuffle_channel(&b, &t, g, cmd.stream());
 }
 
+// ------------------------------------------------------------------ LRN (src/layer/lrn.cpp)
+LRN::LRN()
+{
+    one_blob_only = true;
+    support_inplace = true; // as the reference declares it; the device kernel writes a fresh blob and swaps it in
+    region_type = 0;
+    local_size = 5;
+    alpha = 1.f;
+    beta = 0.75f;
+    bias = 1.f;
+}
+
+int LRN::load_param(const ParamDict& pd) // :14-24
+{
+    region_type = pd.get(0, 0);
+    local_size = pd.get(1, 5);
+    alpha = pd.get(2, 1.f);
+    beta = pd.get(3, 0.75f);
+    bias = pd.get(4, 1.f);
+    return 0;
+}
+
+int LRN::forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const
+{
+    // the window reads neighbours, so the kernel is out of place: a new blob takes the old one's place
+    if (bottom_top_blob.dims != 3) return -1;
+    CudaMat top_blob;
+    top_blob.create_like(bottom_top_blob, cmd.blob_allocator(opt));
+    if (top_blob.empty()) return -100;
+    ncnn_cuda_tensor b = bottom_top_blob.view(), t = top_blob.view();
+    int ret = ncnn_cuda_lrn(&b, &t, region_type, local_size, alpha, beta, bias, cmd.stream());
+    if (ret == 0) bottom_top_blob = top_blob;
+    return ret;
+}
+
+// ------------------------------------------------------------------ Noop (src/layer/noop.cpp)
+Noop::Noop()
+{
+    support_inplace = true;
+}
+
+int Noop::forward_inplace(std::vector<CudaMat>&, CudaCompute&, const Option&) const
+{
+    return 0;
+}
+
+int Noop::forward_inplace(CudaMat&, CudaCompute&, const Option&) const
+{
+    return 0;
+}
+
+// ------------------------------------------------------------------ Crop (src/layer/crop.cpp)
+Crop::Crop()
+{
+    one_blob_only = true;
+    support_inplace = false;
+    woffset = hoffset = doffset = coffset = 0;
+    outw = outh = outd = outc = 0;
+    woffset2 = hoffset2 = doffset2 = coffset2 = 0;
+}
+
+int Crop::load_param(const ParamDict& pd) // :18-60
+{
+    woffset = pd.get(0, 0);
+    hoffset = pd.get(1, 0);
+    doffset = pd.get(13, 0);
+    coffset = pd.get(2, 0);
+    outw = pd.get(3, 0);
+    outh = pd.get(4, 0);
+    outd = pd.get(14, 0);
+    outc = pd.get(5, 0);
+    woffset2 = pd.get(6, 0);
+    hoffset2 = pd.get(7, 0);
+    doffset2 = pd.get(15, 0);
+    coffset2 = pd.get(8, 0);
+    starts = pd.get(9, Mat());
+    ends = pd.get(10, Mat());
+    axes = pd.get(11, Mat());
+    return 0;
+}
+
+static inline void crop_numpy_axis(int extent, int start, int end, int& offset, int& out)
+{
+    if (start == -233) start = 0;
+    if (end == -233) end = extent;
+    offset = start >= 0 ? start : extent + start;
+    int e = end > 0 ? end : extent + end;
+    if (e > extent) e = extent;
+    out = e - offset;
+}
+
+int Crop::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const
+{
+    // resolve_crop_roi, crop.cpp:390-590
+    const int dims = bottom_blob.dims;
+    const int w = bottom_blob.w, h = bottom_blob.h, d = bottom_blob.d, channels = bottom_blob.c;
+    int _wo = 0, _ho = 0, _do = 0, _co = 0, _ow = w, _oh = h, _od = d, _oc = channels;
+    if (!starts.empty() && !ends.empty())
+    {
+        const int* sp = (const int*)starts.data;
+        const int* ep = (const int*)ends.data;
+        const int* ap = (const int*)axes.data;
+        int num_axis = axes.w;
+        int ax[4] = {0, 1, 2, 3};
+        if (num_axis == 0)
+            num_axis = dims;
+        else
+            for (int i = 0; i < num_axis && i < 4; i++) ax[i] = ap[i] < 0 ? dims + ap[i] : ap[i];
+        if (num_axis > 4 || num_axis > starts.w || num_axis > ends.w) return -1;
+        for (int i = 0; i < num_axis; i++)
+        {
+            const int a = ax[i];
+            // logical axis -> (extent, offset, out): dims 1: w; 2: h,w; 3: c,h,w; 4: c,d,h,w
+            const int k = a + (4 - dims); // position in (c, d, h, w)
+            if (a < 0 || a >= dims) return -1;
+            if (dims == 2 && a == 0)
+                crop_numpy_axis(h, sp[i], ep[i], _ho, _oh);
+            else if (k == 3)
+                crop_numpy_axis(w, sp[i], ep[i], _wo, _ow);
+            else if (k == 2)
+                crop_numpy_axis(h, sp[i], ep[i], _ho, _oh);
+            else if (k == 1 && dims == 4)
+                crop_numpy_axis(d, sp[i], ep[i], _do, _od);
+            else
+                crop_numpy_axis(channels, sp[i], ep[i], _co, _oc);
+        }
+    }
+    else
+    {
+        _wo = woffset;
+        _ho = hoffset;
+        _do = doffset;
+        _co = coffset;
+        _ow = w - woffset - woffset2;
+        if (outw != -233) _ow = outw < _ow ? outw : _ow;
+        if (dims >= 2)
+        {
+            _oh = h - hoffset - hoffset2;
+            if (outh != -233) _oh = outh < _oh ? outh : _oh;
+        }
+        if (dims >= 3)
+        {
+            _oc = channels - coffset - coffset2;
+            if (outc != -233) _oc = outc < _oc ? outc : _oc;
+        }
+        if (dims == 4)
+        {
+            _od = d - doffset - doffset2;
+            if (outd != -233) _od = outd < _od ? outd : _od;
+        }
+    }
+    if (_ow <= 0 || _oh <= 0 || _od <= 0 || _oc <= 0 || _wo < 0 || _ho < 0 || _do < 0 || _co < 0) return -1;
+    if (_wo + _ow > w || (dims >= 2 && _ho + _oh > h) || (dims == 4 && _do + _od > d) || (dims >= 3 && _co + _oc > channels)) return -1;
+    if (_ow == w && _oh == h && _od == d && _oc == channels)
+    {
+        top_blob = bottom_blob; // crop.cpp:80-85: nothing to cut
+        return 0;
+    }
+    // one single-axis copy per axis that is actually cut (ncnn_cuda_copy_from_axis); axis numbers in the blob's own rank
+    struct Cut
+    {
+        int axis, offset, extent, full;
+    };
+    Cut cuts[4];
+    int nc = 0;
+    if (dims == 1)
+        cuts[nc++] = Cut{0, _wo, _ow, w};
+    else if (dims == 2)
+    {
+        cuts[nc++] = Cut{0, _ho, _oh, h};
+        cuts[nc++] = Cut{1, _wo, _ow, w};
+    }
+    else if (dims == 3)
+    {
+        cuts[nc++] = Cut{0, _co, _oc, channels};
+        cuts[nc++] = Cut{1, _ho, _oh, h};
+        cuts[nc++] = Cut{2, _wo, _ow, w};
+    }
+    else
+    {
+        cuts[nc++] = Cut{0, _co, _oc, channels};
+        cuts[nc++] = Cut{1, _do, _od, d};
+        cuts[nc++] = Cut{2, _ho, _oh, h};
+        cuts[nc++] = Cut{3, _wo, _ow, w};
+    }
+    CudaMat cur = bottom_blob;
+    for (int i = 0; i < nc; i++)
+    {
+        if (cuts[i].extent == cuts[i].full) continue;
+        int cw = cur.w, ch = cur.h, cd = cur.d, cc = cur.c;
+        const int k = cuts[i].axis + (4 - dims); // position in (c, d, h, w)
+        if (dims == 2 && cuts[i].axis == 0)
+            ch = cuts[i].extent;
+        else if (k == 3)
+            cw = cuts[i].extent;
+        else if (k == 2)
+            ch = cuts[i].extent;
+        else if (k == 1 && dims == 4)
+            cd = cuts[i].extent;
+        else
+            cc = cuts[i].extent;
+        CudaMat next;
+        next.create_dims(dims, cw, ch, cd, cc, cur.elemtype, cur.n, cmd.blob_allocator(opt));
+        if (next.empty()) return -100;
+        ncnn_cuda_tensor b = cur.view(), t = next.view();
+        int ret = ncnn_cuda_copy_from_axis(&b, &t, cuts[i].axis, cuts[i].offset, cmd.stream());
+        if (ret != 0) return ret;
+        cur = next;
+    }
+    top_blob = cur;
+    return 0;
+}
+
 } // namespace ncnn

@@ -38,6 +38,9 @@ DEFINE_LAYER_CREATOR(Padding)
 DEFINE_LAYER_CREATOR(BatchNorm)
 DEFINE_LAYER_CREATOR(Scale)
 DEFINE_LAYER_CREATOR(ShuffleChannel)
+DEFINE_LAYER_CREATOR(LRN)
+DEFINE_LAYER_CREATOR(Noop)
+DEFINE_LAYER_CREATOR(Crop)
 
 static const layer_registry_entry cuda_layer_registry[] = {
     {"Input", Input_layer_creator},
@@ -69,6 +72,9 @@ static const layer_registry_entry cuda_layer_registry[] = {
     {"BatchNorm", BatchNorm_layer_creator},
     {"Scale", Scale_layer_creator},
     {"ShuffleChannel", ShuffleChannel_layer_creator},
+    {"LRN", LRN_layer_creator},
+    {"Noop", Noop_layer_creator},
+    {"Crop", Crop_layer_creator},
 };
 
 static const int layer_type_count = (int)(sizeof(layer_type_names) / sizeof(layer_type_names[0]));

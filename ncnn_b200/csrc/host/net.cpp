@@ -640,10 +640,10 @@ int Net::find_layer_index_by_name(const char* name) const
 //   Convolution (activation_type 0) -> Eltwise(SUM, 2 inputs, no coeffs) [-> ReLU]  => residual add (+ReLU) in the epilogue
 //   Eltwise -> ReLU                                                               => fused_relu
 namespace {
-class Noop : public Layer
+class RetiredLayer : public Layer
 {
 public:
-    Noop()
+    RetiredLayer()
     {
         one_blob_only = false;
         support_inplace = false;
@@ -663,7 +663,7 @@ int NetPrivate::fuse_graph(const Option&)
     auto retire = [&](int li) {
         // turn layer li into a disconnected no-op
         Layer* old = layers[li];
-        Noop* n = new Noop;
+        RetiredLayer* n = new RetiredLayer;
         n->type = "Noop";
         n->name = old->name;
         int ci = layer_custom_index[li];

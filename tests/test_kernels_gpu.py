@@ -493,3 +493,22 @@ def test_batchnorm_scale_shufflechannel(ref, elemtype):
         cabi.check(L.ncnn_cuda_shuffle_channel(C.byref(sd), C.byref(dd), g, None), "shuffle_channel")
         sync()
         assert np.array_equal(dst.numpy(), want), ("shufflechannel", ch, group, reverse)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_lrn(ref, elemtype):
+    """LRN across channels (AlexNet / GoogLeNet) and within channel against the reference's naive layer (src/layer/lrn.cpp)"""
+    L = cabi.lib()
+    L.ncnn_cuda_lrn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(61)
+    tol = 1e-5 if elemtype == F32 else 1e-4
+    for (c, h, w, region, size, alpha, beta, bias) in [(96, 13, 13, 0, 5, 1e-4, 0.75, 1.0), (7, 5, 6, 0, 3, 0.5, 0.6, 2.0), (16, 9, 11, 1, 3, 0.3, 0.75, 1.0),
+                                                      (5, 8, 7, 1, 5, 1e-2, 0.5, 1.5), (3, 4, 4, 0, 9, 1.0, 0.75, 1.0)]:
+        x = quant(rand(rng, (2, c, h, w), -2.0, 2.0), elemtype)
+        want = ref.layer_forward("LRN", {0: region, 1: size, 2: float(alpha), 3: float(beta), 4: float(bias)}, [], [x], batched=True)[0]
+        src = cabi.Blob.from_numpy(x, elemtype)
+        dst = cabi.Blob((c, h, w), 2, elemtype, fill=float("nan"))
+        sd, dd = src.desc(), dst.desc()
+        cabi.check(L.ncnn_cuda_lrn(C.byref(sd), C.byref(dd), region, size, alpha, beta, bias, None), "lrn")
+        sync()
+        assert nerr(dst.numpy(), want, elemtype) <= tol, ("lrn", c, h, w, region, size)

@@ -26,4 +26,5 @@ prof() { # name regex skip count workload
 }
 prof tc_gemm tc_gemm 159 53 resnet50
 prof dwconv dwconv 51 17 mobilenet_v2
+bash tools/ncu_hot.sh rn_stage2 tc_gemm 212 6 resnet50
 du -sh gpurun_out; ls -la gpurun_out
