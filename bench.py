@@ -150,9 +150,10 @@ def main():
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer table to stderr")
-    ap.add_argument("--e2e-threads", type=int, default=2,
+    ap.add_argument("--e2e-threads", type=int, default=3,
                     help="host threads feeding the end-to-end path, one Extractor (own stream, own device pool) per call: with 2 the H2D "
-                         "copy of one step overlaps the kernels of the previous one (the reference's one-extractor-per-thread rule)")
+                         "copy of one step overlaps the kernels of the previous ones (the reference's one-extractor-per-thread rule); "
+                         "measured on ResNet-50 bs256: 1 -> 36 k, 2 -> 51 k, 3 -> 60 k, 4 -> 61 k images/s")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
