@@ -274,6 +274,50 @@ def main():
     e2e_value = replicas.throughput(batch, args.steps, world, e2e_s * 1000.0)
     e2e_serial_value = replicas.throughput(batch, args.steps, world, e2e_serial_s * 1000.0)
     h2d, d2h = int(sess.last_h2d), int(sess.last_d2h)
+
+    # ---- the same with device pre-processing: the step's input is the batch of 8-bit BGR images a deployment
+    # actually holds; from_pixels + substract_mean_normalize run on the device (ncnn_extractor_input_pixels), so 1/4 of the bytes
+    # cross PCIe.  Reported beside, not instead of, the fp32-Mat figure.
+    px = (np.random.default_rng(2 + rank).integers(0, 256, (batch, size, size, 3), dtype=np.uint8))
+    mean_vals = np.asarray([104.0, 117.0, 123.0], np.float32)
+    norm_vals = np.asarray([0.017, 0.0175, 0.0171], np.float32)
+
+    def e2e_pixels_run(n_threads, steps):
+        bufs = [sess.pinned_pixels(px) for _ in range(n_threads)]
+        per = [steps // n_threads + (1 if i < steps % n_threads else 0) for i in range(n_threads)]
+        errs = []
+
+        def worker(i):
+            try:
+                lib.ncnn_cuda_set_device(local_rank)
+                for _ in range(per[i]):
+                    lib.ncnn_mat_destroy(sess.extract_host_pixels(bufs[i][1], bufs[i][2], 2, mean_vals, norm_vals))
+            except Exception as e:
+                errs.append(e)
+
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(n_threads)]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        for b in bufs:
+            lib.ncnn_mat_destroy(b[0])
+        if errs:
+            raise errs[0]
+        return dt
+
+    e2e_pixels_value = None
+    h2d_pixels = None
+    try:
+        e2e_pixels_run(nthreads, 2 * nthreads)
+        barrier()
+        pix_s = max_over_ranks(e2e_pixels_run(nthreads, args.steps))
+        e2e_pixels_value = replicas.throughput(batch, args.steps, world, pix_s * 1000.0)
+        h2d_pixels = int(sess.last_h2d_pixels)
+    except Exception as e:  # the fp32-Mat e2e above is the contract figure; this one is extra
+        sys.stderr.write("e2e with pixel input failed: %s\n" % e)
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
     if rank == 0:
         sampler.stop()
@@ -338,6 +382,7 @@ def main():
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.storage], "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads": nthreads,
                     "serial_value": e2e_serial_value,
+                    "pixels_value": e2e_pixels_value, "pixels_h2d_bytes_per_step": h2d_pixels,
                     "mode": "each step = extractor.input(pinned host Mat) + extract(host Mat); steps dealt to %d host thread(s), one Extractor/stream per step" % nthreads},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "fused_layers": sess.fused_layers}
 

@@ -267,6 +267,13 @@ NCNN_C_API int ncnn_cuda_mat_get_elemtype(const ncnn_cuda_mat_t mat);
 NCNN_C_API void* ncnn_cuda_mat_get_data(const ncnn_cuda_mat_t mat);
 NCNN_C_API int ncnn_extractor_input_cuda(ncnn_extractor_t ex, const char* name, const ncnn_cuda_mat_t mat);
 NCNN_C_API int ncnn_extractor_extract_cuda(ncnn_extractor_t ex, const char* name, ncnn_cuda_mat_t* mat, ncnn_cuda_compute_t cmd);
+/* Device pre-processing: feed `name` with n interleaved 8-bit images; the equivalent of ncnn_mat_from_pixels(pixels, type, w, h,
+ * stride) (src/c_api.h:104-109, types as NCNN_MAT_PIXEL_*) + ncnn_mat_substract_mean_normalize(mean_vals, norm_vals)
+ * (src/c_api.h:117) per image runs on the device at extract time; only the raw bytes cross PCIe.  stride 0 = w * channels,
+ * nstride (bytes between images) 0 = h * stride; mean_vals / norm_vals may be NULL.  `pixels` must stay valid until the
+ * extract call returns. */
+NCNN_C_API int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
+                                           const float* mean_vals, const float* norm_vals);
 /* PCIe bytes of the last ncnn_extractor_extract call */
 NCNN_C_API size_t ncnn_extractor_get_last_h2d_bytes(const ncnn_extractor_t ex);
 NCNN_C_API size_t ncnn_extractor_get_last_d2h_bytes(const ncnn_extractor_t ex);

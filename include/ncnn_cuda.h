@@ -115,6 +115,14 @@ NCNN_CUDA_API int ncnn_cuda_unpack_to_planar(const ncnn_cuda_tensor* src, const 
 /* general re-layout: dst's logical element order (ncnn dense order n, c, d, h, w) is taken from
  * src's logical order: covers Reshape / Flatten (src/layer/reshape.cpp, flatten.cpp), dtype casts
  * and clone (VkCompute::record_clone). Total logical element counts per sample must match. */
+/* Device pre-processing: Mat::from_pixels (src/mat_pixel.cpp) + Mat::substract_mean_normalize (src/mat.cpp)
+ * in one kernel.  `pixels_dev`: n images of h rows x `stride` bytes of interleaved 8-bit pixels with `channels` (1, 3, 4)
+ * bytes each, `nstride` bytes apart, ALREADY on the device; swap_rb reverses the first three channels (PIXEL_RGB2BGR /
+ * PIXEL_BGR2RGB).  top(w, h, channels)[c] = (pixel[c] - mean[c]) * norm[c]; mean_vals / norm_vals are HOST arrays of
+ * `channels` floats or NULL (0 / 1). */
+NCNN_CUDA_API int ncnn_cuda_pixels_to_blob(const unsigned char* pixels_dev, int channels, int w, int h, int stride, long long nstride, int swap_rb, const float* mean_vals,
+                                           const float* norm_vals, const ncnn_cuda_tensor* top, void* stream);
+
 NCNN_CUDA_API int ncnn_cuda_reshape(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, void* stream);
 /* Permute (src/layer/permute.cpp:16-164): order_type as in the reference */
 NCNN_CUDA_API int ncnn_cuda_permute(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, int order_type, void* stream);

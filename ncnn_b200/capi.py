@@ -282,6 +282,34 @@ class Net(object):
                 L.ncnn_mat_destroy(m)
         return res
 
+    def run_pixels(self, name, pixels, pixel_type, mean_vals=None, norm_vals=None, outputs=None):
+        """pixels: (n, h, w, channels) uint8, interleaved; pre-processing (from_pixels + substract_mean_normalize) runs on the
+        device (ncnn_extractor_input_pixels, product library only); returns {blob name: ndarray (n, ...)}"""
+        import numpy as np
+        L = self.api.lib
+        L.ncnn_extractor_input_pixels.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        pixels = np.ascontiguousarray(pixels, np.uint8)
+        n, h, w, ch = pixels.shape
+        mean = np.asarray(mean_vals, np.float32) if mean_vals is not None else None
+        norm = np.asarray(norm_vals, np.float32) if norm_vals is not None else None
+        ex = L.ncnn_extractor_create(self.net)
+        res = {}
+        try:
+            r = L.ncnn_extractor_input_pixels(ex, name.encode(), pixels.ctypes.data_as(C.c_void_p), pixel_type, w, h, w * ch, n, h * w * ch,
+                                              mean.ctypes.data_as(C.c_void_p) if mean is not None else None, norm.ctypes.data_as(C.c_void_p) if norm is not None else None)
+            if r != 0:
+                raise RuntimeError("input_pixels %s returned %d" % (name, r))
+            for oname in (outputs or self.output_names):
+                out = C.c_void_p()
+                r = L.ncnn_extractor_extract(ex, oname.encode(), C.byref(out))
+                if r != 0:
+                    raise RuntimeError("extract %s returned %d" % (oname, r))
+                res[oname] = self.api.mat_to_numpy(out, force_batch=True)
+                L.ncnn_mat_destroy(out)
+        finally:
+            L.ncnn_extractor_destroy(ex)
+        return res
+
     def close(self):
         if self.net:
             self.api.lib.ncnn_net_destroy(self.net)

@@ -277,6 +277,60 @@ static int dispatch_gather(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* 
 
 using namespace ncnn_cuda;
 
+// ---------------------------------------------------------------- interleaved 8-bit pixels -> device blob
+// Mat::from_pixels (src/mat_pixel.cpp: from_rgb / from_rgb2bgr / from_gray / from_rgba) followed by
+// Mat::substract_mean_normalize (src/mat.cpp): value = (pixel - mean[c]) * norm[c].  The interleaved HWC byte order IS the
+// channel-innermost device order, so one thread converts one pixel and writes its channel vector; no transpose, and the
+// fp32 planar image never exists (4x fewer bytes over PCIe than uploading the converted Mat).
+struct PixelAffine
+{
+    float mean[4];
+    float norm[4];
+};
+
+template<typename T, int CH>
+__global__ void __launch_bounds__(256) pixels_to_blob_kernel(const unsigned char* __restrict__ pixels, int w, int h, int stride, long long nstride, int swap_rb, PixelAffine pa,
+                                                             T* __restrict__ out, int cpitch, long long out_nstep, int n)
+{
+    NC_PDL_PROLOGUE();
+    const long long total = (long long)n * h * w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        const int x = (int)(idx % w);
+        long long r = idx / w;
+        const int y = (int)(r % h);
+        const int b = (int)(r / h);
+        const unsigned char* px = pixels + (long long)b * nstride + (long long)y * stride + (long long)x * CH;
+        T* o = out + (long long)b * out_nstep + ((long long)y * w + x) * cpitch;
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+        {
+            // swap_rb reverses the first three channels (RGB <-> BGR; a fourth, alpha, stays in place)
+            const int sc = (swap_rb && c < 3) ? 2 - c : c;
+            o[c] = from_f32<T>(((float)px[sc] - pa.mean[c]) * pa.norm[c]);
+        }
+        for (int c = CH; c < cpitch; c++) o[c] = from_f32<T>(0.f); // padding lanes: zeros (the stem kernels read whole pixels)
+    }
+}
+
+template<typename T>
+static int run_pixels(const unsigned char* pixels, int ch, int w, int h, int stride, long long nstride, int swap_rb, const PixelAffine& pa, const ncnn_cuda_tensor* top,
+                      cudaStream_t stream)
+{
+    TView tv = make_view(top);
+    const long long total = (long long)tv.n * h * w;
+    if (total == 0) return 0;
+    const int grid = grid_for(total, 256);
+    if (ch == 1)
+        NC_PDL_LAUNCH((pixels_to_blob_kernel<T, 1>), grid, 256, 0, stream, pixels, w, h, stride, nstride, swap_rb, pa, (T*)top->data, tv.cpitch, tv.nstep, tv.n);
+    else if (ch == 3)
+        NC_PDL_LAUNCH((pixels_to_blob_kernel<T, 3>), grid, 256, 0, stream, pixels, w, h, stride, nstride, swap_rb, pa, (T*)top->data, tv.cpitch, tv.nstep, tv.n);
+    else
+        NC_PDL_LAUNCH((pixels_to_blob_kernel<T, 4>), grid, 256, 0, stream, pixels, w, h, stride, nstride, swap_rb, pa, (T*)top->data, tv.cpitch, tv.nstep, tv.n);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" {
 
 int ncnn_cuda_pack_from_planar(const ncnn_cuda_hostmat* src, const ncnn_cuda_tensor* dst, void* stream)
@@ -297,6 +351,27 @@ int ncnn_cuda_unpack_to_planar(const ncnn_cuda_tensor* src, const ncnn_cuda_host
     case NCNN_CUDA_F32: return planar_convert<float, false>(dst, src, as_stream(stream));
     case NCNN_CUDA_BF16: return planar_convert<__nv_bfloat16, false>(dst, src, as_stream(stream));
     case NCNN_CUDA_F16: return planar_convert<__half, false>(dst, src, as_stream(stream));
+    }
+    return -1;
+}
+
+int ncnn_cuda_pixels_to_blob(const unsigned char* pixels_dev, int channels, int w, int h, int stride, long long nstride, int swap_rb, const float* mean_vals, const float* norm_vals,
+                             const ncnn_cuda_tensor* top, void* stream)
+{
+    NC_REQUIRE(pixels_dev && top && top->dims == 3 && top->w == w && top->h == h && top->c == channels, "pixels_to_blob: the top blob must be (w, h, channels)");
+    NC_REQUIRE(channels == 1 || channels == 3 || channels == 4, "pixels_to_blob: 1, 3 or 4 interleaved channels");
+    NC_REQUIRE(stride >= w * channels, "pixels_to_blob: stride shorter than a row");
+    PixelAffine pa;
+    for (int c = 0; c < 4; c++)
+    {
+        pa.mean[c] = (mean_vals && c < channels) ? mean_vals[c] : 0.f;
+        pa.norm[c] = (norm_vals && c < channels) ? norm_vals[c] : 1.f;
+    }
+    switch (top->elemtype)
+    {
+    case NCNN_CUDA_F32: return run_pixels<float>(pixels_dev, channels, w, h, stride, nstride, swap_rb, pa, top, as_stream(stream));
+    case NCNN_CUDA_BF16: return run_pixels<__nv_bfloat16>(pixels_dev, channels, w, h, stride, nstride, swap_rb, pa, top, as_stream(stream));
+    case NCNN_CUDA_F16: return run_pixels<__half>(pixels_dev, channels, w, h, stride, nstride, swap_rb, pa, top, as_stream(stream));
     }
     return -1;
 }

@@ -1006,6 +1006,11 @@ int ncnn_extractor_input(ncnn_extractor_t ex, const char* name, const ncnn_mat_t
 {
     return ((Extractor*)ex)->input(name, *(const Mat*)mat);
 }
+int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
+                                const float* mean_vals, const float* norm_vals)
+{
+    return ((Extractor*)ex)->input_pixels(name, pixels, type, w, h, stride, n, nstride, mean_vals, norm_vals);
+}
 int ncnn_extractor_extract(ncnn_extractor_t ex, const char* name, ncnn_mat_t* mat)
 {
     Mat m;

@@ -176,6 +176,61 @@ int CudaCompute::record_upload(const Mat& src, CudaMat& dst, const Option& opt)
     return ret;
 }
 
+// pixel type codes of the reference (src/mat.h:213-262): PIXEL_RGB 1, BGR 2, GRAY 3, RGBA 4, BGRA 5; conversion = from | (to << 16)
+int CudaCompute::record_upload_pixels(const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals, const float* norm_vals,
+                                      CudaMat& dst, const Option& opt)
+{
+    if (!pixels || w <= 0 || h <= 0 || n <= 0) return -100;
+    const int from = type & 0xffff, to = (type >> 16) & 0xffff;
+    int channels;
+    switch (from)
+    {
+    case 1:
+    case 2: channels = 3; break;
+    case 3: channels = 1; break;
+    case 4:
+    case 5: channels = 4; break;
+    default: NCNN_LOGE("record_upload_pixels: unknown pixel type %d", type); return -1;
+    }
+    int swap_rb = 0;
+    if (to != 0 && to != from)
+    {
+        const bool rgb_bgr = (from == 1 && to == 2) || (from == 2 && to == 1) || (from == 4 && to == 5) || (from == 5 && to == 4);
+        if (!rgb_bgr)
+        {
+            NCNN_LOGE("record_upload_pixels: pixel conversion %d -> %d is not on the device path", from, to);
+            return -1;
+        }
+        swap_rb = 1;
+    }
+    if (stride <= 0) stride = w * channels;
+    if (nstride == 0) nstride = (size_t)h * stride;
+    void* st = stream();
+    const size_t bytes = (size_t)(n - 1) * nstride + (size_t)h * stride;
+    CudaMat raw;
+    raw.create((int)((bytes + 3) / 4), NCNN_CUDA_F32, 1, workspace_allocator(opt));
+    if (raw.empty()) return -100;
+    const void* hsrc = pixels;
+    if (!ncnn_cuda_host_is_pinned(pixels))
+    {
+        Allocator* sa = ctx_->staging_allocator;
+        void* staging = sa->fastMalloc(bytes);
+        if (!staging) return -100;
+        memcpy(staging, pixels, bytes);
+        staging_in_flight_.push_back(staging);
+        hsrc = staging;
+    }
+    int ret = ncnn_cuda_memcpy_h2d_async(raw.data, hsrc, bytes, st);
+    if (ret != 0) return ret;
+    h2d_bytes += bytes;
+    dst.create_dims(3, w, h, 1, channels, opt.cuda_elemtype(), n, blob_allocator(opt));
+    if (dst.empty()) return -100;
+    ncnn_cuda_tensor t = dst.view();
+    ret = ncnn_cuda_pixels_to_blob((const unsigned char*)raw.data, channels, w, h, stride, (long long)nstride, swap_rb, mean_vals, norm_vals, &t, st);
+    keep_alive_.push_back(raw);
+    return ret;
+}
+
 int CudaCompute::record_download(const CudaMat& src, Mat& dst, const Option& opt)
 {
     if (src.empty()) return -100;

@@ -974,6 +974,17 @@ public:
     std::vector<CudaMat> blob_mats_gpu;
     Option opt;
     size_t h2d, d2h;
+    // inputs given as raw 8-bit pixels, converted on the device when the walk starts
+    struct PixelInput
+    {
+        int blob_index;
+        const unsigned char* pixels;
+        int type, w, h, stride, n;
+        size_t nstride;
+        bool has_mean, has_norm;
+        float mean_vals[4], norm_vals[4];
+    };
+    std::vector<PixelInput> pixel_inputs;
 };
 
 Extractor::Extractor(const Net* _net, size_t blob_count)
@@ -1067,6 +1078,46 @@ int Extractor::input(int blob_index, const CudaMat& in)
     return 0;
 }
 
+int Extractor::input_pixels(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals,
+                            const float* norm_vals)
+{
+    int blob_index = d->net->find_blob_index_by_name(blob_name);
+    if (blob_index == -1 || !pixels) return -1;
+    ExtractorPrivate::PixelInput pi;
+    pi.blob_index = blob_index;
+    pi.pixels = pixels;
+    pi.type = type;
+    pi.w = w;
+    pi.h = h;
+    pi.stride = stride;
+    pi.n = n < 1 ? 1 : n;
+    pi.nstride = nstride;
+    pi.has_mean = mean_vals != 0;
+    pi.has_norm = norm_vals != 0;
+    for (int i = 0; i < 4; i++)
+    {
+        pi.mean_vals[i] = 0.f;
+        pi.norm_vals[i] = 1.f;
+    }
+    const int from = type & 0xffff;
+    const int channels = from == 3 ? 1 : (from == 4 || from == 5 ? 4 : 3);
+    for (int i = 0; i < channels; i++)
+    {
+        if (mean_vals) pi.mean_vals[i] = mean_vals[i];
+        if (norm_vals) pi.norm_vals[i] = norm_vals[i];
+    }
+    d->blob_mats[blob_index].release();
+    d->blob_mats_gpu[blob_index].release();
+    for (size_t i = 0; i < d->pixel_inputs.size(); i++)
+        if (d->pixel_inputs[i].blob_index == blob_index)
+        {
+            d->pixel_inputs[i] = pi;
+            return 0;
+        }
+    d->pixel_inputs.push_back(pi);
+    return 0;
+}
+
 int Extractor::extract(const char* blob_name, Mat& feat, int type)
 {
     int blob_index = d->net->find_blob_index_by_name(blob_name);
@@ -1127,6 +1178,15 @@ int Extractor::extract(int blob_index, CudaMat& feat, CudaCompute& cmd)
 {
     if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
     int ret = 0;
+    // pixel inputs first: upload the raw bytes, convert + normalise on the device
+    for (size_t i = 0; i < d->pixel_inputs.size(); i++)
+    {
+        const ExtractorPrivate::PixelInput& pi = d->pixel_inputs[i];
+        ret = cmd.record_upload_pixels(pi.pixels, pi.type, pi.w, pi.h, pi.stride, pi.n, pi.nstride, pi.has_mean ? pi.mean_vals : 0, pi.has_norm ? pi.norm_vals : 0,
+                                       d->blob_mats_gpu[pi.blob_index], d->opt);
+        if (ret != 0) return ret;
+    }
+    d->pixel_inputs.clear();
     if (d->blob_mats_gpu[blob_index].empty())
     {
         if (!d->blob_mats[blob_index].empty())

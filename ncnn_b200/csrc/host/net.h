@@ -106,6 +106,12 @@ public:
     int extract(const char* blob_name, CudaMat& feat, CudaCompute& cmd);
     int extract(int blob_index, CudaMat& feat, CudaCompute& cmd);
 
+    // device pre-processing: the blob is fed as n interleaved 8-bit images; Mat::from_pixels(type) and
+    // substract_mean_normalize(mean_vals, norm_vals) run on the device at extract time.  The pixel memory must stay valid
+    // until extract() returns (it is read by the upload, like a Mat view).
+    int input_pixels(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals,
+                     const float* norm_vals);
+
     // bytes moved over PCIe by the last extract(Mat&) call
     size_t last_h2d_bytes() const;
     size_t last_d2h_bytes() const;

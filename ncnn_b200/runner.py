@@ -125,6 +125,41 @@ class Session(object):
             lib.ncnn_extractor_destroy(ex)
         return out
 
+    def pinned_pixels(self, pixels):
+        """pixels: (n, h, w, ch) uint8 -> (pinned Mat that owns the bytes, ctypes pointer, shape)"""
+        lib = self.L.lib
+        pixels = np.ascontiguousarray(pixels, np.uint8)
+        nbytes = pixels.size
+        lib.ncnn_mat_create_1d.restype = C.c_void_p
+        lib.ncnn_mat_create_1d.argtypes = [C.c_int, C.c_void_p]
+        lib.ncnn_mat_get_data.restype = C.c_void_p
+        lib.ncnn_mat_get_data.argtypes = [C.c_void_p]
+        m = lib.ncnn_mat_create_1d((nbytes + 3) // 4, self.staging)
+        ptr = lib.ncnn_mat_get_data(m)
+        C.memmove(ptr, pixels.ctypes.data, nbytes)
+        return m, ptr, pixels.shape
+
+    def extract_host_pixels(self, ptr, shape, pixel_type, mean_vals, norm_vals):
+        """one call with device pre-processing: Extractor.input_pixels(pinned 8-bit images) + extract(host Mat)"""
+        lib = self.L.lib
+        lib.ncnn_extractor_input_pixels.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        n, h, w, ch = shape
+        ex = lib.ncnn_extractor_create(self.net)
+        out = C.c_void_p()
+        try:
+            r = lib.ncnn_extractor_input_pixels(ex, self.input_name, C.c_void_p(ptr), pixel_type, w, h, w * ch, n, h * w * ch,
+                                                mean_vals.ctypes.data_as(C.c_void_p) if mean_vals is not None else None,
+                                                norm_vals.ctypes.data_as(C.c_void_p) if norm_vals is not None else None)
+            if r != 0:
+                raise RuntimeError("input_pixels returned %d" % r)
+            r = lib.ncnn_extractor_extract(ex, self.output_name, C.byref(out))
+            if r != 0:
+                raise RuntimeError("extract returned %d: %s" % (r, lib.ncnn_cuda_last_error().decode()))
+            self.last_h2d_pixels = lib.ncnn_extractor_get_last_h2d_bytes(ex)
+        finally:
+            lib.ncnn_extractor_destroy(ex)
+        return out
+
     def run_host(self, x):
         m = self.pinned_input(x)
         out = self.extract_host(m)

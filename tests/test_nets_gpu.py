@@ -234,3 +234,61 @@ def test_reference_benchmark_graphs(ref, name, mode):
         e = nerr(got[o], want[o])
         tol = TOL[mode] if mode == "fp32" else EXTRA_TOL16.get(name, TOL[mode])
         assert e <= tol, (name, o, e)
+
+
+PIXEL_RGB, PIXEL_BGR, PIXEL_GRAY, PIXEL_RGBA = 1, 2, 3, 4
+PIXEL_RGB2BGR = PIXEL_RGB | (PIXEL_BGR << 16)
+
+
+def reference_preprocess(ref, pixels, pixel_type, mean_vals, norm_vals):
+    """the reference's own pre-processing, per image, through its C API: ncnn_mat_from_pixels (src/c_api.h:104) +
+    ncnn_mat_substract_mean_normalize (src/c_api.h:117) -> (n, c, h, w) float32"""
+    import ctypes as C
+    L = ref.lib
+    L.ncnn_mat_from_pixels.restype = C.c_void_p
+    L.ncnn_mat_from_pixels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.ncnn_mat_substract_mean_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    out = []
+    for img in pixels:
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        m = L.ncnn_mat_from_pixels(img.ctypes.data_as(C.c_void_p), pixel_type, w, h, w * ch, None)
+        mean = np.asarray(mean_vals, np.float32) if mean_vals is not None else None
+        norm = np.asarray(norm_vals, np.float32) if norm_vals is not None else None
+        L.ncnn_mat_substract_mean_normalize(C.c_void_p(m), mean.ctypes.data_as(C.c_void_p) if mean is not None else None,
+                                            norm.ctypes.data_as(C.c_void_p) if norm is not None else None)
+        out.append(ref.mat_to_numpy(C.c_void_p(m)))
+        L.ncnn_mat_destroy(C.c_void_p(m))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_device_preprocessing_pixels(ref, mode):
+    """Extractor.input_pixels -- 8-bit interleaved images in, from_pixels + substract_mean_normalize on the
+    device -- against the reference's own from_pixels / substract_mean_normalize followed by its CPU network path.  Checked
+    twice: on the converted input blob itself and on the logits of a ResNet-18."""
+    from ncnn_b200 import capi
+    L = product()
+    rng = np.random.default_rng(17)
+    size, n = 224, 3
+    text = open(os.path.join(EXTRA, "resnet18.param")).read()
+    layers = modelzoo.parse_param(text)
+    logits = layers[-1][2][0]
+    weights = modelzoo.random_model_bytes(text, seed=5)
+    opt = L.make_option(1, **MODES[mode])
+    net = capi.Net(L, text, weights, opt)
+    try:
+        for (ptype, ch, mean, norm) in [(PIXEL_BGR, 3, [104.0, 117.0, 123.0], [0.017, 0.0175, 0.0171]), (PIXEL_RGB2BGR, 3, [123.7, 116.3, 103.5], None),
+                                        (PIXEL_RGB, 3, None, [1 / 255.0] * 3)]:
+            pixels = rng.integers(0, 256, (n, size, size, ch), dtype=np.uint8)
+            x = reference_preprocess(ref, pixels, ptype, mean, norm)
+            got = net.run_pixels("data", pixels, ptype, mean, norm, outputs=["data", logits])
+            # the converted blob: exact up to the storage rounding of the blob type
+            e_in = nerr(got["data"], x)
+            assert e_in <= (1e-6 if mode == "fp32" else 2.0 ** -8), (ptype, e_in)
+            want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=[logits])[logits]
+            e = nerr(got[logits], want)
+            assert e <= TOL[mode], (ptype, e)
+    finally:
+        net.close()
+        L.lib.ncnn_option_destroy(opt)
