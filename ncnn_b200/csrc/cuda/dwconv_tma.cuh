@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
     for (int i = tid; i < 10 * C::CB; i += kThreads)
     {
         const int t = i / C::CB, c = cb * C::CB + (i - t * C::CB);
-        smem_w[i] = t < 9 ? p.w[(long long)t * p.cpad + c] : (p.bias ? p.bias[c] : 0.f);
+        // (the last channel block may be partial: its missing channels read as zeros from the TMA and are never stored)
+        smem_w[i] = c < p.C ? (t < 9 ? p.w[(long long)t * p.cpad + c] : (p.bias ? p.bias[c] : 0.f)) : 0.f;
     }
     __syncthreads();
     tc::pdl_wait(); // the filter slice above is a constant; the previous layer's blob is touched only from here on
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
         }
         const int ox = txi * TW + tx;
         const int oy0 = tyi * C::TH + ty * R;
-        if (ox < p.outw)
+        if (ox < p.outw && c0 < p.C)
         {
             T* op = out + ((long long)b * p.out_nstep + ((long long)oy0 * p.outw + ox) * p.out_cpitch + c0);
 #pragma unroll
@@ -342,7 +343,7 @@ static int launch_dw_tma(const CUtensorMap& tm, T* out, Params& p, cudaStream_t 
     p.tiles_x = (p.outw + TW - 1) / TW;
     p.tiles_y = (p.outh + C::TH - 1) / C::TH;
     const long long n_spatial = (long long)p.n * p.tiles_x * p.tiles_y;
-    const int cblocks = p.C / C::CB;
+    const int cblocks = (p.C + C::CB - 1) / C::CB;
     if (n_spatial > 0x3fffffffLL) return 1; // caller falls back
     p.n_spatial = (int)n_spatial;
     p.num_tiles = 0;
@@ -435,6 +436,15 @@ static int forward(const Call& c, cudaStream_t stream)
 
     if (c.stride == 1)
     {
+        // maps of 7k rows up to 32 columns wide (7x7, 14x14, 28x28): one column x seven rows per thread -- each staged pixel is
+        // converted once for up to three outputs and the per-tile fixed cost is spread over 7 outputs per thread; wide channel
+        // blocks keep 256 threads busy on narrow maps (the last block may be partial)
+        if (c.outh % 7 == 0 && c.C >= 8 * VEC)
+        {
+            if (c.outw <= 8 && c.C >= 24 * VEC) NC_DW(1, 32, 8, 1, 7);
+            if (c.outw <= 16 && c.outw > 8 && c.C >= 12 * VEC) NC_DW(1, 16, 16, 1, 7);
+            if (c.outw <= 32 && c.outw > 16) NC_DW(1, 8, 32, 1, 7);
+        }
         if (small && cv == 8) NC_DW(1, 8, 8, 4, 2);
         if (cv == 8) NC_DW(1, 8, 16, 2, 4);
         if (cv == 4) NC_DW(1, 4, 16, 4, 4);

@@ -281,6 +281,9 @@ def test_convolutiondepthwise_mobilenet_shapes(ref, elemtype):
     for (w, c, s, act) in [(56, 32, 1, 1), (56, 96, 2, 3), (28, 144, 1, 3), (29, 144, 2, 0), (14, 384, 1, 3), (14, 576, 2, 1), (7, 960, 1, 3), (15, 192, 2, 3),
                            (33, 48, 1, 2), (9, 64, 2, 4)]:
         run_dw(ref, rng, elemtype, 2, w, w + (w % 3), c, c, c, 3, 1, s, 1, True, act)
+    # maps of 7k rows (one column x seven rows per thread, wide and possibly partial channel blocks)
+    for (w, h, c, act) in [(7, 7, 960, 3), (14, 14, 576, 3), (28, 28, 192, 1), (14, 14, 384, 0), (13, 7, 208, 3), (30, 14, 72, 1), (8, 21, 1040, 3)]:
+        run_dw(ref, rng, elemtype, 3, w, h, c, c, c, 3, 1, 1, 1, True, act)
 
 
 def test_convolutiondepthwise_many_tiles(ref):
