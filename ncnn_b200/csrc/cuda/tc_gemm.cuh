@@ -921,7 +921,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 row_ok = pix < p.M;
             }
             T* const orow = reinterpret_cast<T*>(p.out) + pix * p.out_cpitch + n0;
+            const bool fast_store = row_ok && v8ok && (n0 + BLOCK_N <= n8);
 
+            // bias of this tile's columns in shared memory: the layer's resident copy, or -- for the rare layer whose bias vector
+            // does not fit -- a per-warp copy of the tile's BLOCK_N values made here, so that the group loop has ONE bias path
+            int bias_base = n0;
+            if (!bias_in_smem)
+            {
+                bias_base = (warp - kEpilogueWarp0) * BLOCK_N;
+                __syncwarp();
+                for (int i = lane; i < BLOCK_N; i += 32) smem_bias[bias_base + i] = __ldg(p.bias + n0 + i);
+                __syncwarp();
+            }
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -967,29 +978,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int col0 = g * 32;
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)col0, r);
-                // bias of the group while the TMEM load is in flight (LDS broadcast; layers whose bias vector does not fit in shared
-                // memory read it through the read-only path -- kept as two explicit branches so that the common one is LDS, not
-                // a generic load with its descriptor set-up)
+                // bias of the group while the TMEM load is in flight: always an LDS broadcast (bias_base, see the tile set-up)
                 float bv[32];
-                if (bias_in_smem)
                 {
-                    const float* bs = smem_bias + n0 + col0;
+                    const float* bs = smem_bias + bias_base + col0;
 #pragma unroll
                     for (int q = 0; q < 8; q++)
                     {
                         const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * q);
-                        bv[4 * q + 0] = b4.x;
-                        bv[4 * q + 1] = b4.y;
-                        bv[4 * q + 2] = b4.z;
-                        bv[4 * q + 3] = b4.w;
-                    }
-                }
-                else
-                {
-#pragma unroll
-                    for (int q = 0; q < 8; q++)
-                    {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col0) + q);
                         bv[4 * q + 0] = b4.x;
                         bv[4 * q + 1] = b4.y;
                         bv[4 * q + 2] = b4.z;
@@ -1060,7 +1056,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t o[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) o[j] = Pack8<T>::pack2(v[2 * j], v[2 * j + 1]);
-                if (row_ok)
+                if (fast_store)
+                {
+                    // the whole tile is inside the blob and 32-byte aligned: two unconditional sector stores
+                    st_global_v8(orow + col0, &o[0]);
+                    st_global_v8(orow + col0 + 16, &o[8]);
+                }
+                else if (row_ok)
                 {
 #pragma unroll
                     for (int h = 0; h < 2; h++)
