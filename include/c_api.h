@@ -92,6 +92,16 @@ NCNN_C_API ncnn_mat_t ncnn_mat_create_external_3d(int w, int h, int c, void* dat
 NCNN_C_API ncnn_mat_t ncnn_mat_create_external_4d(int w, int h, int d, int c, void* data, ncnn_allocator_t allocator);
 NCNN_C_API void ncnn_mat_destroy(ncnn_mat_t mat);
 NCNN_C_API void ncnn_mat_fill_float(ncnn_mat_t mat, float v);
+
+/* pixel pre-processing on the host, as in the reference (src/c_api.h:167-185); the device path is ncnn_extractor_input_pixels */
+#define NCNN_MAT_PIXEL_RGB       1
+#define NCNN_MAT_PIXEL_BGR       2
+#define NCNN_MAT_PIXEL_GRAY      3
+#define NCNN_MAT_PIXEL_RGBA      4
+#define NCNN_MAT_PIXEL_BGRA      5
+#define NCNN_MAT_PIXEL_X2Y(X, Y) (X | (Y << 16))
+NCNN_C_API ncnn_mat_t ncnn_mat_from_pixels(const unsigned char* pixels, int type, int w, int h, int stride, ncnn_allocator_t allocator);
+NCNN_C_API void ncnn_mat_substract_mean_normalize(ncnn_mat_t mat, const float* mean_vals, const float* norm_vals);
 NCNN_C_API ncnn_mat_t ncnn_mat_clone(const ncnn_mat_t mat, ncnn_allocator_t allocator);
 NCNN_C_API ncnn_mat_t ncnn_mat_reshape_1d(const ncnn_mat_t mat, int w, ncnn_allocator_t allocator);
 NCNN_C_API ncnn_mat_t ncnn_mat_reshape_2d(const ncnn_mat_t mat, int w, int h, ncnn_allocator_t allocator);

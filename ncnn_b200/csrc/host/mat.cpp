@@ -253,6 +253,87 @@ void Mat::fill(int v)
     for (size_t i = 0; i < count; i++) p[i] = v;
 }
 
+// Mat::from_pixels (src/mat_pixel.cpp:2440-2545): every conversion of the reference's table, expressed as one rule per output
+// channel: copy source byte k, the 8-bit luma (77 R + 150 G + 29 B) >> 8 (from_rgb2gray, :736-800), or the constant 255 (alpha).
+Mat Mat::from_pixels(const unsigned char* pixels, int type, int w, int h, int stride, Allocator* allocator)
+{
+    Mat m;
+    const int from = type & 0xffff;
+    int to = (type >> 16) & 0xffff;
+    if (to == 0) to = from;
+    const int in_ch = from == 3 ? 1 : (from == 4 || from == 5 ? 4 : (from == 1 || from == 2 ? 3 : 0));
+    const int out_ch = to == 3 ? 1 : (to == 4 || to == 5 ? 4 : (to == 1 || to == 2 ? 3 : 0));
+    if (!pixels || in_ch == 0 || out_ch == 0 || w <= 0 || h <= 0)
+    {
+        NCNN_LOGE("from_pixels: unsupported pixel type %d", type);
+        return m;
+    }
+    if (stride <= 0) stride = w * in_ch;
+    // position of R, G, B (and A) inside a source pixel; gray sources have a single byte
+    const bool from_bgr = from == 2 || from == 5;
+    const int sr = from_bgr ? 2 : 0, sg = 1, sb = from_bgr ? 0 : 2;
+    // rule per output channel: >= 0 copy that source byte, -1 luma, -2 constant 255
+    int rule[4] = {0, 0, 0, 0};
+    if (to == 3)
+        rule[0] = from == 3 ? 0 : -1;
+    else
+    {
+        const bool to_bgr = to == 2 || to == 5;
+        if (from == 3)
+            rule[0] = rule[1] = rule[2] = 0; // gray replicated
+        else
+        {
+            rule[0] = to_bgr ? sb : sr;
+            rule[1] = sg;
+            rule[2] = to_bgr ? sr : sb;
+        }
+        if (out_ch == 4) rule[3] = in_ch == 4 ? 3 : -2;
+    }
+    m.create(w, h, out_ch, (size_t)4u, allocator);
+    if (m.empty()) return m;
+    for (int c = 0; c < out_ch; c++)
+    {
+        float* dst = m.channel(c);
+        const int r = rule[c];
+        for (int y = 0; y < h; y++)
+        {
+            const unsigned char* row = pixels + (size_t)y * stride;
+            float* d = dst + (size_t)y * w;
+            if (r >= 0)
+                for (int x = 0; x < w; x++) d[x] = (float)row[x * in_ch + r];
+            else if (r == -1)
+                for (int x = 0; x < w; x++)
+                {
+                    const unsigned char* px = row + x * in_ch;
+                    d[x] = (float)((px[sr] * 77 + px[sg] * 150 + px[sb] * 29) >> 8);
+                }
+            else
+                for (int x = 0; x < w; x++) d[x] = 255.f;
+        }
+    }
+    return m;
+}
+
+// Mat::substract_mean_normalize (src/mat.cpp): (x - mean[c]) * norm[c]; either array may be NULL
+void Mat::substract_mean_normalize(const float* mean_vals, const float* norm_vals)
+{
+    if (empty() || (!mean_vals && !norm_vals)) return;
+    const int chs = dims == 1 ? 1 : (dims == 2 ? 1 : c);
+    const size_t size = dims == 1 ? (size_t)w : (dims == 2 ? (size_t)w * h : (size_t)w * h * d);
+    for (int q = 0; q < chs; q++)
+    {
+        float* ptr = dims >= 3 ? (float*)channel(q) : (float*)data;
+        const float mean = mean_vals ? mean_vals[q] : 0.f;
+        const float norm = norm_vals ? norm_vals[q] : 1.f;
+        if (mean_vals && norm_vals)
+            for (size_t i = 0; i < size; i++) ptr[i] = (ptr[i] - mean) * norm;
+        else if (mean_vals)
+            for (size_t i = 0; i < size; i++) ptr[i] -= mean;
+        else
+            for (size_t i = 0; i < size; i++) ptr[i] *= norm;
+    }
+}
+
 Mat Mat::clone(Allocator* _allocator) const
 {
     if (empty()) return Mat();

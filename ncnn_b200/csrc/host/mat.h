@@ -39,6 +39,11 @@ public:
     void fill(float v);
     void fill(int v);
     Mat clone(Allocator* allocator = 0) const;
+
+    // src/mat_pixel.cpp / src/mat.cpp: 8-bit interleaved pixels -> planar fp32 (type = from | (to << 16), codes 1 RGB 2 BGR 3 GRAY
+    // 4 RGBA 5 BGRA), and the per-channel (x - mean) * norm pass.  Host versions; the device path is Extractor::input_pixels.
+    static Mat from_pixels(const unsigned char* pixels, int type, int w, int h, int stride, Allocator* allocator = 0);
+    void substract_mean_normalize(const float* mean_vals, const float* norm_vals);
     void clone_from(const Mat& mat, Allocator* allocator = 0);
     Mat reshape(int w, Allocator* allocator = 0) const;
     Mat reshape(int w, int h, Allocator* allocator = 0) const;

@@ -145,3 +145,35 @@ def test_seeded_weight_stream_is_consumed_exactly(ref, name):
     rd.close()
     L.ncnn_net_destroy(net)
     L.ncnn_option_destroy(opt)
+
+
+def test_from_pixels_and_normalize_match_reference(ours, ref):
+    """host pre-processing: ncnn_mat_from_pixels for every conversion of the reference's table (src/mat_pixel.cpp:2440-2545) and
+    ncnn_mat_substract_mean_normalize, bit-exact against the reference's own implementation on random images with a row stride"""
+    rng = np.random.default_rng(23)
+    RGB, BGR, GRAY, RGBA, BGRA = 1, 2, 3, 4, 5
+    chans = {RGB: 3, BGR: 3, GRAY: 1, RGBA: 4, BGRA: 4}
+    pairs = [(a, a) for a in chans] + [(RGB, BGR), (BGR, RGB), (RGB, GRAY), (BGR, GRAY), (RGB, RGBA), (BGR, BGRA), (BGR, RGBA), (RGB, BGRA), (GRAY, RGB), (GRAY, BGR),
+                                       (GRAY, RGBA), (GRAY, BGRA), (RGBA, RGB), (BGRA, BGR), (RGBA, BGR), (BGRA, RGB), (RGBA, GRAY), (BGRA, GRAY), (RGBA, BGRA), (BGRA, RGBA)]
+    for api in (ours, ref):
+        api.lib.ncnn_mat_from_pixels.restype = C.c_void_p
+        api.lib.ncnn_mat_from_pixels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        api.lib.ncnn_mat_substract_mean_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    w, h = 37, 11
+    for (a, b) in pairs:
+        ch = chans[a]
+        stride = w * ch + 5
+        buf = rng.integers(0, 256, (h, stride), dtype=np.uint8)
+        t = a if a == b else (a | (b << 16))
+        mean = rng.uniform(0, 200, chans[b]).astype(np.float32)
+        norm = rng.uniform(0.005, 0.05, chans[b]).astype(np.float32)
+        res = []
+        for api in (ours, ref):
+            m = api.lib.ncnn_mat_from_pixels(buf.ctypes.data_as(C.c_void_p), t, w, h, stride, None)
+            plain = api.mat_to_numpy(C.c_void_p(m)).copy()
+            api.lib.ncnn_mat_substract_mean_normalize(C.c_void_p(m), mean.ctypes.data_as(C.c_void_p), norm.ctypes.data_as(C.c_void_p))
+            res.append((plain, api.mat_to_numpy(C.c_void_p(m)).copy()))
+            api.lib.ncnn_mat_destroy(C.c_void_p(m))
+        assert res[0][0].shape == res[1][0].shape == (chans[b], h, w), (a, b, res[0][0].shape, res[1][0].shape)
+        assert np.array_equal(res[0][0], res[1][0]), ("from_pixels", a, b)
+        assert np.allclose(res[0][1], res[1][1], rtol=0, atol=1e-5), ("substract_mean_normalize", a, b)
