@@ -187,6 +187,30 @@ NCNN_CUDA_API int ncnn_cuda_dwconv2d_destroy(ncnn_cuda_dwconv2d_t conv);
 NCNN_CUDA_API int ncnn_cuda_dwconv2d_forward(ncnn_cuda_dwconv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top,
                                              int pad_left, int pad_top, void* stream);
 
+/* ------------------------------------------------------------------ Deconvolution / DeconvolutionDepthWise
+ * src/layer/deconvolution.cpp:68-146 and src/layer/deconvolutiondepthwise.cpp:68-208 (group == 1 is Deconvolution).
+ * weights [group][outch_g][inch_g][kh][kw] fp32 as the reference's load_model keeps them, re-packed once.
+ * The reference computes a bordered output of (w-1)*stride + dilation*(kernel-1) + 1 + output_pad per axis and then
+ * cuts the pads (cut_padding, deconvolution.cpp:364-392); here the host resolves the cut (pad_left/pad_top, or the
+ * SAME_UPPER / SAME_LOWER split of the difference to output_w/output_h) and `top` is the already-cut blob:
+ * top[y][x] = bordered[y + cut_top][x + cut_left]. */
+typedef struct ncnn_cuda_deconv2d_desc
+{
+    int inch, outch, group;
+    int kernel_w, kernel_h, dilation_w, dilation_h, stride_w, stride_h;
+    int output_pad_right, output_pad_bottom;
+    int bias_term;
+    ncnn_cuda_activation act;
+    int elemtype;
+} ncnn_cuda_deconv2d_desc;
+
+typedef struct ncnn_cuda_deconv2d* ncnn_cuda_deconv2d_t;
+
+NCNN_CUDA_API int ncnn_cuda_deconv2d_create(ncnn_cuda_deconv2d_t* conv, const ncnn_cuda_deconv2d_desc* desc, const float* weight_host, const float* bias_host, void* stream);
+NCNN_CUDA_API int ncnn_cuda_deconv2d_destroy(ncnn_cuda_deconv2d_t conv);
+NCNN_CUDA_API int ncnn_cuda_deconv2d_forward(ncnn_cuda_deconv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top,
+                                             int cut_left, int cut_top, void* stream);
+
 /* ------------------------------------------------------------------ Pooling
  * src/layer/pooling.cpp:39-348 (+ make_padding :350-412).  The host resolves pad_mode into
  * pad_left/pad_top and the output size; the kernel treats everything outside the real input as
@@ -272,6 +296,14 @@ NCNN_CUDA_API int ncnn_cuda_channel_affine(const ncnn_cuda_tensor* bottom, const
  * local_size channels (region_type 0) or local_size x local_size pixels (region_type 1) around each element, zeros outside.
  * bottom and top must be distinct blobs (the window reads neighbours). */
 NCNN_CUDA_API int ncnn_cuda_lrn(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int region_type, int local_size, float alpha, float beta, float bias, void* stream);
+
+/* Reduction (src/layer/reduction.cpp:216-752): operation 0 sum, 1 asum, 2 sumsq, 3 mean, 4 max, 5 min, 6 prod, 7 L1, 8 L2,
+ * 9 logsum, 10 logsumexp over the flagged axes of `bottom` (flags for axes the rank does not have are ignored; a 1-D blob
+ * always reduces w, :786-789).  `top` has the shape resolve_reduce_flags_and_output_shape (:753-856) gives: the same rank
+ * with 1s when keepdims, else the surviving extents in (w, h, d, c) order (a full reduction is a 1-D blob of w = 1).
+ * `coeff` multiplies the result (divided by the reduced element count for the mean, :709-749). */
+NCNN_CUDA_API int ncnn_cuda_reduction(int operation, int reduce_w, int reduce_h, int reduce_d, int reduce_c, int keepdims, float coeff,
+                                      const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
 
 /* ShuffleChannel (src/layer/shufflechannel.cpp:22-60): top channel group*j + i = bottom channel (c/group)*i + j.
  * `group` is the effective group count (the caller resolves the layer's `reverse` flag: group = c / group). */

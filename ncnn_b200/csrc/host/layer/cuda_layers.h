@@ -72,6 +72,38 @@ public:
     int handle_elemtype;
 };
 
+// src/layer/deconvolution.cpp; `group` stays 1 here and is read from id 7 by DeconvolutionDepthWise
+class Deconvolution : public Layer
+{
+public:
+    Deconvolution();
+    virtual ~Deconvolution();
+    virtual int load_param(const ParamDict& pd);
+    virtual int load_model(const ModelBin& mb);
+    virtual int create_pipeline(const Option& opt);
+    virtual int destroy_pipeline(const Option& opt);
+    virtual int forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const;
+    virtual bool reads_group() const { return false; }
+
+public:
+    int num_output, kernel_w, kernel_h, dilation_w, dilation_h, stride_w, stride_h;
+    int pad_left, pad_right, pad_top, pad_bottom;
+    int output_pad_right, output_pad_bottom, output_w, output_h;
+    int bias_term, weight_data_size, group, activation_type;
+    Mat activation_params;
+    int dynamic_weight;
+    Mat weight_data, bias_data;
+    ncnn_cuda_deconv2d_t handle;
+};
+
+// src/layer/deconvolutiondepthwise.cpp: same parameters plus id 7 = group; depthwise and grouped branches share one kernel
+class DeconvolutionDepthWise : public Deconvolution
+{
+public:
+    DeconvolutionDepthWise();
+    virtual bool reads_group() const { return true; }
+};
+
 // src/layer/innerproduct.cpp
 class InnerProduct : public Layer
 {
@@ -245,6 +277,33 @@ public:
     virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
     int region_type, local_size;
     float alpha, beta, bias;
+};
+
+// src/layer/reduction.cpp
+class Reduction : public Layer
+{
+public:
+    Reduction();
+    virtual int load_param(const ParamDict& pd);
+    virtual int forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const;
+    int operation, reduce_all, keepdims;
+    float coeff;
+    Mat axes;
+};
+
+// src/layer/memorydata.cpp -- a constant blob stored in the model file; uploaded once, handed out by reference
+class MemoryData : public Layer
+{
+public:
+    MemoryData();
+    virtual int load_param(const ParamDict& pd);
+    virtual int load_model(const ModelBin& mb);
+    virtual int create_pipeline(const Option& opt);
+    virtual int destroy_pipeline(const Option& opt);
+    virtual int forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat>& top_blobs, CudaCompute& cmd, const Option& opt) const;
+    int w, h, d, c, load_type;
+    Mat data;
+    CudaMat data_dev;
 };
 
 // src/layer/noop.cpp -- passes its blobs through

@@ -190,6 +190,169 @@ int LRN::forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Optio
     return ret;
 }
 
+// ------------------------------------------------------------------ Reduction (src/layer/reduction.cpp)
+Reduction::Reduction()
+{
+    one_blob_only = true;
+    support_inplace = false;
+}
+
+// src/layer/reduction.cpp:17-33
+int Reduction::load_param(const ParamDict& pd)
+{
+    operation = pd.get(0, 0);
+    reduce_all = pd.get(1, 1);
+    coeff = pd.get(2, 1.f);
+    axes = pd.get(3, Mat());
+    keepdims = pd.get(4, 0);
+    int fixbug0 = pd.get(5, 0);
+    if (fixbug0 == 0 && !axes.empty())
+    {
+        NCNN_LOGE("param is too old, please regenerate!");
+        return -1;
+    }
+    if (operation < 0 || operation > 10) return -1;
+    return 0;
+}
+
+// flags and output shape: src/layer/reduction.cpp:753-856
+int Reduction::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const
+{
+    const int dims = bottom_blob.dims;
+    if (dims < 1 || dims > 4) return -1;
+    bool reduce_w = false, reduce_h = false, reduce_d = false, reduce_c = false;
+    if (reduce_all)
+    {
+        reduce_w = reduce_h = reduce_d = reduce_c = true;
+    }
+    else
+    {
+        int axes_flag[4] = {0, 0, 0, 0};
+        const int* axes_ptr = (const int*)axes.data;
+        for (int i = 0; i < axes.w; i++)
+        {
+            int axis = axes_ptr[i];
+            if (axis < 0) axis += dims;
+            if (axis < 0 || axis >= dims) return -1;
+            axes_flag[axis] = 1;
+        }
+        if (dims == 1) reduce_w = true;
+        if (dims == 2)
+        {
+            reduce_h = axes_flag[0] == 1;
+            reduce_w = axes_flag[1] == 1;
+        }
+        if (dims == 3)
+        {
+            reduce_c = axes_flag[0] == 1;
+            reduce_h = axes_flag[1] == 1;
+            reduce_w = axes_flag[2] == 1;
+        }
+        if (dims == 4)
+        {
+            reduce_c = axes_flag[0] == 1;
+            reduce_d = axes_flag[1] == 1;
+            reduce_h = axes_flag[2] == 1;
+            reduce_w = axes_flag[3] == 1;
+        }
+    }
+    int outdims, outw = 1, outh = 1, outd = 1, outc = 1;
+    if (keepdims)
+    {
+        outdims = dims;
+        outw = reduce_w ? 1 : bottom_blob.w;
+        outh = (dims >= 2 && !reduce_h) ? bottom_blob.h : 1;
+        outd = (dims == 4 && !reduce_d) ? bottom_blob.d : 1;
+        outc = (dims >= 3 && !reduce_c) ? bottom_blob.c : 1;
+    }
+    else
+    {
+        int shape[4], ns = 0;
+        if (!reduce_w) shape[ns++] = bottom_blob.w;
+        if (dims >= 2 && !reduce_h) shape[ns++] = bottom_blob.h;
+        if (dims == 4 && !reduce_d) shape[ns++] = bottom_blob.d;
+        if (dims >= 3 && !reduce_c) shape[ns++] = bottom_blob.c;
+        outdims = ns == 0 ? 1 : ns; // a full reduction is a 1-element 1-D blob (:866-869)
+        if (ns >= 1) outw = shape[0];
+        if (ns >= 2) outh = shape[1];
+        if (ns == 3) outc = shape[2];
+        if (ns == 4)
+        {
+            outd = shape[2];
+            outc = shape[3];
+        }
+    }
+    top_blob.create_dims(outdims, outw, outh, outd, outc, bottom_blob.elemtype, bottom_blob.n, cmd.blob_allocator(opt));
+    if (top_blob.empty()) return -100;
+    ncnn_cuda_tensor b = bottom_blob.view(), t = top_blob.view();
+    return ncnn_cuda_reduction(operation, reduce_w, reduce_h, reduce_d, reduce_c, keepdims, coeff, &b, &t, cmd.stream());
+}
+
+// ------------------------------------------------------------------ MemoryData (src/layer/memorydata.cpp)
+MemoryData::MemoryData()
+{
+    one_blob_only = false;
+    support_inplace = false;
+    w = h = d = c = 0;
+    load_type = 1;
+}
+
+// src/layer/memorydata.cpp:15-24
+int MemoryData::load_param(const ParamDict& pd)
+{
+    w = pd.get(0, 0);
+    h = pd.get(1, 0);
+    d = pd.get(11, 0);
+    c = pd.get(2, 0);
+    load_type = pd.get(21, 1);
+    return 0;
+}
+
+// src/layer/memorydata.cpp:26-53
+int MemoryData::load_model(const ModelBin& mb)
+{
+    if (d != 0)
+        data = mb.load(w, h, d, c, load_type);
+    else if (c != 0)
+        data = mb.load(w, h, c, load_type);
+    else if (h != 0)
+        data = mb.load(w, h, load_type);
+    else if (w != 0)
+        data = mb.load(w, load_type);
+    else
+    {
+        data.create(1);
+        if (!data.empty()) ((float*)data.data)[0] = 0.f;
+    }
+    if (data.empty()) return -100;
+    return 0;
+}
+
+int MemoryData::create_pipeline(const Option& opt)
+{
+    if (data.elemsize != 4u) return -1; // integer constants (load_type 4) are outside the float-only device blobs
+    int ret = upload_const(data, opt.cuda_elemtype(), data_dev);
+    if (ret != 0) return ret;
+    if (opt.lightmode) data.release();
+    return 0;
+}
+
+int MemoryData::destroy_pipeline(const Option&)
+{
+    data_dev.release();
+    return 0;
+}
+
+// The reference clones the constant per forward (memorydata.cpp:55-64).  Device blobs are shared by reference count and
+// the executor already clones a shared blob before handing it to an in-place layer (NetPrivate::do_forward_layer), so the
+// constant is handed out as a reference: no copy, and it stays immutable.
+int MemoryData::forward(const std::vector<CudaMat>&, std::vector<CudaMat>& top_blobs, CudaCompute&, const Option&) const
+{
+    if (data_dev.empty()) return -100;
+    top_blobs[0] = data_dev;
+    return 0;
+}
+
 // ------------------------------------------------------------------ Noop (src/layer/noop.cpp)
 Noop::Noop()
 {

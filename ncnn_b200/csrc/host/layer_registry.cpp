@@ -41,6 +41,10 @@ DEFINE_LAYER_CREATOR(ShuffleChannel)
 DEFINE_LAYER_CREATOR(LRN)
 DEFINE_LAYER_CREATOR(Noop)
 DEFINE_LAYER_CREATOR(Crop)
+DEFINE_LAYER_CREATOR(Reduction)
+DEFINE_LAYER_CREATOR(MemoryData)
+DEFINE_LAYER_CREATOR(Deconvolution)
+DEFINE_LAYER_CREATOR(DeconvolutionDepthWise)
 
 static const layer_registry_entry cuda_layer_registry[] = {
     {"Input", Input_layer_creator},
@@ -75,6 +79,10 @@ static const layer_registry_entry cuda_layer_registry[] = {
     {"LRN", LRN_layer_creator},
     {"Noop", Noop_layer_creator},
     {"Crop", Crop_layer_creator},
+    {"Reduction", Reduction_layer_creator},
+    {"MemoryData", MemoryData_layer_creator},
+    {"Deconvolution", Deconvolution_layer_creator},
+    {"DeconvolutionDepthWise", DeconvolutionDepthWise_layer_creator},
 };
 
 static const int layer_type_count = (int)(sizeof(layer_type_names) / sizeof(layer_type_names[0]));

@@ -39,6 +39,12 @@ class DwConvDesc(C.Structure):
                 ("elemtype", C.c_int)]
 
 
+class DeconvDesc(C.Structure):
+    _fields_ = [("inch", C.c_int), ("outch", C.c_int), ("group", C.c_int), ("kernel_w", C.c_int), ("kernel_h", C.c_int), ("dilation_w", C.c_int),
+                ("dilation_h", C.c_int), ("stride_w", C.c_int), ("stride_h", C.c_int), ("output_pad_right", C.c_int), ("output_pad_bottom", C.c_int),
+                ("bias_term", C.c_int), ("act", Activation), ("elemtype", C.c_int)]
+
+
 class PoolDesc(C.Structure):
     _fields_ = [("pooling_type", C.c_int), ("kernel_w", C.c_int), ("kernel_h", C.c_int), ("stride_w", C.c_int), ("stride_h", C.c_int), ("pad_left", C.c_int),
                 ("pad_top", C.c_int), ("global_pooling", C.c_int), ("avgpool_count_include_pad", C.c_int), ("adaptive_pooling", C.c_int),

@@ -295,6 +295,103 @@ def test_convolutiondepthwise_many_tiles(ref):
     run_dw(ref, rng, F16, 40, 14, 14, 384, 384, 384, 3, 1, 1, 1, True, 3)
 
 
+# ------------------------------------------------------------------------------------------ Deconvolution
+def deconv_cut(w, h, k, d, s, pad, opr, opb, output_w, output_h):
+    """bordered size and the cut of the reference (src/layer/deconvolution.cpp:156-157 and cut_padding :364-392) ->
+    (outw, outh, cut_left, cut_top)"""
+    ext = d * (k - 1) + 1
+    fw, fh = (w - 1) * s + ext + opr, (h - 1) * s + ext + opb
+    if pad > 0:
+        return fw - 2 * pad, fh - 2 * pad, pad, pad
+    if output_w > 0 and output_h > 0:
+        wcut, hcut = fw - output_w, fh - output_h
+        if pad == -233:
+            return output_w, output_h, wcut // 2, hcut // 2
+        if pad == -234:
+            return output_w, output_h, wcut - wcut // 2, hcut - hcut // 2
+    return fw, fh, 0, 0
+
+
+def run_deconv(ref, rng, elemtype, n, w, h, ch, outch, group, k, d, s, pad, bias, act_type, opr=0, opb=0, output_w=0, output_h=0):
+    L = cabi.lib()
+    if output_w > 0 and output_h > 0 and pad not in (-233, -234):
+        pad = -233  # as tests/test_deconvolution.cpp:10-13 of the reference
+    x = quant(rand(rng, (n, ch, h, w)), elemtype)
+    wt = rand(rng, (outch, ch // group, k, k)) * np.float32(0.5)
+    b = rand(rng, (outch,)) if bias else None
+    params = {0: outch, 1: k, 2: d, 3: s, 4: pad, 5: int(bias), 6: wt.size, 9: act_type, 18: opr, 19: opb, 20: output_w, 21: output_h}
+    if group != 1:
+        params[7] = group
+    if ACT_PARAMS[act_type]:
+        params[10] = np.asarray(ACT_PARAMS[act_type], np.float32)
+    want = ref.layer_forward("Deconvolution" if group == 1 else "DeconvolutionDepthWise", params, [wt] + ([b] if bias else []), [x], batched=True)[0]
+    outw, outh, cut_left, cut_top = deconv_cut(w, h, k, d, s, pad, opr, opb, output_w, output_h)
+    assert want.shape == (n, outch, outh, outw), (want.shape, (n, outch, outh, outw))
+    desc = cabi.DeconvDesc(ch, outch, group, k, k, d, d, s, s, opr, opb, int(bias), act_of(act_type), elemtype)
+    handle = C.c_void_p()
+    wa, wp = cabi.fptr(wt)
+    if bias:
+        ba, bp = cabi.fptr(b)
+    else:
+        bp = None
+    cabi.check(L.ncnn_cuda_deconv2d_create(C.byref(handle), C.byref(desc), wp, bp, None), "deconv2d_create")
+    bottom = cabi.Blob.from_numpy(x, elemtype)
+    top = cabi.Blob((outch, outh, outw), n, elemtype, fill=float("nan"))
+    bd, td = bottom.desc(), top.desc()
+    cabi.check(L.ncnn_cuda_deconv2d_forward(handle, C.byref(bd), C.byref(td), cut_left, cut_top, None), "deconv2d_forward")
+    sync()
+    got = top.numpy()
+    L.ncnn_cuda_deconv2d_destroy(handle)
+    tol = 1e-5 if elemtype == F32 else 1e-4  # 16-bit: fp32 weights and accumulation, only the output store rounds
+    e = nerr(got, want, elemtype)
+    assert e <= tol, "deconv n%d %dx%dx%d->%d g%d k%d d%d s%d p%d op%d,%d out%dx%d: err %.3g" % (n, w, h, ch, outch, group, k, d, s, pad, opr, opb, output_w, output_h, e)
+
+
+DECONV_KDSP = [(1, 1, 1, 0), (1, 1, 2, 0), (2, 1, 1, 1), (2, 1, 2, -233), (3, 1, 1, 1), (3, 1, 2, 1), (3, 2, 1, 1), (4, 1, 1, -233), (4, 1, 2, -234),
+               (4, 2, 1, -234), (5, 1, 1, 2), (5, 1, 2, 2), (5, 2, 2, 2), (7, 1, 1, 3), (7, 1, 2, 3), (7, 2, 1, -233)]
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_deconvolution_grid(ref, elemtype):
+    """the kernel / dilation / stride / pad table and the output_pad / output_w,h cases of the reference's
+    tests/test_deconvolution.cpp:97-131, with a batch axis, against its naive layer"""
+    rng = np.random.default_rng(71)
+    i = 0
+    for (k, d, s, pad) in DECONV_KDSP:
+        for (w, h, c, outch, bias, opr, opb, ow, oh) in [(9, 7, 1, 1, 1, 0, 0, 0, 0), (9, 7, 4, 13, 0, 1, 1, 7, 5), (9, 7, 13, 4, 1, 1, 0, 0, 0),
+                                                         (9, 7, 8, 4, 1, 0, 0, 7, 5), (7, 7, 12, 12, 1, 0, 1, 0, 0), (4, 5, 12, 11, 0, 0, 1, 1, 0),
+                                                         (9, 7, 8, 13, 0, 2, 2, 0, 0), (9, 7, 16, 16, 0, 0, 2, 7, 5)]:
+            if pad > 0 and ((w - 1) * s + d * (k - 1) + 1 + opr - 2 * pad <= 0 or (h - 1) * s + d * (k - 1) + 1 + opb - 2 * pad <= 0):
+                continue
+            if elemtype == F32 or i % 2 == 0:
+                run_deconv(ref, rng, elemtype, 1 + i % 3, w, h, c, outch, 1, k, d, s, pad, bool(bias), i % 7, opr, opb, ow, oh)
+            i += 1
+    # wide channel counts (the 4x4 stride-2 upsampling heads of detection / segmentation graphs)
+    for (c, outch) in [(24, 32), (32, 28), (64, 64)]:
+        run_deconv(ref, rng, elemtype, 2, 7, 5, c, outch, 1, 4, 1, 2, 1, True, 1)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_deconvolutiondepthwise_grid(ref, elemtype):
+    """depthwise and grouped branches (src/layer/deconvolutiondepthwise.cpp:103-205); grid of the reference's
+    tests/test_deconvolutiondepthwise.cpp, with a batch axis"""
+    rng = np.random.default_rng(72)
+    i = 0
+    for (k, d, s, pad) in DECONV_KDSP:
+        for (w, h, c, outch, group, bias, opr, opb, ow, oh) in [(15, 7, 1, 1, 1, 1, 0, 0, 0, 0), (15, 7, 2, 2, 2, 0, 1, 1, 7, 5), (15, 7, 3, 3, 3, 1, 0, 1, 0, 0),
+                                                                (15, 7, 4, 2, 2, 0, 0, 0, 7, 5), (15, 7, 7, 7, 7, 1, 2, 2, 0, 0), (15, 7, 8, 8, 2, 1, 0, 0, 7, 5),
+                                                                (15, 7, 12, 12, 4, 0, 2, 2, 0, 0), (15, 7, 16, 32, 8, 1, 2, 0, 0, 0), (15, 7, 64, 64, 64, 1, 0, 0, 0, 0)]:
+            if group == 1:
+                continue
+            if pad > 0 and ((h - 1) * s + d * (k - 1) + 1 + opb - 2 * pad <= 0):
+                continue
+            if elemtype == F32 or i % 2 == 1:
+                run_deconv(ref, rng, elemtype, 1 + i % 2, w, h, c, outch, group, k, d, s, pad, bool(bias), i % 7, opr, opb, ow, oh)
+            i += 1
+    # the 2x depthwise upsampling of mobilenet_yolo / mobilenetv2_yolov3 (benchmark/models): k2 s2 on 13x13 maps
+    run_deconv(ref, rng, elemtype, 3, 13, 13, 96, 96, 96, 2, 1, 2, 0, False, 0)
+
+
 # ------------------------------------------------------------------------------------------ Pooling
 def run_pool(ref, rng, elemtype, n, w, h, c, ptype, k, s, pad, pad_mode, global_pool=0, include_pad=0, adaptive=0, out_wh=(0, 0)):
     L = cabi.lib()
@@ -515,3 +612,58 @@ def test_lrn(ref, elemtype):
         cabi.check(L.ncnn_cuda_lrn(C.byref(sd), C.byref(dd), region, size, alpha, beta, bias, None), "lrn")
         sync()
         assert nerr(dst.numpy(), want, elemtype) <= tol, ("lrn", c, h, w, region, size)
+
+
+# ------------------------------------------------------------------------------------------ Reduction
+def reduce_shape(shape, axes, keepdims):
+    """(flags w,h,d,c), top shape in numpy order -- src/layer/reduction.cpp:753-856; `shape` is numpy order (c,[d,]h,w) etc."""
+    dims = len(shape)
+    names = {1: ["w"], 2: ["h", "w"], 3: ["c", "h", "w"], 4: ["c", "d", "h", "w"]}[dims]
+    if axes is None:
+        red = set(names)
+    elif dims == 1:
+        red = {"w"}
+    else:
+        red = set(names[a if a >= 0 else a + dims] for a in axes)
+    if keepdims:
+        out = tuple(1 if nm in red else e for nm, e in zip(names, shape))
+    else:
+        out = tuple(e for nm, e in zip(names, shape) if nm not in red)
+        if not out:
+            out = (1,)
+    return tuple(int(nm in red) for nm in ["w", "h", "d", "c"]), out
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_reduction(ref, elemtype):
+    """all 11 operations x the axis sets of the reference's tests/test_reduction.cpp:116-172 (1-D .. 4-D, keepdims on/off,
+    coeff 1 / 2), batched, against its naive layer"""
+    L = cabi.lib()
+    L.ncnn_cuda_reduction.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(81)
+    cases = [((13,), [None, [0]]), ((5, 12), [None, [0], [1], [0, 1], [-1]]), ((7, 5, 9), [None, [0], [1], [2], [0, 2], [1, 2], [0, 1, 2], [-2, -1]]),
+             ((6, 3, 5, 4), [None, [0], [3], [0, 3], [1, 3], [2, 3], [1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3], [0, 1, 2, 3]]), ((40, 14, 14), [[1, 2]]), ((1, 1, 300), [[2]])]
+    i = 0
+    for shape, axis_sets in cases:
+        for axes in axis_sets:
+            for op in range(11):
+                i += 1
+                if elemtype != F32 and i % 3:
+                    continue
+                keepdims, coeff = i % 2, (2.0 if i % 4 < 2 else 1.0)
+                lo, hi = (0.001, 2.0) if op in (9, 10) else ((0.7, 1.3) if op == 6 else (-1.0, 1.0))  # positive for the logs; a product stays O(1)
+                x = quant(rand(rng, (2,) + shape, lo, hi), elemtype)
+                params = {0: op, 1: int(axes is None), 2: float(coeff), 4: keepdims, 5: 1}
+                if axes is not None:
+                    params[3] = np.asarray(axes, np.int32)
+                want = ref.layer_forward("Reduction", params, [], [x], batched=True)[0]
+                flags, oshape = reduce_shape(shape, axes, keepdims)
+                assert want.shape == (2,) + oshape, (want.shape, oshape, shape, axes, keepdims)
+                src = cabi.Blob.from_numpy(x, elemtype)
+                dst = cabi.Blob(oshape, 2, elemtype, fill=float("nan"))
+                sd, dd = src.desc(), dst.desc()
+                cabi.check(L.ncnn_cuda_reduction(op, flags[0], flags[1], flags[2], flags[3], keepdims, coeff, C.byref(sd), C.byref(dd), None), "reduction")
+                sync()
+                tol = 1e-5 if elemtype == F32 else 1e-4
+                e = nerr(dst.numpy(), want, elemtype)
+                assert e <= tol, ("reduction", shape, axes, op, keepdims, e)

@@ -197,9 +197,40 @@ def test_unfused_batchnorm_scale_shufflechannel_graph(ref, mode):
     assert nerr(got, want) <= TOL[mode], nerr(got, want)
 
 
+DECONV_PARAM = """7767517
+9 9
+Input                   data     0 1 data 0=20 1=16 2=3
+Convolution             conv1    1 1 data conv1 0=32 1=3 3=2 4=1 5=1 6=864 9=1
+Deconvolution           up1      1 1 conv1 up1 0=24 1=4 3=2 4=1 5=1 6=12288 9=1
+DeconvolutionDepthWise  up2      1 1 up1 up2 0=24 1=2 3=2 5=0 6=96 7=24
+Deconvolution           up3      1 1 up2 up3 0=16 1=3 3=2 4=-233 18=1 20=77 21=61 5=1 6=3456 9=2 -23310=1,0.1
+DeconvolutionDepthWise  up4      1 1 up3 up4 0=8 1=3 2=2 3=1 4=2 5=1 6=288 7=4
+Convolution             conv2    1 1 up4 conv2 0=8 1=3 3=2 5=1 6=576
+Pooling                 gap      1 1 conv2 gap 0=1 4=1
+InnerProduct            fc       1 1 gap fc 0=10 1=1 2=80
+"""
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_deconvolution_graph(ref, mode):
+    """Deconvolution / DeconvolutionDepthWise (explicit pads, SAME_UPPER with output_w/h + output_pad,
+    depthwise and grouped, dilation, fused activations) through Net.load_param / load_model / Extractor against the
+    reference CPU path on the same bytes; every intermediate blob is compared, not only the logits"""
+    text = DECONV_PARAM
+    weights = modelzoo.random_model_bytes(text, seed=17)
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-1, 1, (3, 3, 16, 20)).astype(np.float32)
+    outs = ["up1", "up2", "up3", "up4", "fc"]
+    want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=outs)
+    got = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=outs)
+    for o in outs:
+        assert got[o].shape == want[o].shape, (o, got[o].shape, want[o].shape)
+        assert nerr(got[o], want[o]) <= TOL[mode], (o, nerr(got[o], want[o]))
+
+
 EXTRA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
 EXTRA_MODELS = ["mobilenet", "mobilenet_v3", "shufflenet", "shufflenet_v2", "mnasnet", "proxylessnasnet", "efficientnet_b0", "regnety_400m", "resnet18",
-                "squeezenet", "blazeface", "FastestDet", "alexnet", "googlenet", "nanodet_m", "yolo-fastestv2"]
+                "squeezenet", "blazeface", "FastestDet", "alexnet", "googlenet", "nanodet_m", "yolo-fastestv2", "efficientnetv2_b0"]
 EXTRA_INPUT = {"blazeface": 128, "FastestDet": 352, "squeezenet": 227, "alexnet": 227, "nanodet_m": 320, "yolo-fastestv2": 352}
 # The detection graphs (FastestDet, yolo-fastestv2, nanodet_m) only expose the concatenation of its sigmoid / softmax heads (no linear blob to assert on) after ~70 stored
 # fp16 activations: measured 2.1e-3, so its 16-bit bound is 4e-3; its fp32 bound stays 1e-5 like every other graph.

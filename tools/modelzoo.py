@@ -360,12 +360,15 @@ def random_model_bytes(text, seed=7767517, bias_scale=0.1, dtype=np.float32):
         for b in bs:
             consumer[b] = t
     for t, n, bs, ts, p in layers:
-        if t in ("Convolution", "ConvolutionDepthWise", "InnerProduct"):
+        if t in ("Convolution", "ConvolutionDepthWise", "InnerProduct", "Deconvolution", "DeconvolutionDepthWise"):
             if t == "InnerProduct":
                 num_output, bias_term, wsize = p[0], p.get(1, 0), p[2]
             else:
                 num_output, bias_term, wsize = p[0], p.get(5, 0), p[6]
             fan_in = wsize // num_output
+            if t.startswith("Deconvolution"):
+                # an output pixel only sees the taps congruent to it modulo the stride
+                fan_in = max(1, fan_in // (p.get(3, 1) * p.get(13, p.get(3, 1))))
             nxt = consumer.get(ts[0], "")
             if p.get(9, 0) != 0 or nxt in ("ReLU", "Swish"):
                 a = np.sqrt(6.0 / fan_in)          # He-uniform: keeps the second moment through ReLU / SiLU
@@ -391,7 +394,13 @@ def random_model_bytes(text, seed=7767517, bias_scale=0.1, dtype=np.float32):
             chunks.append(rng.uniform(0.5, 1.5, c).astype(np.float32).tobytes())
             if p.get(1, 0):
                 chunks.append(rng.uniform(-0.2, 0.2, c).astype(np.float32).tobytes())
-        elif t in ("PReLU", "Gemm", "Deconvolution"):
+        elif t == "MemoryData":
+            # src/layer/memorydata.cpp:26-53: w*h*d*c raw fp32 (load type 1, no tag)
+            count = max(p.get(0, 0), 1) * max(p.get(1, 0), 1) * max(p.get(11, 0), 1) * max(p.get(2, 0), 1)
+            if p.get(21, 1) != 1:
+                raise NotImplementedError("MemoryData load_type %d" % p.get(21, 1))
+            chunks.append(rng.uniform(0.5, 1.5, count).astype(np.float32).tobytes())
+        elif t in ("PReLU", "Gemm"):
             raise NotImplementedError("random weights for " + t)
     return b"".join(chunks)
 
