@@ -285,6 +285,7 @@ NCNN_CUDA_API int ncnn_cuda_gemm_strided(const ncnn_cuda_gemm_args* args, void* 
 #define NCNN_CUDA_UNARY_SCALE     8 /* x * p0 (Dropout with scale != 1, dropout.cpp:14-40) */
 #define NCNN_CUDA_UNARY_TANH      9
 #define NCNN_CUDA_UNARY_HARDSIGMOID 10 /* p0 = alpha, p1 = beta */
+#define NCNN_CUDA_UNARY_GELU      11 /* p0 != 0: the tanh form (fast_gelu), else 0.5 x erfc(-x / sqrt 2); src/layer/gelu.cpp:21-58 */
 NCNN_CUDA_API int ncnn_cuda_unary(int op, float p0, float p1, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
 
 /* BatchNorm (src/layer/batchnorm.cpp:57-120: value = b * value + a) and Scale (src/layer/scale.cpp:44-168: value * s + bias):
@@ -304,6 +305,13 @@ NCNN_CUDA_API int ncnn_cuda_lrn(const ncnn_cuda_tensor* bottom, const ncnn_cuda_
  * `coeff` multiplies the result (divided by the reduced element count for the mean, :709-749). */
 NCNN_CUDA_API int ncnn_cuda_reduction(int operation, int reduce_w, int reduce_h, int reduce_d, int reduce_c, int keepdims, float coeff,
                                       const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, void* stream);
+
+/* LayerNorm (src/layer/layernorm.cpp:38-181): every run of `group_size` consecutive elements along the reference's planar
+ * order inside one channel (1-D / 2-D blobs: inside one row) is normalised to zero mean / unit variance (biased, + eps) and,
+ * when gamma/beta (fp32 device arrays of group_size values, both or neither) are given, scaled and shifted element-wise.
+ * group_size is w, w*h or w*h*d as the layer's affine_size selects; in place (bottom == top) allowed. */
+NCNN_CUDA_API int ncnn_cuda_layernorm(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group_size, float eps, const float* gamma_dev,
+                                      const float* beta_dev, void* stream);
 
 /* ShuffleChannel (src/layer/shufflechannel.cpp:22-60): top channel group*j + i = bottom channel (c/group)*i + j.
  * `group` is the effective group count (the caller resolves the layer's `reverse` flag: group = c / group). */

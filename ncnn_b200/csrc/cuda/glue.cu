@@ -55,6 +55,8 @@ __device__ __forceinline__ float unary_apply(int op, float v, float p0, float p1
         float lower = -p1 / p0, upper = (1.f / p0) + lower;
         return v < lower ? 0.f : (v > upper ? 1.f : v * p0 + p1);
     }
+    case NCNN_CUDA_UNARY_GELU: // gelu.cpp:37, :52
+        return p0 != 0.f ? 0.5f * v * (1.0f + tanhf(0.79788452f * (v + 0.044715f * v * v * v))) : 0.5f * v * erfcf(-0.70710678f * v);
     }
     return v;
 }

@@ -1,4 +1,4 @@
-// reduction.cu -- Reduction (src/layer/reduction.cpp:216-752 of the reference): sum / asum / sumsq / mean / max / min /
+// reduction.cu -- Reduction (src/layer/reduction.cpp:216-752 of the reference) and LayerNorm (layernorm.cpp, second half of the file): sum / asum / sumsq / mean / max / min /
 // prod / L1 / L2 / logsum / logsumexp over any subset of the (w, h, d, c) axes of a batched blob, with or without
 // keepdims.  One warp per output element: the lanes stride over the reduced index space (channel fastest when c is
 // reduced, so a warp reads contiguous lanes of the channel-innermost blob), combine with shuffles, and lane 0 applies
@@ -240,3 +240,112 @@ int ncnn_cuda_reduction(int operation, int reduce_w, int reduce_h, int reduce_d,
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// src/layer/layernorm.cpp:38-76 per group: mean, biased variance of (x - mean), y = (x * a + b) * gamma + beta with
+// a = 1/sqrt(var + eps), b = -mean * a.  One warp per group; the group's elements are `stride` apart (1 for 1-D/2-D blobs
+// whose rows are contiguous, cpitch for the pixels of one channel of a 3-D/4-D blob).  Three passes over data that stays
+// in L1/L2; fp32 arithmetic.
+namespace {
+
+struct LnGeom
+{
+    int n, groups_per_block, blocks, size; // per sample: `blocks` x `groups_per_block` groups of `size` elements
+    long long block_stride, group_stride, elem_stride, in_nstep, out_nstep;
+    float eps;
+};
+
+template<typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* in, T* out, const float* __restrict__ gamma, const float* __restrict__ beta, LnGeom g)
+{
+    NC_PDL_PROLOGUE();
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long per_sample = (long long)g.blocks * g.groups_per_block;
+    const long long total = per_sample * g.n;
+    for (long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < total; o += warps)
+    {
+        const int b = (int)(o / per_sample);
+        const long long r = o - (long long)b * per_sample;
+        const long long blk = r / g.groups_per_block, grp = r - blk * g.groups_per_block;
+        const long long off = blk * g.block_stride + grp * g.group_stride;
+        const T* src = in + b * g.in_nstep + off;
+        T* dst = out + b * g.out_nstep + off;
+        float sum = 0.f;
+        for (int i = lane; i < g.size; i += 32) sum += to_f32(src[i * g.elem_stride]);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        const float mean = sum / g.size;
+        float sq = 0.f;
+        for (int i = lane; i < g.size; i += 32)
+        {
+            const float v = to_f32(src[i * g.elem_stride]) - mean;
+            sq = fmaf(v, v, sq);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, s);
+        const float a = 1.f / sqrtf(sq / g.size + g.eps);
+        const float bb = -mean * a;
+        for (int i = lane; i < g.size; i += 32)
+        {
+            float v = to_f32(src[i * g.elem_stride]) * a + bb;
+            if (gamma) v = v * gamma[i] + beta[i];
+            dst[i * g.elem_stride] = from_f32<T>(v);
+        }
+    }
+}
+
+template<typename T>
+static int run_layernorm(const LnGeom& g, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const float* gamma, const float* beta, cudaStream_t stream)
+{
+    const long long total = (long long)g.blocks * g.groups_per_block * g.n;
+    NC_PDL_LAUNCH((layernorm_kernel<T>), grid_for(total * 32, 256, 16), 256, 0, stream, (const T*)bottom->data, (T*)top->data, gamma, beta, g);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace
+
+extern "C" int ncnn_cuda_layernorm(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group_size, float eps, const float* gamma_dev, const float* beta_dev, void* stream)
+{
+    NC_REQUIRE(bottom && top && bottom->elemtype == top->elemtype && bottom->dims == top->dims && bottom->dims >= 1 && bottom->dims <= 4, "layernorm: blob pair of one type and rank required");
+    NC_REQUIRE(bottom->w == top->w && bottom->h == top->h && bottom->d == top->d && bottom->c == top->c && bottom->cpitch == top->cpitch, "layernorm: shapes differ");
+    NC_REQUIRE((gamma_dev == 0) == (beta_dev == 0), "layernorm: gamma and beta come together");
+    NC_REQUIRE(group_size > 0, "layernorm: empty group");
+    LnGeom g;
+    g.n = bottom->n < 1 ? 1 : bottom->n;
+    NC_REQUIRE((top->n < 1 ? 1 : top->n) == g.n, "layernorm: batch mismatch");
+    g.in_nstep = bottom->nstep;
+    g.out_nstep = top->nstep;
+    g.eps = eps;
+    g.size = group_size;
+    if (bottom->dims <= 2)
+    {
+        // rows are contiguous (w innermost): one group per row
+        NC_REQUIRE(group_size == bottom->w, "layernorm: a 1-D / 2-D blob is normalised over w");
+        g.blocks = bottom->dims == 2 ? bottom->h : 1;
+        g.groups_per_block = 1;
+        g.block_stride = bottom->cpitch;
+        g.group_stride = 0;
+        g.elem_stride = 1;
+    }
+    else
+    {
+        // the pixels of one channel are cpitch apart; a group is `group_size` consecutive pixels of a channel
+        const long long pixels = (long long)bottom->w * bottom->h * (bottom->dims == 4 ? bottom->d : 1);
+        NC_REQUIRE(pixels % group_size == 0 && (group_size == bottom->w || group_size == bottom->w * bottom->h || group_size == pixels), "layernorm: group is not w, w*h or w*h*d");
+        g.blocks = (int)(pixels / group_size);
+        g.groups_per_block = bottom->c;
+        g.block_stride = (long long)group_size * bottom->cpitch;
+        g.group_stride = 1;
+        g.elem_stride = bottom->cpitch;
+    }
+    if ((long long)g.blocks * g.groups_per_block * g.n == 0) return 0;
+    switch (bottom->elemtype)
+    {
+    case NCNN_CUDA_F32: return run_layernorm<float>(g, bottom, top, gamma_dev, beta_dev, as_stream(stream));
+    case NCNN_CUDA_BF16: return run_layernorm<__nv_bfloat16>(g, bottom, top, gamma_dev, beta_dev, as_stream(stream));
+    case NCNN_CUDA_F16: return run_layernorm<__half>(g, bottom, top, gamma_dev, beta_dev, as_stream(stream));
+    }
+    return -1;
+}

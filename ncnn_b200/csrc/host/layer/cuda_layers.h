@@ -223,6 +223,11 @@ class Dropout : public UnaryActivation
 public:
     virtual int load_param(const ParamDict& pd);
 };
+class GELU : public UnaryActivation // src/layer/gelu.cpp
+{
+public:
+    virtual int load_param(const ParamDict& pd);
+};
 
 // a constant host Mat (1-D / 2-D) as a device blob of the same logical shape, allocated from the weight allocator (gemm_layer.cpp)
 int upload_const(const Mat& src, int elemtype, CudaMat& dst);
@@ -277,6 +282,22 @@ public:
     virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
     int region_type, local_size;
     float alpha, beta, bias;
+};
+
+// src/layer/layernorm.cpp
+class LayerNorm : public Layer
+{
+public:
+    LayerNorm();
+    virtual int load_param(const ParamDict& pd);
+    virtual int load_model(const ModelBin& mb);
+    virtual int create_pipeline(const Option& opt);
+    virtual int destroy_pipeline(const Option& opt);
+    virtual int forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option& opt) const;
+    int affine_size, affine;
+    float eps;
+    Mat gamma_data, beta_data;
+    CudaMat gamma_dev, beta_dev;
 };
 
 // src/layer/reduction.cpp

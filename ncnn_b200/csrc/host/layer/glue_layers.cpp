@@ -96,6 +96,14 @@ int HardSigmoid::load_param(const ParamDict& pd)
     return 0;
 }
 
+// src/layer/gelu.cpp:14-19
+int GELU::load_param(const ParamDict& pd)
+{
+    op = NCNN_CUDA_UNARY_GELU;
+    p0 = pd.get(0, 0) ? 1.f : 0.f; // fast_gelu
+    return 0;
+}
+
 // src/layer/dropout.cpp:14-40: identity unless scale != 1
 int Dropout::load_param(const ParamDict& pd)
 {

@@ -190,6 +190,68 @@ int LRN::forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Optio
     return ret;
 }
 
+// ------------------------------------------------------------------ LayerNorm (src/layer/layernorm.cpp)
+LayerNorm::LayerNorm()
+{
+    one_blob_only = true;
+    support_inplace = true;
+}
+
+// src/layer/layernorm.cpp:14-21
+int LayerNorm::load_param(const ParamDict& pd)
+{
+    affine_size = pd.get(0, 0);
+    eps = pd.get(1, 0.001f);
+    affine = pd.get(2, 1);
+    return 0;
+}
+
+// src/layer/layernorm.cpp:23-36
+int LayerNorm::load_model(const ModelBin& mb)
+{
+    if (affine == 0) return 0;
+    gamma_data = mb.load(affine_size, 1);
+    if (gamma_data.empty()) return -100;
+    beta_data = mb.load(affine_size, 1);
+    if (beta_data.empty()) return -100;
+    return 0;
+}
+
+int LayerNorm::create_pipeline(const Option&)
+{
+    if (affine == 0) return 0;
+    int ret = upload_const(gamma_data, NCNN_CUDA_F32, gamma_dev);
+    if (ret == 0) ret = upload_const(beta_data, NCNN_CUDA_F32, beta_dev);
+    return ret;
+}
+
+int LayerNorm::destroy_pipeline(const Option&)
+{
+    gamma_dev.release();
+    beta_dev.release();
+    return 0;
+}
+
+// group selection: src/layer/layernorm.cpp:78-181 (w for 1-D / 2-D blobs; w, w*h or w*h*d by affine_size otherwise)
+int LayerNorm::forward_inplace(CudaMat& bottom_top_blob, CudaCompute& cmd, const Option&) const
+{
+    const CudaMat& m = bottom_top_blob;
+    int size;
+    if (m.dims <= 2)
+        size = m.w;
+    else if (m.dims == 3)
+        size = affine_size == m.w ? m.w : m.w * m.h;
+    else
+        size = affine_size == m.w ? m.w : (affine_size == m.w * m.h ? m.w * m.h : m.w * m.h * m.d);
+    if (affine && size != affine_size)
+    {
+        NCNN_LOGE("LayerNorm: affine_size %d does not match the normalised extent %d", affine_size, size);
+        return -1;
+    }
+    ncnn_cuda_tensor t = bottom_top_blob.view();
+    return ncnn_cuda_layernorm(&t, &t, size, eps, affine ? (const float*)gamma_dev.data : 0, affine ? (const float*)beta_dev.data : 0, cmd.stream());
+}
+
 // ------------------------------------------------------------------ Reduction (src/layer/reduction.cpp)
 Reduction::Reduction()
 {

@@ -42,6 +42,8 @@ DEFINE_LAYER_CREATOR(LRN)
 DEFINE_LAYER_CREATOR(Noop)
 DEFINE_LAYER_CREATOR(Crop)
 DEFINE_LAYER_CREATOR(Reduction)
+DEFINE_LAYER_CREATOR(LayerNorm)
+DEFINE_LAYER_CREATOR(GELU)
 DEFINE_LAYER_CREATOR(MemoryData)
 DEFINE_LAYER_CREATOR(Deconvolution)
 DEFINE_LAYER_CREATOR(DeconvolutionDepthWise)
@@ -80,6 +82,8 @@ static const layer_registry_entry cuda_layer_registry[] = {
     {"Noop", Noop_layer_creator},
     {"Crop", Crop_layer_creator},
     {"Reduction", Reduction_layer_creator},
+    {"LayerNorm", LayerNorm_layer_creator},
+    {"GELU", GELU_layer_creator},
     {"MemoryData", MemoryData_layer_creator},
     {"Deconvolution", Deconvolution_layer_creator},
     {"DeconvolutionDepthWise", DeconvolutionDepthWise_layer_creator},

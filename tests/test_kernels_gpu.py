@@ -667,3 +667,47 @@ def test_reduction(ref, elemtype):
                 tol = 1e-5 if elemtype == F32 else 1e-4
                 e = nerr(dst.numpy(), want, elemtype)
                 assert e <= tol, ("reduction", shape, axes, op, keepdims, e)
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm / GELU
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_layernorm(ref, elemtype):
+    """LayerNorm over w / w*h / w*h*d with and without the element-wise affine, 1-D .. 4-D blobs (the shapes of the reference's
+    tests/test_layernorm.cpp plus a transformer-sized row), in place, batched, against its naive layer"""
+    import torch
+    L = cabi.lib()
+    L.ncnn_cuda_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(91)
+    tol = 1e-5 if elemtype == F32 else 1e-4
+    cases = [((15,), 15), ((9, 24), 24), ((145, 768), 768), ((5, 6, 8), 8), ((5, 6, 8), 48), ((12, 4, 7), 7), ((3, 2, 5, 6), 6), ((3, 2, 5, 6), 30), ((3, 2, 5, 6), 60)]
+    for i, (shape, size) in enumerate(cases):
+        for affine in (1, 0):
+            eps = [1e-5, 1e-3, 1e-6][i % 3]
+            x = quant(rand(rng, (2,) + shape, -2.0, 3.0), elemtype)
+            gamma, beta = rand(rng, (size,), 0.5, 1.5), rand(rng, (size,), -0.5, 0.5)
+            want = ref.layer_forward("LayerNorm", {0: size, 1: float(eps), 2: affine}, [gamma, beta] if affine else [], [x], batched=True)[0]
+            blob = cabi.Blob.from_numpy(x, elemtype)
+            d = blob.desc()
+            gd, bd = torch.from_numpy(gamma).cuda(), torch.from_numpy(beta).cuda()
+            cabi.check(L.ncnn_cuda_layernorm(C.byref(d), C.byref(d), size, eps, C.c_void_p(gd.data_ptr()) if affine else None, C.c_void_p(bd.data_ptr()) if affine else None, None), "layernorm")
+            sync()
+            e = nerr(blob.numpy(), want, elemtype)
+            assert e <= tol, ("layernorm", shape, size, affine, e)
+
+
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_gelu(ref, elemtype):
+    """GELU, erfc and tanh forms (src/layer/gelu.cpp), through the unary entry point"""
+    L = cabi.lib()
+    L.ncnn_cuda_unary.argtypes = [C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(92)
+    tol = 1e-5 if elemtype == F32 else 1e-4
+    for shape in [(33,), (7, 40), (12, 9, 11)]:
+        for fast in (0, 1):
+            x = quant(rand(rng, (3,) + shape, -6.0, 6.0), elemtype)
+            want = ref.layer_forward("GELU", {0: fast}, [], [x], batched=True)[0]
+            blob = cabi.Blob.from_numpy(x, elemtype)
+            d = blob.desc()
+            cabi.check(L.ncnn_cuda_unary(11, float(fast), 0.0, C.byref(d), C.byref(d), None), "gelu")
+            sync()
+            assert nerr(blob.numpy(), want, elemtype) <= tol, ("gelu", shape, fast)

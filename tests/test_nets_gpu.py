@@ -53,9 +53,9 @@ def run_ours(text, weights, inputs, mode, batched, outputs=None, fusion=1):
         L.lib.ncnn_option_destroy(opt)
 
 
-def run_ref(ref, text, weights, inputs, batched, outputs=None):
+def run_ref(ref, text, weights, inputs, batched, outputs=None, packing=True):
     from oracle import ref as oref
-    opt = ref.strict_fp32_option(num_threads=ref.cpu_count(), packing=True)
+    opt = ref.strict_fp32_option(num_threads=ref.cpu_count(), packing=packing)
     net = oref.Net(ref, text, weights, opt)
     try:
         return net.run(inputs, outputs=outputs, batched=batched)
@@ -256,6 +256,38 @@ def test_deconvolution_graph(ref, mode):
     x = rng.uniform(-1, 1, (3, 3, 16, 20)).astype(np.float32)
     outs = ["up1", "up2", "up3", "up4", "fc"]
     want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=outs)
+    got = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=outs)
+    for o in outs:
+        assert got[o].shape == want[o].shape, (o, got[o].shape, want[o].shape)
+        assert nerr(got[o], want[o]) <= TOL[mode], (o, nerr(got[o], want[o]))
+
+
+NORM_PARAM = """7767517
+8 8
+Input         data   0 1 data 0=12 1=10 2=3
+MemoryData    gate   0 1 gate 0=16
+Convolution   conv1  1 1 data conv1 0=16 1=3 4=1 5=1 6=432
+LayerNorm     ln     1 1 conv1 ln 0=12 1=0.00001 2=1
+GELU          gelu   1 1 ln gelu 0=1
+BinaryOp      mul    2 1 gelu gate mul 0=2
+Reduction     red    1 1 mul red 0=3 1=0 -23303=2,1,2 4=0 5=1
+InnerProduct  fc     1 1 red fc 0=10 1=1 2=160
+"""
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_layernorm_gelu_memorydata_reduction_graph(ref, mode):
+    """LayerNorm (affine over w), GELU, a MemoryData constant broadcast per channel against a batched blob, and a mean
+    Reduction over (h, w), through Net.load_param / load_model / Extractor against the reference CPU path.
+    The reference runs with use_packing_layout off here: its packed x86 LayerNorm takes 1/sqrt(var + eps) from the approximate
+    _mm256_rsqrt_ps without a refinement step (src/layer/x86/layernorm_x86.cpp:219-271), which puts the reference's own
+    optimised path 2e-4 away from its naive layer; the unpacked path (:295) is the exact 1.f / sqrtf the naive layer uses."""
+    text = NORM_PARAM
+    weights = modelzoo.random_model_bytes(text, seed=19)
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-1, 1, (3, 3, 10, 12)).astype(np.float32)
+    outs = ["ln", "mul", "red", "fc"]
+    want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=outs, packing=False)
     got = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=outs)
     for o in outs:
         assert got[o].shape == want[o].shape, (o, got[o].shape, want[o].shape)

@@ -394,6 +394,11 @@ def random_model_bytes(text, seed=7767517, bias_scale=0.1, dtype=np.float32):
             chunks.append(rng.uniform(0.5, 1.5, c).astype(np.float32).tobytes())
             if p.get(1, 0):
                 chunks.append(rng.uniform(-0.2, 0.2, c).astype(np.float32).tobytes())
+        elif t == "LayerNorm":
+            # src/layer/layernorm.cpp:23-36: gamma, beta raw fp32 when affine (id 2, default 1)
+            if p.get(2, 1):
+                chunks.append(rng.uniform(0.5, 1.5, p[0]).astype(np.float32).tobytes())
+                chunks.append(rng.uniform(-0.2, 0.2, p[0]).astype(np.float32).tobytes())
         elif t == "MemoryData":
             # src/layer/memorydata.cpp:26-53: w*h*d*c raw fp32 (load type 1, no tag)
             count = max(p.get(0, 0), 1) * max(p.get(1, 0), 1) * max(p.get(11, 0), 1) * max(p.get(2, 0), 1)
