@@ -282,7 +282,7 @@ def main():
     mean_vals = np.asarray([104.0, 117.0, 123.0], np.float32)
     norm_vals = np.asarray([0.017, 0.0175, 0.0171], np.float32)
 
-    def e2e_pixels_run(n_threads, steps):
+    def e2e_pixels_run(n_threads, steps, decode=None):
         bufs = [sess.pinned_pixels(px) for _ in range(n_threads)]
         per = [steps // n_threads + (1 if i < steps % n_threads else 0) for i in range(n_threads)]
         errs = []
@@ -291,7 +291,7 @@ def main():
             try:
                 lib.ncnn_cuda_set_device(local_rank)
                 for _ in range(per[i]):
-                    lib.ncnn_mat_destroy(sess.extract_host_pixels(bufs[i][1], bufs[i][2], 2, mean_vals, norm_vals))
+                    lib.ncnn_mat_destroy(sess.extract_host_pixels(bufs[i][1], bufs[i][2], 2, mean_vals, norm_vals, yolov8_decode=decode))
             except Exception as e:
                 errs.append(e)
 
@@ -318,6 +318,19 @@ def main():
         h2d_pixels = int(sess.last_h2d_pixels)
     except Exception as e:  # the fp32-Mat e2e above is the contract figure; this one is extra
         sys.stderr.write("e2e with pixel input failed: %s\n" % e)
+    # ---- detection heads: pixel input AND the decode of the prediction blob on the device (examples/yolov8.cpp generate_proposals,
+    # ncnn_extractor_extract_yolov8_proposals): 6 floats per anchor come back instead of 64 + classes
+    e2e_decoded_value = d2h_decoded = None
+    if model == "yolov8s":
+        try:
+            dec = ([8, 16, 32], 0.25)
+            e2e_pixels_run(nthreads, 2 * nthreads, decode=dec)
+            barrier()
+            dec_s = max_over_ranks(e2e_pixels_run(nthreads, args.steps, decode=dec))
+            e2e_decoded_value = replicas.throughput(batch, args.steps, world, dec_s * 1000.0)
+            d2h_decoded = int(sess.last_d2h_pixels)
+        except Exception as e:
+            sys.stderr.write("e2e with device decode failed: %s\n" % e)
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
     if rank == 0:
         sampler.stop()
@@ -383,6 +396,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_threads": nthreads,
                     "serial_value": e2e_serial_value,
                     "pixels_value": e2e_pixels_value, "pixels_h2d_bytes_per_step": h2d_pixels,
+                    "pixels_decoded_value": e2e_decoded_value, "pixels_decoded_d2h_bytes_per_step": d2h_decoded,
                     "mode": "each step = extractor.input(pinned host Mat) + extract(host Mat); steps dealt to %d host thread(s), one Extractor/stream per step" % nthreads},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "fused_layers": sess.fused_layers}
 

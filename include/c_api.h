@@ -284,6 +284,14 @@ NCNN_C_API int ncnn_extractor_extract_cuda(ncnn_extractor_t ex, const char* name
  * extract call returns. */
 NCNN_C_API int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
                                            const float* mean_vals, const float* norm_vals);
+/* Device post-processing for YOLOv8-style heads: runs the graph up to blob `name` (the 2-D prediction blob, see
+ * ncnn_cuda_yolov8_decode in ncnn_cuda.h), decodes it on the device as generate_proposals of the reference's
+ * examples/yolov8.cpp:160-273 does on the host, and downloads only the decoded records: `*proposals` becomes a batched 2-D
+ * fp32 Mat, w = 6 {x, y, width, height, prob, label}, h = anchors, one row per anchor in anchor order; rows below
+ * prob_threshold have prob = 0 and label = -1.  in_w / in_h: size of the (padded) network input.  The caller sorts the
+ * surviving rows and applies NMS as the example does. */
+NCNN_C_API int ncnn_extractor_extract_yolov8_proposals(ncnn_extractor_t ex, const char* name, const int* strides, int num_strides, int in_w, int in_h,
+                                                       float prob_threshold, ncnn_mat_t* proposals);
 /* PCIe bytes of the last ncnn_extractor_extract call */
 NCNN_C_API size_t ncnn_extractor_get_last_h2d_bytes(const ncnn_extractor_t ex);
 NCNN_C_API size_t ncnn_extractor_get_last_d2h_bytes(const ncnn_extractor_t ex);

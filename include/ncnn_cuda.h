@@ -313,6 +313,15 @@ NCNN_CUDA_API int ncnn_cuda_reduction(int operation, int reduce_w, int reduce_h,
 NCNN_CUDA_API int ncnn_cuda_layernorm(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group_size, float eps, const float* gamma_dev,
                                       const float* beta_dev, void* stream);
 
+/* YOLOv8 head decode on the device: the generate_proposals step of the reference's examples/yolov8.cpp:160-273.
+ * `pred`: 2-D blob per image, one row per anchor point = 4 x 16 box-distribution logits + num_class class logits
+ * (w = 64 + num_class, h = sum over strides of (in_w / stride) * (in_h / stride), rows ordered stride by stride, y-major).
+ * `proposals`: 2-D fp32 blob, w = 6, h = pred->h, same batch: per anchor {x, y, width, height, prob, label} in input pixels,
+ * prob = sigmoid(max class logit); anchors with prob < prob_threshold get prob = 0, label = -1.  One record per anchor in
+ * anchor order (deterministic); sorting and NMS (examples/yolov8.cpp:73-153) stay with the caller. */
+NCNN_CUDA_API int ncnn_cuda_yolov8_decode(const ncnn_cuda_tensor* pred, const int* strides, int num_strides, int in_w, int in_h, float prob_threshold,
+                                          const ncnn_cuda_tensor* proposals, void* stream);
+
 /* ShuffleChannel (src/layer/shufflechannel.cpp:22-60): top channel group*j + i = bottom channel (c/group)*i + j.
  * `group` is the effective group count (the caller resolves the layer's `reverse` flag: group = c / group). */
 NCNN_CUDA_API int ncnn_cuda_shuffle_channel(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, int group, void* stream);

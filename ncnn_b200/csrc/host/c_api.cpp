@@ -1019,6 +1019,14 @@ int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const uns
 {
     return ((Extractor*)ex)->input_pixels(name, pixels, type, w, h, stride, n, nstride, mean_vals, norm_vals);
 }
+int ncnn_extractor_extract_yolov8_proposals(ncnn_extractor_t ex, const char* name, const int* strides, int num_strides, int in_w, int in_h, float prob_threshold,
+                                            ncnn_mat_t* proposals)
+{
+    Mat m;
+    int ret = ((Extractor*)ex)->extract_yolov8_proposals(name, strides, num_strides, in_w, in_h, prob_threshold, m);
+    *proposals = ret == 0 ? (ncnn_mat_t)(new Mat(m)) : 0;
+    return ret;
+}
 int ncnn_extractor_extract(ncnn_extractor_t ex, const char* name, ncnn_mat_t* mat)
 {
     Mat m;

@@ -1209,6 +1209,42 @@ int Extractor::extract(int blob_index, CudaMat& feat, CudaCompute& cmd)
     return 0;
 }
 
+int Extractor::extract_yolov8_proposals(const char* blob_name, const int* strides, int num_strides, int in_w, int in_h, float prob_threshold, Mat& proposals)
+{
+    int blob_index = d->net->find_blob_index_by_name(blob_name);
+    if (blob_index == -1) return -1;
+    CudaContext* ctx = acquire_cuda_context(d->net->opt.cuda_device_index);
+    if (!ctx)
+    {
+        NCNN_LOGE("no CUDA device available: %s", ncnn_cuda_last_error());
+        return -1;
+    }
+    int ret;
+    {
+        CudaCompute cmd(ctx);
+        CudaMat pred, decoded;
+        ret = extract(blob_index, pred, cmd);
+        if (ret == 0 && pred.dims != 2) ret = -1;
+        if (ret == 0)
+        {
+            decoded.create(6, pred.h, NCNN_CUDA_F32, pred.n, cmd.blob_allocator(d->opt));
+            if (decoded.empty()) ret = -100;
+        }
+        if (ret == 0)
+        {
+            ncnn_cuda_tensor p = pred.view(), q = decoded.view();
+            ret = ncnn_cuda_yolov8_decode(&p, strides, num_strides, in_w, in_h, prob_threshold, &q, cmd.stream());
+        }
+        if (ret == 0) ret = cmd.record_download(decoded, proposals, d->opt);
+        int sret = cmd.submit_and_wait();
+        if (ret == 0) ret = sret;
+        d->h2d = cmd.h2d_bytes;
+        d->d2h = cmd.d2h_bytes;
+    }
+    reclaim_cuda_context(ctx);
+    return ret;
+}
+
 size_t Extractor::last_h2d_bytes() const
 {
     return d->h2d;

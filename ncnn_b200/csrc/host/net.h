@@ -112,6 +112,10 @@ public:
     int input_pixels(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals,
                      const float* norm_vals);
 
+    // device post-processing: forward to the YOLOv8 prediction blob, decode it on the device
+    // (examples/yolov8.cpp:160-273 generate_proposals) and download one {x, y, w, h, prob, label} row per anchor
+    int extract_yolov8_proposals(const char* blob_name, const int* strides, int num_strides, int in_w, int in_h, float prob_threshold, Mat& proposals);
+
     // bytes moved over PCIe by the last extract(Mat&) call
     size_t last_h2d_bytes() const;
     size_t last_d2h_bytes() const;

@@ -139,9 +139,13 @@ class Session(object):
         C.memmove(ptr, pixels.ctypes.data, nbytes)
         return m, ptr, pixels.shape
 
-    def extract_host_pixels(self, ptr, shape, pixel_type, mean_vals, norm_vals):
-        """one call with device pre-processing: Extractor.input_pixels(pinned 8-bit images) + extract(host Mat)"""
+    def extract_host_pixels(self, ptr, shape, pixel_type, mean_vals, norm_vals, yolov8_decode=None):
+        """one call with device pre-processing: Extractor.input_pixels(pinned 8-bit images) + extract(host Mat).
+        yolov8_decode = (strides, prob_threshold): the result is decoded on the device as well
+        (ncnn_extractor_extract_yolov8_proposals) and only 6 floats per anchor come back"""
         lib = self.L.lib
+        lib.ncnn_extractor_extract_yolov8_proposals.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        lib.ncnn_extractor_get_last_d2h_bytes.restype = C.c_size_t
         lib.ncnn_extractor_input_pixels.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         n, h, w, ch = shape
         ex = lib.ncnn_extractor_create(self.net)
@@ -152,10 +156,16 @@ class Session(object):
                                                 norm_vals.ctypes.data_as(C.c_void_p) if norm_vals is not None else None)
             if r != 0:
                 raise RuntimeError("input_pixels returned %d" % r)
-            r = lib.ncnn_extractor_extract(ex, self.output_name, C.byref(out))
+            if yolov8_decode is not None:
+                strides, thr = yolov8_decode
+                st = (C.c_int * len(strides))(*strides)
+                r = lib.ncnn_extractor_extract_yolov8_proposals(ex, self.output_name, st, len(strides), w, h, thr, C.byref(out))
+            else:
+                r = lib.ncnn_extractor_extract(ex, self.output_name, C.byref(out))
             if r != 0:
                 raise RuntimeError("extract returned %d: %s" % (r, lib.ncnn_cuda_last_error().decode()))
             self.last_h2d_pixels = lib.ncnn_extractor_get_last_h2d_bytes(ex)
+            self.last_d2h_pixels = lib.ncnn_extractor_get_last_d2h_bytes(ex)
         finally:
             lib.ncnn_extractor_destroy(ex)
         return out

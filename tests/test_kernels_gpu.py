@@ -711,3 +711,37 @@ def test_gelu(ref, elemtype):
             cabi.check(L.ncnn_cuda_unary(11, float(fast), 0.0, C.byref(d), C.byref(d), None), "gelu")
             sync()
             assert nerr(blob.numpy(), want, elemtype) <= tol, ("gelu", shape, fast)
+
+
+# ------------------------------------------------------------------------------------------ YOLOv8 decode
+@pytest.mark.parametrize("elemtype", [F32, BF16, F16])
+def test_yolov8_decode(elemtype):
+    """device decode of the YOLOv8 head (detect.cu) against the restatement of examples/yolov8.cpp generate_proposals
+    (oracle/yolov8_decode.py): three strides, 80 / 5 / 33 classes, a mix of rows above and below the threshold, batched"""
+    from oracle import yolov8_decode as oy
+    L = cabi.lib()
+    L.ncnn_cuda_yolov8_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(101)
+    strides = [8, 16, 32]
+    for (in_w, in_h, num_class, thr) in [(96, 64, 80, 0.25), (64, 64, 5, 0.4), (160, 96, 33, 0.25)]:
+        rows = sum((in_w // s) * (in_h // s) for s in strides)
+        n = 3
+        pred = rand(rng, (n, rows, 64 + num_class), -3.0, 0.0)
+        pred[:, :, :64] = rand(rng, (n, rows, 64), -2.0, 4.0)
+        pred[:, :, 64:] += rand(rng, (n, rows, 1), -2.0, 1.5)  # per-anchor offset: some rows pass, some do not
+        pred[0, 3, 64:] = -1.0                                    # all classes equal: the first one wins
+        pred = quant(pred, elemtype)
+        want = np.stack([oy.generate_proposals(pred[b], strides, in_w, in_h, thr) for b in range(n)])
+        src = cabi.Blob.from_numpy(pred, elemtype)
+        dst = cabi.Blob((rows, 6), n, F32, fill=float("nan"))
+        sd, dd = src.desc(), dst.desc()
+        st = (C.c_int * 3)(*strides)
+        cabi.check(L.ncnn_cuda_yolov8_decode(C.byref(sd), st, 3, in_w, in_h, thr, C.byref(dd), None), "yolov8_decode")
+        sync()
+        got = dst.numpy()
+        score = 1.0 / (1.0 + np.exp(-pred[:, :, 64:].max(-1).astype(np.float64)))
+        sure = np.abs(score - thr) > 1e-5   # a score within rounding of the threshold may fall on either side
+        assert 0.1 < (want[..., 5] >= 0).mean() < 0.9, "the case should mix accepted and rejected anchors"
+        assert np.array_equal(got[..., 5][sure], want[..., 5][sure]), "labels / accepted set differ"
+        assert np.abs(got[..., 4] - want[..., 4])[sure].max() <= 1e-6
+        assert np.abs(got[..., :4] - want[..., :4])[sure].max() <= 1e-5 * max(in_w, in_h)

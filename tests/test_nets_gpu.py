@@ -389,3 +389,55 @@ def test_device_preprocessing_pixels(ref, mode):
     finally:
         net.close()
         L.lib.ncnn_option_destroy(opt)
+
+
+def test_yolov8_device_decode(ref):
+    """ncnn_extractor_extract_yolov8_proposals (forward + decode on the device, 6 floats per anchor come
+    back) against the restated examples/yolov8.cpp generate_proposals applied to the REFERENCE's out0 blob, then the same
+    NMS on both"""
+    import ctypes as C
+    from ncnn_b200 import capi
+    from oracle import yolov8_decode as oy
+    name, size, n, thr = "yolov8s", 320, 2, 0.534  # random-init heads put every score near 0.53: the threshold splits them
+    text = netutil.with_input_size(modelzoo.param_text(name), size)
+    weights = modelzoo.random_model_bytes(text, seed=netutil.WEIGHT_SEED)
+    x = netutil.random_input(name, n, size, seed=1)
+    want_pred = run_ref(ref, text, weights, {"in0": x}, batched=True, outputs=["out0"])["out0"]
+    strides = [8, 16, 32]
+    want = np.stack([oy.generate_proposals(want_pred[b], strides, size, size, thr) for b in range(n)])
+    api = product()
+    L = api.lib
+    opt = api.make_option(1, **MODES["fp32"])
+    net = capi.Net(api, text, weights, opt)
+    ex = L.ncnn_extractor_create(net.net)
+    try:
+        m = api.mat_from_numpy(x, batched=True)
+        assert L.ncnn_extractor_input(ex, b"in0", m) == 0
+        out = C.c_void_p()
+        L.ncnn_extractor_extract_yolov8_proposals.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        st = (C.c_int * 3)(*strides)
+        assert L.ncnn_extractor_extract_yolov8_proposals(ex, b"out0", st, 3, size, size, thr, C.byref(out)) == 0
+        got = api.mat_to_numpy(out, force_batch=True)
+        L.ncnn_extractor_get_last_d2h_bytes.restype = C.c_size_t
+        d2h = L.ncnn_extractor_get_last_d2h_bytes(ex)
+        L.ncnn_mat_destroy(out)
+        L.ncnn_mat_destroy(m)
+    finally:
+        L.ncnn_extractor_destroy(ex)
+        net.close()
+        L.ncnn_option_destroy(opt)
+    assert got.shape == want.shape == (n, 2100, 6)
+    assert d2h <= n * 2100 * 8 * 4  # 6 floats (padded to 8) per anchor instead of 144
+    score = 1.0 / (1.0 + np.exp(-want_pred[:, :, 64:].max(-1).astype(np.float64)))
+    sure = np.abs(score - thr) > 1e-4
+    assert 0.1 < (want[..., 5] >= 0).mean() < 0.9
+    assert np.array_equal(got[..., 5][sure], want[..., 5][sure])
+    assert np.abs(got[..., 4] - want[..., 4])[sure].max() <= 1e-5
+    assert np.abs(got[..., :4] - want[..., :4])[sure].max() <= 1e-5 * size * 16
+    # the caller's part (sort + class-aware NMS, examples/yolov8.cpp:73-153) gives the same detections from both
+    for b in range(n):
+        keep = sure[b] & (want[b, :, 5] >= 0)
+        a, w_ = got[b][keep], want[b][keep]
+        oa, ow = np.argsort(-a[:, 4], kind="stable")[:300], np.argsort(-w_[:, 4], kind="stable")[:300]
+        if np.array_equal(oa, ow):  # equal scores can order differently; NMS is only comparable on the same order
+            assert oy.nms_sorted_bboxes(a[oa], 0.45) == oy.nms_sorted_bboxes(w_[ow], 0.45)
