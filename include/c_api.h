@@ -102,6 +102,8 @@ NCNN_C_API void ncnn_mat_fill_float(ncnn_mat_t mat, float v);
 #define NCNN_MAT_PIXEL_X2Y(X, Y) (X | (Y << 16))
 NCNN_C_API ncnn_mat_t ncnn_mat_from_pixels(const unsigned char* pixels, int type, int w, int h, int stride, ncnn_allocator_t allocator);
 NCNN_C_API void ncnn_mat_substract_mean_normalize(ncnn_mat_t mat, const float* mean_vals, const float* norm_vals);
+/* src/c_api.h:180 */
+NCNN_C_API void ncnn_mat_to_pixels(const ncnn_mat_t mat, unsigned char* pixels, int type, int stride);
 NCNN_C_API ncnn_mat_t ncnn_mat_clone(const ncnn_mat_t mat, ncnn_allocator_t allocator);
 NCNN_C_API ncnn_mat_t ncnn_mat_reshape_1d(const ncnn_mat_t mat, int w, ncnn_allocator_t allocator);
 NCNN_C_API ncnn_mat_t ncnn_mat_reshape_2d(const ncnn_mat_t mat, int w, int h, ncnn_allocator_t allocator);

@@ -211,6 +211,10 @@ void ncnn_mat_substract_mean_normalize(ncnn_mat_t mat, const float* mean_vals, c
 {
     ((Mat*)mat)->substract_mean_normalize(mean_vals, norm_vals);
 }
+void ncnn_mat_to_pixels(const ncnn_mat_t mat, unsigned char* pixels, int type, int stride)
+{
+    ((const Mat*)mat)->to_pixels(pixels, type, stride);
+}
 void ncnn_mat_fill_float(ncnn_mat_t mat, float v)
 {
     ((Mat*)mat)->fill(v);

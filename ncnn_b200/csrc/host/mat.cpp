@@ -314,6 +314,58 @@ Mat Mat::from_pixels(const unsigned char* pixels, int type, int w, int h, int st
     return m;
 }
 
+// Mat::to_pixels (src/mat_pixel.cpp:2710-2753): the eight conversion families of the reference as one rule per output byte:
+// the Mat channel to take (saturated as SATURATE_CAST_UCHAR does, :147: truncate toward zero, clamp to 0..255) or the
+// constant 255 for a synthesised alpha.  Conversions the reference does not implement (e.g. RGB2GRAY) are refused the same way.
+void Mat::to_pixels(unsigned char* pixels, int type, int stride) const
+{
+    if (empty() || !pixels || dims != 3) return;
+    const int from = type & 0xffff;
+    int to = (type >> 16) & 0xffff;
+    if (to == 0) to = from;
+    const int in_ch = from == 3 ? 1 : (from == 4 || from == 5 ? 4 : (from == 1 || from == 2 ? 3 : 0));
+    const int out_ch = to == 3 ? 1 : (to == 4 || to == 5 ? 4 : (to == 1 || to == 2 ? 3 : 0));
+    const bool swap = ((from == 1 || from == 4) && (to == 2 || to == 5)) || ((from == 2 || from == 5) && (to == 1 || to == 4));
+    // implemented families: same type; RGB<->BGR; RGB/BGR -> RGBA/BGRA (either order); GRAY -> RGBA/BGRA; RGBA<->BGRA
+    const bool ok = in_ch != 0 && out_ch != 0 && c >= in_ch
+                    && (to == from || (in_ch == 3 && out_ch == 3) || (in_ch == 3 && out_ch == 4) || (in_ch == 1 && out_ch == 4) || (in_ch == 4 && out_ch == 4));
+    if (!ok)
+    {
+        NCNN_LOGE("unimplemented convert type %d", type);
+        return;
+    }
+    int rule[4] = {0, 1, 2, 3}; // -2: constant 255
+    if (in_ch == 1)
+        rule[0] = rule[1] = rule[2] = 0;
+    else if (swap)
+    {
+        rule[0] = 2;
+        rule[2] = 0;
+    }
+    if (out_ch == 4 && in_ch != 4) rule[3] = -2;
+    if (stride <= 0) stride = w * out_ch;
+    for (int k = 0; k < out_ch; k++)
+    {
+        const int r = rule[k];
+        const float* src = r >= 0 ? (const float*)channel(r) : 0;
+        for (int y = 0; y < h; y++)
+        {
+            unsigned char* row = pixels + (size_t)y * stride + k;
+            if (!src)
+            {
+                for (int x = 0; x < w; x++) row[x * out_ch] = 255;
+                continue;
+            }
+            const float* sp = src + (size_t)y * w;
+            for (int x = 0; x < w; x++)
+            {
+                int v = (int)sp[x];
+                row[x * out_ch] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+        }
+    }
+}
+
 // Mat::substract_mean_normalize (src/mat.cpp): (x - mean[c]) * norm[c]; either array may be NULL
 void Mat::substract_mean_normalize(const float* mean_vals, const float* norm_vals)
 {

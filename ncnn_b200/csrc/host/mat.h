@@ -44,6 +44,8 @@ public:
     // 4 RGBA 5 BGRA), and the per-channel (x - mean) * norm pass.  Host versions; the device path is Extractor::input_pixels.
     static Mat from_pixels(const unsigned char* pixels, int type, int w, int h, int stride, Allocator* allocator = 0);
     void substract_mean_normalize(const float* mean_vals, const float* norm_vals);
+    // src/mat_pixel.cpp:2692-2753; stride 0 = w * channels of the target type
+    void to_pixels(unsigned char* pixels, int type, int stride = 0) const;
     void clone_from(const Mat& mat, Allocator* allocator = 0);
     Mat reshape(int w, Allocator* allocator = 0) const;
     Mat reshape(int w, int h, Allocator* allocator = 0) const;

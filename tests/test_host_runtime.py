@@ -177,3 +177,30 @@ def test_from_pixels_and_normalize_match_reference(ours, ref):
         assert res[0][0].shape == res[1][0].shape == (chans[b], h, w), (a, b, res[0][0].shape, res[1][0].shape)
         assert np.array_equal(res[0][0], res[1][0]), ("from_pixels", a, b)
         assert np.allclose(res[0][1], res[1][1], rtol=0, atol=1e-5), ("substract_mean_normalize", a, b)
+
+
+def test_to_pixels_matches_reference(ours, ref):
+    """host post-processing: ncnn_mat_to_pixels for the conversion families the reference implements (src/mat_pixel.cpp:2710-2753),
+    byte-exact against the reference on float images with fractions, negatives and values above 255, with a row stride"""
+    rng = np.random.default_rng(29)
+    RGB, BGR, GRAY, RGBA, BGRA = 1, 2, 3, 4, 5
+    chans = {RGB: 3, BGR: 3, GRAY: 1, RGBA: 4, BGRA: 4}
+    pairs = [(a, a) for a in chans] + [(RGB, BGR), (BGR, RGB), (RGB, RGBA), (BGR, BGRA), (BGR, RGBA), (RGB, BGRA), (GRAY, RGBA), (GRAY, BGRA), (RGBA, BGRA), (BGRA, RGBA)]
+    for api in (ours, ref):
+        api.lib.ncnn_mat_to_pixels.restype = None
+        api.lib.ncnn_mat_to_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    w, h = 29, 13
+    for (a, b) in pairs:
+        x = rng.uniform(-40.0, 300.0, (chans[a], h, w)).astype(np.float32)
+        x[0, 0, :6] = [0.0, 0.999, 254.999, 255.0, 255.5, -0.5]
+        stride = w * chans[b] + 7
+        t = a if a == b else (a | (b << 16))
+        res = []
+        for api in (ours, ref):
+            m = api.mat_from_numpy(x)
+            buf = np.full((h, stride), 171, np.uint8)
+            api.lib.ncnn_mat_to_pixels(m, buf.ctypes.data_as(C.c_void_p), t, stride)
+            api.lib.ncnn_mat_destroy(m)
+            res.append(buf)
+        assert np.array_equal(res[0], res[1]), ("to_pixels", a, b)
+        assert (res[0][:, w * chans[b]:] == 171).all()  # the stride padding is left alone
