@@ -286,6 +286,11 @@ NCNN_C_API int ncnn_extractor_extract_cuda(ncnn_extractor_t ex, const char* name
  * extract call returns. */
 NCNN_C_API int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
                                            const float* mean_vals, const float* norm_vals);
+/* The same with ncnn_mat_from_pixels_resize (src/c_api.h:177): every image is brought to target_w x target_h by the reference's
+ * 8-bit bilinear resize (src/mat_pixel_resize.cpp, bit-exact) on the device before the conversion; the source images may be
+ * larger or smaller than the network input and only their raw bytes cross PCIe. */
+NCNN_C_API int ncnn_extractor_input_pixels_resize(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
+                                                  int target_w, int target_h, const float* mean_vals, const float* norm_vals);
 /* Device post-processing for YOLOv8-style heads: runs the graph up to blob `name` (the 2-D prediction blob, see
  * ncnn_cuda_yolov8_decode in ncnn_cuda.h), decodes it on the device as generate_proposals of the reference's
  * examples/yolov8.cpp:160-273 does on the host, and downloads only the decoded records: `*proposals` becomes a batched 2-D

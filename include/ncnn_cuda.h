@@ -123,6 +123,17 @@ NCNN_CUDA_API int ncnn_cuda_unpack_to_planar(const ncnn_cuda_tensor* src, const 
 NCNN_CUDA_API int ncnn_cuda_pixels_to_blob(const unsigned char* pixels_dev, int channels, int w, int h, int stride, long long nstride, int swap_rb, const float* mean_vals,
                                            const float* norm_vals, const ncnn_cuda_tensor* top, void* stream);
 
+/* The same with the reference's bilinear resize in front: Mat::from_pixels_resize (src/mat_pixel.cpp:2546-2578), i.e.
+ * resize_bilinear_c1/c3/c4 (src/mat_pixel_resize.cpp:210-1039, 11-bit integer coefficients) on the 8-bit image, then from_pixels
+ * and substract_mean_normalize, one thread per output pixel, bit-exact with the reference's integer arithmetic.
+ * ncnn_cuda_resize_tables (host only, no device work) fills 3 * (w + h) ints -- source column / row offsets and the short
+ * coefficients exactly as :599-669 compute them -- which the caller copies to the device as `tables_dev`.
+ * top: (w, h, channels) blob of the target size; the source must be at least 2 x 2. */
+NCNN_CUDA_API int ncnn_cuda_resize_tables_count(int w, int h);
+NCNN_CUDA_API int ncnn_cuda_resize_tables(int src_w, int src_h, int w, int h, int* tables_host);
+NCNN_CUDA_API int ncnn_cuda_pixels_resize_to_blob(const unsigned char* pixels_dev, int channels, int src_w, int src_h, int stride, long long nstride, int swap_rb,
+                                                  const float* mean_vals, const float* norm_vals, const int* tables_dev, const ncnn_cuda_tensor* top, void* stream);
+
 NCNN_CUDA_API int ncnn_cuda_reshape(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, void* stream);
 /* Permute (src/layer/permute.cpp:16-164): order_type as in the reference */
 NCNN_CUDA_API int ncnn_cuda_permute(const ncnn_cuda_tensor* src, const ncnn_cuda_tensor* dst, int order_type, void* stream);

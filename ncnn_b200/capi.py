@@ -282,7 +282,7 @@ class Net(object):
                 L.ncnn_mat_destroy(m)
         return res
 
-    def run_pixels(self, name, pixels, pixel_type, mean_vals=None, norm_vals=None, outputs=None):
+    def run_pixels(self, name, pixels, pixel_type, mean_vals=None, norm_vals=None, outputs=None, resize=None):
         """pixels: (n, h, w, channels) uint8, interleaved; pre-processing (from_pixels + substract_mean_normalize) runs on the
         device (ncnn_extractor_input_pixels, product library only); returns {blob name: ndarray (n, ...)}"""
         import numpy as np
@@ -295,8 +295,14 @@ class Net(object):
         ex = L.ncnn_extractor_create(self.net)
         res = {}
         try:
-            r = L.ncnn_extractor_input_pixels(ex, name.encode(), pixels.ctypes.data_as(C.c_void_p), pixel_type, w, h, w * ch, n, h * w * ch,
-                                              mean.ctypes.data_as(C.c_void_p) if mean is not None else None, norm.ctypes.data_as(C.c_void_p) if norm is not None else None)
+            mp = mean.ctypes.data_as(C.c_void_p) if mean is not None else None
+            npp = norm.ctypes.data_as(C.c_void_p) if norm is not None else None
+            if resize is not None:  # (target_w, target_h): the reference's from_pixels_resize, on the device
+                L.ncnn_extractor_input_pixels_resize.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                                                 C.c_void_p, C.c_void_p]
+                r = L.ncnn_extractor_input_pixels_resize(ex, name.encode(), pixels.ctypes.data_as(C.c_void_p), pixel_type, w, h, w * ch, n, h * w * ch, resize[0], resize[1], mp, npp)
+            else:
+                r = L.ncnn_extractor_input_pixels(ex, name.encode(), pixels.ctypes.data_as(C.c_void_p), pixel_type, w, h, w * ch, n, h * w * ch, mp, npp)
             if r != 0:
                 raise RuntimeError("input_pixels %s returned %d" % (name, r))
             for oname in (outputs or self.output_names):

@@ -331,6 +331,161 @@ static int run_pixels(const unsigned char* pixels, int ch, int w, int h, int str
     return 0;
 }
 
+// ---------------------------------------------------------------- the same with the reference's bilinear resize in front
+// Mat::from_pixels_resize (src/mat_pixel.cpp:2546-2578) = resize_bilinear_c1/c3/c4 (src/mat_pixel_resize.cpp:210-1039) on the
+// 8-bit image, then from_pixels.  The reference's resize is integer arithmetic on 11-bit coefficients:
+//   row value  r = (S[sx] * a0 + S[sx + 1] * a1) >> 4                       (hresize, :789-794)
+//   pixel      v = (((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2) >> 2          (vresize_one, :182-186), saturated to 8 bits,
+// a pure function of four source bytes per channel, so one thread produces one output pixel bit-exactly; the per-column /
+// per-row source offsets and coefficients (the float -> short rounding of :617-669) come from ncnn_cuda_resize_tables,
+// computed once on the host exactly as the reference computes them.
+template<typename T, int CH>
+__global__ void __launch_bounds__(256) pixels_resize_to_blob_kernel(const unsigned char* __restrict__ pixels, int stride, long long nstride, const int* __restrict__ tab, int w, int h,
+                                                                    int swap_rb, PixelAffine pa, T* __restrict__ out, int cpitch, long long out_nstep, int n)
+{
+    NC_PDL_PROLOGUE();
+    const int* xofs = tab;
+    const int* yofs = tab + w;
+    const int* alpha = tab + w + h;      // a0, a1 per column
+    const int* beta = tab + w + h + 2 * w; // b0, b1 per row
+    const long long total = (long long)n * h * w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        const int x = (int)(idx % w);
+        long long r = idx / w;
+        const int y = (int)(r % h);
+        const int b = (int)(r / h);
+        const int sx = xofs[x], sy = yofs[y];
+        const int a0 = alpha[2 * x], a1 = alpha[2 * x + 1], b0 = beta[2 * y], b1 = beta[2 * y + 1];
+        const unsigned char* s0 = pixels + (long long)b * nstride + (long long)sy * stride + (long long)sx * CH;
+        const unsigned char* s1 = s0 + stride;
+        int v[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+        {
+            const int r0 = (s0[c] * a0 + s0[c + CH] * a1) >> 4;
+            const int r1 = (s1[c] * a0 + s1[c + CH] * a1) >> 4;
+            const int q = (((b0 * r0) >> 16) + ((b1 * r1) >> 16) + 2) >> 2;
+            v[c] = q < 0 ? 0 : (q > 255 ? 255 : q);
+        }
+        T* o = out + (long long)b * out_nstep + ((long long)y * w + x) * cpitch;
+#pragma unroll
+        for (int c = 0; c < CH; c++)
+        {
+            const int sc = (swap_rb && c < 3) ? 2 - c : c;
+            o[c] = from_f32<T>(((float)v[sc] - pa.mean[c]) * pa.norm[c]);
+        }
+        for (int c = CH; c < cpitch; c++) o[c] = from_f32<T>(0.f);
+    }
+}
+
+template<typename T>
+static int run_pixels_resize(const unsigned char* pixels, int ch, int stride, long long nstride, const int* tab, int swap_rb, const PixelAffine& pa, const ncnn_cuda_tensor* top,
+                             cudaStream_t stream)
+{
+    TView tv = make_view(top);
+    const int w = top->w, h = top->h;
+    const long long total = (long long)tv.n * h * w;
+    if (total == 0) return 0;
+    const int grid = grid_for(total, 256);
+    if (ch == 1)
+        NC_PDL_LAUNCH((pixels_resize_to_blob_kernel<T, 1>), grid, 256, 0, stream, pixels, stride, nstride, tab, w, h, swap_rb, pa, (T*)top->data, tv.cpitch, tv.nstep, tv.n);
+    else if (ch == 3)
+        NC_PDL_LAUNCH((pixels_resize_to_blob_kernel<T, 3>), grid, 256, 0, stream, pixels, stride, nstride, tab, w, h, swap_rb, pa, (T*)top->data, tv.cpitch, tv.nstep, tv.n);
+    else
+        NC_PDL_LAUNCH((pixels_resize_to_blob_kernel<T, 4>), grid, 256, 0, stream, pixels, stride, nstride, tab, w, h, swap_rb, pa, (T*)top->data, tv.cpitch, tv.nstep, tv.n);
+    NC_LAUNCH_CHECK();
+    return 0;
+}
+
+// round half away from zero, saturated to short: SATURATE_CAST_SHORT of src/mat_pixel_resize.cpp:619
+static int resize_coef(float v)
+{
+    int i = (int)(v + (v >= 0.f ? 0.5f : -0.5f));
+    return i < -32768 ? -32768 : (i > 32767 ? 32767 : i);
+}
+
+extern "C" {
+
+int ncnn_cuda_resize_tables_count(int w, int h)
+{
+    return 3 * (w + h);
+}
+
+// host-only: [xofs(w) | yofs(h) | a0,a1 per column (2w) | b0,b1 per row (2h)]; src/mat_pixel_resize.cpp:599-669
+int ncnn_cuda_resize_tables(int src_w, int src_h, int w, int h, int* tables)
+{
+    NC_REQUIRE(tables && src_w >= 2 && src_h >= 2 && w > 0 && h > 0, "resize_tables: the source must be at least 2 x 2");
+    const double scale_x = (double)src_w / w;
+    const double scale_y = (double)src_h / h;
+    int* xofs = tables;
+    int* yofs = tables + w;
+    int* alpha = tables + w + h;
+    int* beta = tables + w + h + 2 * w;
+    for (int dx = 0; dx < w; dx++)
+    {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)floor(fx);
+        fx -= sx;
+        if (sx < 0)
+        {
+            sx = 0;
+            fx = 0.f;
+        }
+        if (sx >= src_w - 1)
+        {
+            sx = src_w - 2;
+            fx = 1.f;
+        }
+        xofs[dx] = sx;
+        alpha[2 * dx] = resize_coef((1.f - fx) * 2048);
+        alpha[2 * dx + 1] = resize_coef(fx * 2048);
+    }
+    for (int dy = 0; dy < h; dy++)
+    {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floor(fy);
+        fy -= sy;
+        if (sy < 0)
+        {
+            sy = 0;
+            fy = 0.f;
+        }
+        if (sy >= src_h - 1)
+        {
+            sy = src_h - 2;
+            fy = 1.f;
+        }
+        yofs[dy] = sy;
+        beta[2 * dy] = resize_coef((1.f - fy) * 2048);
+        beta[2 * dy + 1] = resize_coef(fy * 2048);
+    }
+    return 0;
+}
+
+int ncnn_cuda_pixels_resize_to_blob(const unsigned char* pixels_dev, int channels, int src_w, int src_h, int stride, long long nstride, int swap_rb, const float* mean_vals,
+                                    const float* norm_vals, const int* tables_dev, const ncnn_cuda_tensor* top, void* stream)
+{
+    NC_REQUIRE(pixels_dev && tables_dev && top && top->dims == 3 && top->c == channels, "pixels_resize_to_blob: the top blob must be (target w, target h, channels)");
+    NC_REQUIRE(channels == 1 || channels == 3 || channels == 4, "pixels_resize_to_blob: 1, 3 or 4 interleaved channels");
+    NC_REQUIRE(src_w >= 2 && src_h >= 2 && stride >= src_w * channels, "pixels_resize_to_blob: bad source geometry");
+    PixelAffine pa;
+    for (int c = 0; c < 4; c++)
+    {
+        pa.mean[c] = (mean_vals && c < channels) ? mean_vals[c] : 0.f;
+        pa.norm[c] = (norm_vals && c < channels) ? norm_vals[c] : 1.f;
+    }
+    switch (top->elemtype)
+    {
+    case NCNN_CUDA_F32: return run_pixels_resize<float>(pixels_dev, channels, stride, nstride, tables_dev, swap_rb, pa, top, as_stream(stream));
+    case NCNN_CUDA_BF16: return run_pixels_resize<__nv_bfloat16>(pixels_dev, channels, stride, nstride, tables_dev, swap_rb, pa, top, as_stream(stream));
+    case NCNN_CUDA_F16: return run_pixels_resize<__half>(pixels_dev, channels, stride, nstride, tables_dev, swap_rb, pa, top, as_stream(stream));
+    }
+    return -1;
+}
+
+} // extern "C"
+
 extern "C" {
 
 int ncnn_cuda_pack_from_planar(const ncnn_cuda_hostmat* src, const ncnn_cuda_tensor* dst, void* stream)

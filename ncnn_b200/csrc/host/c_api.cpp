@@ -1023,6 +1023,11 @@ int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const uns
 {
     return ((Extractor*)ex)->input_pixels(name, pixels, type, w, h, stride, n, nstride, mean_vals, norm_vals);
 }
+int ncnn_extractor_input_pixels_resize(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
+                                       int target_w, int target_h, const float* mean_vals, const float* norm_vals)
+{
+    return ((Extractor*)ex)->input_pixels_resize(name, pixels, type, w, h, stride, n, nstride, target_w, target_h, mean_vals, norm_vals);
+}
 int ncnn_extractor_extract_yolov8_proposals(ncnn_extractor_t ex, const char* name, const int* strides, int num_strides, int in_w, int in_h, float prob_threshold,
                                             ncnn_mat_t* proposals)
 {

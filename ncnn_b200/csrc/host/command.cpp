@@ -178,9 +178,12 @@ int CudaCompute::record_upload(const Mat& src, CudaMat& dst, const Option& opt)
 
 // pixel type codes of the reference (src/mat.h:213-262): PIXEL_RGB 1, BGR 2, GRAY 3, RGBA 4, BGRA 5; conversion = from | (to << 16)
 int CudaCompute::record_upload_pixels(const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals, const float* norm_vals,
-                                      CudaMat& dst, const Option& opt)
+                                      CudaMat& dst, const Option& opt, int target_w, int target_h)
 {
     if (!pixels || w <= 0 || h <= 0 || n <= 0) return -100;
+    // Mat::from_pixels_resize (src/mat_pixel.cpp:2546-2549): an equal target size is a plain from_pixels
+    const bool resize = target_w > 0 && target_h > 0 && (target_w != w || target_h != h);
+    if (resize && (w < 2 || h < 2)) return -1;
     const int from = type & 0xffff, to = (type >> 16) & 0xffff;
     int channels;
     switch (from)
@@ -223,11 +226,37 @@ int CudaCompute::record_upload_pixels(const unsigned char* pixels, int type, int
     int ret = ncnn_cuda_memcpy_h2d_async(raw.data, hsrc, bytes, st);
     if (ret != 0) return ret;
     h2d_bytes += bytes;
-    dst.create_dims(3, w, h, 1, channels, opt.cuda_elemtype(), n, blob_allocator(opt));
+    if (!resize)
+    {
+        dst.create_dims(3, w, h, 1, channels, opt.cuda_elemtype(), n, blob_allocator(opt));
+        if (dst.empty()) return -100;
+        ncnn_cuda_tensor t = dst.view();
+        ret = ncnn_cuda_pixels_to_blob((const unsigned char*)raw.data, channels, w, h, stride, (long long)nstride, swap_rb, mean_vals, norm_vals, &t, st);
+        keep_alive_.push_back(raw);
+        return ret;
+    }
+    // the reference's bilinear resize on the device: its offset / coefficient tables are computed here on the host
+    // (a few KB), staged through pinned memory and read by the kernel
+    const int count = ncnn_cuda_resize_tables_count(target_w, target_h);
+    const size_t tbytes = (size_t)count * sizeof(int);
+    Allocator* sa = ctx_->staging_allocator;
+    int* tab_host = (int*)sa->fastMalloc(tbytes);
+    if (!tab_host) return -100;
+    staging_in_flight_.push_back(tab_host);
+    ret = ncnn_cuda_resize_tables(w, h, target_w, target_h, tab_host);
+    if (ret != 0) return ret;
+    CudaMat tab;
+    tab.create(count, NCNN_CUDA_F32, 1, workspace_allocator(opt));
+    if (tab.empty()) return -100;
+    ret = ncnn_cuda_memcpy_h2d_async(tab.data, tab_host, tbytes, st);
+    if (ret != 0) return ret;
+    h2d_bytes += tbytes;
+    dst.create_dims(3, target_w, target_h, 1, channels, opt.cuda_elemtype(), n, blob_allocator(opt));
     if (dst.empty()) return -100;
     ncnn_cuda_tensor t = dst.view();
-    ret = ncnn_cuda_pixels_to_blob((const unsigned char*)raw.data, channels, w, h, stride, (long long)nstride, swap_rb, mean_vals, norm_vals, &t, st);
+    ret = ncnn_cuda_pixels_resize_to_blob((const unsigned char*)raw.data, channels, w, h, stride, (long long)nstride, swap_rb, mean_vals, norm_vals, (const int*)tab.data, &t, st);
     keep_alive_.push_back(raw);
+    keep_alive_.push_back(tab);
     return ret;
 }
 

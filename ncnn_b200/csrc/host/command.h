@@ -60,7 +60,7 @@ public:
     // interleaved 8-bit pixels (Mat::from_pixels types PIXEL_RGB/BGR/GRAY/RGBA/BGRA and the RGB<->BGR conversions) -> device blob with
     // (pixel - mean) * norm fused; the raw bytes are what crosses PCIe
     int record_upload_pixels(const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals, const float* norm_vals,
-                             CudaMat& dst, const Option& opt);
+                             CudaMat& dst, const Option& opt, int target_w = 0, int target_h = 0);
     // device blob -> host planar fp32 Mat; dst is valid after submit_and_wait()
     int record_download(const CudaMat& src, Mat& dst, const Option& opt);
     // deep copy on the device

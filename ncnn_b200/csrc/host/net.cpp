@@ -980,6 +980,7 @@ public:
         int blob_index;
         const unsigned char* pixels;
         int type, w, h, stride, n;
+        int target_w, target_h; // 0: no resize
         size_t nstride;
         bool has_mean, has_norm;
         float mean_vals[4], norm_vals[4];
@@ -1081,6 +1082,12 @@ int Extractor::input(int blob_index, const CudaMat& in)
 int Extractor::input_pixels(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals,
                             const float* norm_vals)
 {
+    return input_pixels_resize(blob_name, pixels, type, w, h, stride, n, nstride, 0, 0, mean_vals, norm_vals);
+}
+
+int Extractor::input_pixels_resize(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, int target_w, int target_h,
+                                   const float* mean_vals, const float* norm_vals)
+{
     int blob_index = d->net->find_blob_index_by_name(blob_name);
     if (blob_index == -1 || !pixels) return -1;
     ExtractorPrivate::PixelInput pi;
@@ -1090,6 +1097,8 @@ int Extractor::input_pixels(const char* blob_name, const unsigned char* pixels, 
     pi.w = w;
     pi.h = h;
     pi.stride = stride;
+    pi.target_w = target_w;
+    pi.target_h = target_h;
     pi.n = n < 1 ? 1 : n;
     pi.nstride = nstride;
     pi.has_mean = mean_vals != 0;
@@ -1183,7 +1192,7 @@ int Extractor::extract(int blob_index, CudaMat& feat, CudaCompute& cmd)
     {
         const ExtractorPrivate::PixelInput& pi = d->pixel_inputs[i];
         ret = cmd.record_upload_pixels(pi.pixels, pi.type, pi.w, pi.h, pi.stride, pi.n, pi.nstride, pi.has_mean ? pi.mean_vals : 0, pi.has_norm ? pi.norm_vals : 0,
-                                       d->blob_mats_gpu[pi.blob_index], d->opt);
+                                       d->blob_mats_gpu[pi.blob_index], d->opt, pi.target_w, pi.target_h);
         if (ret != 0) return ret;
     }
     d->pixel_inputs.clear();

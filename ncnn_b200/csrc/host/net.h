@@ -111,6 +111,10 @@ public:
     // until extract() returns (it is read by the upload, like a Mat view).
     int input_pixels(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, const float* mean_vals,
                      const float* norm_vals);
+    // the same with Mat::from_pixels_resize (src/mat_pixel.cpp:2546-2578): every image is resized to target_w x target_h by the
+    // reference's 8-bit bilinear resize, on the device, before the conversion
+    int input_pixels_resize(const char* blob_name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride, int target_w, int target_h,
+                            const float* mean_vals, const float* norm_vals);
 
     // device post-processing: forward to the YOLOv8 prediction blob, decode it on the device
     // (examples/yolov8.cpp:160-273 generate_proposals) and download one {x, y, w, h, prob, label} row per anchor

@@ -204,3 +204,36 @@ def test_to_pixels_matches_reference(ours, ref):
             res.append(buf)
         assert np.array_equal(res[0], res[1]), ("to_pixels", a, b)
         assert (res[0][:, w * chans[b]:] == 171).all()  # the stride padding is left alone
+
+
+def test_resize_tables_reproduce_reference_resize(ref):
+    """ncnn_cuda_resize_tables (host code of the product, no device work) + the integer formula the device kernel evaluates per
+    output pixel (csrc/cuda/layout.cu pixels_resize_to_blob_kernel, restated here in numpy) reproduce the reference's
+    ncnn_mat_from_pixels_resize bit for bit: 1 / 3 / 4 channels, up- and down-scaling, odd sizes, the 2 x 2 minimum, a row stride"""
+    import cabi
+    L = C.CDLL(cabi.LIB_PATH)
+    R = ref.lib
+    R.ncnn_mat_from_pixels_resize.restype = C.c_void_p
+    R.ncnn_mat_from_pixels_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for (ch, typ) in [(3, 1), (1, 3), (4, 4)]:
+        for (sw, sh, w, h) in [(37, 23, 16, 16), (16, 16, 37, 23), (64, 48, 224, 224), (301, 199, 224, 224), (2, 2, 5, 7), (50, 50, 49, 51), (640, 360, 320, 192)]:
+            stride = sw * ch + 3
+            img = rng.integers(0, 256, (sh, stride), dtype=np.uint8)
+            m = R.ncnn_mat_from_pixels_resize(img.ctypes.data_as(C.c_void_p), typ, sw, sh, stride, w, h, None)
+            want = ref.mat_to_numpy(C.c_void_p(m)).copy()
+            R.ncnn_mat_destroy(C.c_void_p(m))
+            assert L.ncnn_cuda_resize_tables_count(w, h) == 3 * (w + h)
+            tab = (C.c_int * (3 * (w + h)))()
+            assert L.ncnn_cuda_resize_tables(sw, sh, w, h, tab) == 0
+            t = np.frombuffer(tab, np.int32).astype(np.int64)
+            xofs, yofs, al, be = t[:w], t[w:w + h], t[w + h:w + h + 2 * w].reshape(w, 2), t[w + h + 2 * w:].reshape(h, 2)
+            src = img[:, :sw * ch].reshape(sh, sw, ch).astype(np.int64)
+            got = np.zeros((ch, h, w), np.float32)
+            for c in range(ch):
+                S = src[:, :, c]
+                r = (S[:, xofs] * al[:, 0] + S[:, xofs + 1] * al[:, 1]) >> 4
+                q = (((be[:, 0:1] * r[yofs]) >> 16) + ((be[:, 1:2] * r[yofs + 1]) >> 16) + 2) >> 2
+                got[c] = np.clip(q, 0, 255)
+            assert np.array_equal(got, want), (ch, sw, sh, w, h)
+    assert L.ncnn_cuda_resize_tables(1, 5, 4, 4, tab) != 0  # the reference reads column sx + 1: a 1-pixel-wide source has none

@@ -391,6 +391,69 @@ def test_device_preprocessing_pixels(ref, mode):
         L.lib.ncnn_option_destroy(opt)
 
 
+def reference_preprocess_resize(ref, pixels, pixel_type, tw, th, mean_vals, norm_vals):
+    """ncnn_mat_from_pixels_resize (src/c_api.h:177) + ncnn_mat_substract_mean_normalize per image -> (n, c, th, tw) float32"""
+    import ctypes as C
+    L = ref.lib
+    L.ncnn_mat_from_pixels_resize.restype = C.c_void_p
+    L.ncnn_mat_from_pixels_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.ncnn_mat_substract_mean_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    out = []
+    for img in pixels:
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        m = L.ncnn_mat_from_pixels_resize(img.ctypes.data_as(C.c_void_p), pixel_type, w, h, w * ch, tw, th, None)
+        mean = np.asarray(mean_vals, np.float32) if mean_vals is not None else None
+        norm = np.asarray(norm_vals, np.float32) if norm_vals is not None else None
+        L.ncnn_mat_substract_mean_normalize(C.c_void_p(m), mean.ctypes.data_as(C.c_void_p) if mean is not None else None,
+                                            norm.ctypes.data_as(C.c_void_p) if norm is not None else None)
+        out.append(ref.mat_to_numpy(C.c_void_p(m)))
+        L.ncnn_mat_destroy(C.c_void_p(m))
+    return np.stack(out)
+
+
+RESIZE_PARAM = """7767517
+3 3
+Input        data  0 1 data
+Convolution  conv  1 1 data conv 0=8 1=3 3=2 4=1 5=1 6=%d 9=1
+Pooling      gap   1 1 conv gap 0=1 4=1
+"""
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_device_preprocessing_pixels_resize(ref, mode):
+    """Extractor.input_pixels_resize -- the reference's 8-bit bilinear resize (src/mat_pixel_resize.cpp) + from_pixels
+    + substract_mean_normalize in one device kernel -- against ncnn_mat_from_pixels_resize of the reference: up- and down-scaling,
+    odd sizes, 1 / 3 / 4 channels, RGB<->BGR.  With integer arithmetic on both sides the fp32 blob must be exact."""
+    from ncnn_b200 import capi
+    L = product()
+    rng = np.random.default_rng(31)
+    opt = L.make_option(1, **MODES[mode])
+    try:
+        for (ptype, ch, sw, sh, tw, th, mean, norm) in [(PIXEL_BGR, 3, 301, 199, 224, 224, [104.0, 117.0, 123.0], [0.017, 0.0175, 0.0171]),
+                                                        (PIXEL_RGB2BGR, 3, 64, 48, 224, 160, [123.7, 116.3, 103.5], None),
+                                                        (PIXEL_GRAY, 1, 37, 23, 16, 16, None, [1 / 255.0]),
+                                                        (PIXEL_RGBA, 4, 50, 50, 49, 51, None, None),
+                                                        (PIXEL_RGB, 3, 640, 360, 320, 192, None, [1 / 255.0] * 3),
+                                                        (PIXEL_RGB, 3, 32, 32, 32, 32, [1.0, 2.0, 3.0], None)]:
+            text = RESIZE_PARAM % (8 * ch * 9)
+            weights = modelzoo.random_model_bytes(text, seed=5)
+            net = capi.Net(L, text, weights, opt)
+            try:
+                pixels = rng.integers(0, 256, (3, sh, sw, ch), dtype=np.uint8)
+                x = reference_preprocess_resize(ref, pixels, ptype, tw, th, mean, norm)
+                got = net.run_pixels("data", pixels, ptype, mean, norm, outputs=["data", "gap"], resize=(tw, th))
+                assert got["data"].shape == x.shape, (got["data"].shape, x.shape)
+                e_in = nerr(got["data"], x)
+                assert e_in <= (1e-6 if mode == "fp32" else 2.0 ** -8), (ptype, sw, sh, tw, th, e_in)
+                want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=["gap"])["gap"]
+                assert nerr(got["gap"], want) <= TOL[mode], (ptype, nerr(got["gap"], want))
+            finally:
+                net.close()
+    finally:
+        L.lib.ncnn_option_destroy(opt)
+
+
 def test_yolov8_device_decode(ref):
     """ncnn_extractor_extract_yolov8_proposals (forward + decode on the device, 6 floats per anchor come
     back) against the restated examples/yolov8.cpp generate_proposals applied to the REFERENCE's out0 blob, then the same
