@@ -215,6 +215,23 @@ void ncnn_mat_to_pixels(const ncnn_mat_t mat, unsigned char* pixels, int type, i
 {
     ((const Mat*)mat)->to_pixels(pixels, type, stride);
 }
+ncnn_mat_t ncnn_mat_from_pixels_resize(const unsigned char* pixels, int type, int w, int h, int stride, int target_width, int target_height, ncnn_allocator_t allocator)
+{
+    return (ncnn_mat_t)(new Mat(Mat::from_pixels_resize(pixels, type, w, h, stride, target_width, target_height, alloc_of(allocator))));
+}
+ncnn_mat_t ncnn_mat_from_pixels_roi(const unsigned char* pixels, int type, int w, int h, int stride, int roix, int roiy, int roiw, int roih, ncnn_allocator_t allocator)
+{
+    return (ncnn_mat_t)(new Mat(Mat::from_pixels_roi(pixels, type, w, h, stride, roix, roiy, roiw, roih, alloc_of(allocator))));
+}
+ncnn_mat_t ncnn_mat_from_pixels_roi_resize(const unsigned char* pixels, int type, int w, int h, int stride, int roix, int roiy, int roiw, int roih, int target_width,
+                                           int target_height, ncnn_allocator_t allocator)
+{
+    return (ncnn_mat_t)(new Mat(Mat::from_pixels_roi_resize(pixels, type, w, h, stride, roix, roiy, roiw, roih, target_width, target_height, alloc_of(allocator))));
+}
+void ncnn_mat_to_pixels_resize(const ncnn_mat_t mat, unsigned char* pixels, int type, int target_width, int target_height, int target_stride)
+{
+    ((const Mat*)mat)->to_pixels_resize(pixels, type, target_width, target_height, target_stride);
+}
 void ncnn_mat_fill_float(ncnn_mat_t mat, float v)
 {
     ((Mat*)mat)->fill(v);

@@ -1,6 +1,8 @@
 // mat.cpp -- see mat.h
 #include "mat.h"
 
+#include <vector>
+
 namespace ncnn {
 
 Mat::Mat()
@@ -364,6 +366,114 @@ void Mat::to_pixels(unsigned char* pixels, int type, int stride) const
             }
         }
     }
+}
+
+// resize_bilinear_c1/c3/c4 of the reference (src/mat_pixel_resize.cpp:210-1039) on the host: the same offset / coefficient tables
+// the device kernel uses (ncnn_cuda_resize_tables, computed as :599-669) and the same integer formula per output byte.
+static int resize_bilinear_u8(const unsigned char* src, int ch, int srcw, int srch, int srcstride, unsigned char* dst, int w, int h, int stride)
+{
+    std::vector<int> tab((size_t)ncnn_cuda_resize_tables_count(w, h));
+    int ret = ncnn_cuda_resize_tables(srcw, srch, w, h, tab.data());
+    if (ret != 0) return ret;
+    const int* xofs = tab.data();
+    const int* yofs = xofs + w;
+    const int* alpha = yofs + h;
+    const int* beta = alpha + 2 * w;
+    std::vector<short> rows0((size_t)w * ch), rows1((size_t)w * ch);
+    int prev_sy = -2;
+    for (int y = 0; y < h; y++)
+    {
+        const int sy = yofs[y];
+        if (sy != prev_sy)
+        {
+            const unsigned char* s0 = src + (size_t)sy * srcstride;
+            const unsigned char* s1 = s0 + srcstride;
+            for (int x = 0; x < w; x++)
+            {
+                const int a0 = alpha[2 * x], a1 = alpha[2 * x + 1];
+                const unsigned char* p0 = s0 + xofs[x] * ch;
+                const unsigned char* p1 = s1 + xofs[x] * ch;
+                for (int c = 0; c < ch; c++)
+                {
+                    rows0[(size_t)x * ch + c] = (short)((p0[c] * a0 + p0[c + ch] * a1) >> 4);
+                    rows1[(size_t)x * ch + c] = (short)((p1[c] * a0 + p1[c + ch] * a1) >> 4);
+                }
+            }
+            prev_sy = sy;
+        }
+        const int b0 = beta[2 * y], b1 = beta[2 * y + 1];
+        unsigned char* d = dst + (size_t)y * stride;
+        for (int i = 0; i < w * ch; i++)
+        {
+            int q = (((b0 * rows0[i]) >> 16) + ((b1 * rows1[i]) >> 16) + 2) >> 2;
+            d[i] = (unsigned char)(q < 0 ? 0 : (q > 255 ? 255 : q));
+        }
+    }
+    return 0;
+}
+
+static int pixel_channels(int fmt)
+{
+    return fmt == 3 ? 1 : (fmt == 4 || fmt == 5 ? 4 : (fmt == 1 || fmt == 2 ? 3 : 0));
+}
+
+// src/mat_pixel.cpp:2546-2578
+Mat Mat::from_pixels_resize(const unsigned char* pixels, int type, int w, int h, int stride, int target_width, int target_height, Allocator* allocator)
+{
+    if (w == target_width && h == target_height) return from_pixels(pixels, type, w, h, stride, allocator);
+    const int ch = pixel_channels(type & 0xffff);
+    if (!pixels || ch == 0 || target_width <= 0 || target_height <= 0)
+    {
+        NCNN_LOGE("unknown convert type %d", type);
+        return Mat();
+    }
+    if (stride <= 0) stride = w * ch;
+    std::vector<unsigned char> resized((size_t)target_width * target_height * ch);
+    if (resize_bilinear_u8(pixels, ch, w, h, stride, resized.data(), target_width, target_height, target_width * ch) != 0) return Mat();
+    return from_pixels(resized.data(), type, target_width, target_height, target_width * ch, allocator);
+}
+
+// src/mat_pixel.cpp:2608-2632
+Mat Mat::from_pixels_roi(const unsigned char* pixels, int type, int w, int h, int stride, int roix, int roiy, int roiw, int roih, Allocator* allocator)
+{
+    const int ch = pixel_channels(type & 0xffff);
+    if (roix < 0 || roiy < 0 || roiw <= 0 || roih <= 0 || roix + roiw > w || roiy + roih > h)
+    {
+        NCNN_LOGE("roi %d %d %d %d out of image %d %d", roix, roiy, roiw, roih, w, h);
+        return Mat();
+    }
+    if (ch == 0) return Mat();
+    if (stride <= 0) stride = w * ch;
+    return from_pixels(pixels + (size_t)roiy * stride + (size_t)roix * ch, type, roiw, roih, stride, allocator);
+}
+
+// src/mat_pixel.cpp:2664-2690
+Mat Mat::from_pixels_roi_resize(const unsigned char* pixels, int type, int w, int h, int stride, int roix, int roiy, int roiw, int roih, int target_width, int target_height,
+                                Allocator* allocator)
+{
+    const int ch = pixel_channels(type & 0xffff);
+    if (roix < 0 || roiy < 0 || roiw <= 0 || roih <= 0 || roix + roiw > w || roiy + roih > h)
+    {
+        NCNN_LOGE("roi %d %d %d %d out of image %d %d", roix, roiy, roiw, roih, w, h);
+        return Mat();
+    }
+    if (ch == 0) return Mat();
+    if (stride <= 0) stride = w * ch;
+    return from_pixels_resize(pixels + (size_t)roiy * stride + (size_t)roix * ch, type, roiw, roih, stride, target_width, target_height, allocator);
+}
+
+// src/mat_pixel.cpp:2773-2806 (an equal target size writes tightly packed rows, as the reference does)
+void Mat::to_pixels_resize(unsigned char* pixels, int type, int target_width, int target_height, int target_stride) const
+{
+    if (w == target_width && h == target_height) return to_pixels(pixels, type);
+    int to = (type >> 16) & 0xffff;
+    if (to == 0) to = type & 0xffff;
+    const int ch = pixel_channels(to);
+    if (empty() || !pixels || ch == 0 || target_width <= 0 || target_height <= 0) return;
+    if (target_stride <= 0) target_stride = target_width * ch;
+    std::vector<unsigned char> full((size_t)w * h * ch);
+    to_pixels(full.data(), type, w * ch);
+    resize_bilinear_u8(full.data(), ch, w, h, w * ch, pixels, target_width, target_height, target_stride);
 }
 
 // Mat::substract_mean_normalize (src/mat.cpp): (x - mean[c]) * norm[c]; either array may be NULL

@@ -46,6 +46,13 @@ public:
     void substract_mean_normalize(const float* mean_vals, const float* norm_vals);
     // src/mat_pixel.cpp:2692-2753; stride 0 = w * channels of the target type
     void to_pixels(unsigned char* pixels, int type, int stride = 0) const;
+    // src/mat_pixel.cpp:2546-2690: the resize / roi forms (resize = the reference's 8-bit bilinear, bit-exact)
+    static Mat from_pixels_resize(const unsigned char* pixels, int type, int w, int h, int stride, int target_width, int target_height, Allocator* allocator = 0);
+    static Mat from_pixels_roi(const unsigned char* pixels, int type, int w, int h, int stride, int roix, int roiy, int roiw, int roih, Allocator* allocator = 0);
+    static Mat from_pixels_roi_resize(const unsigned char* pixels, int type, int w, int h, int stride, int roix, int roiy, int roiw, int roih, int target_width,
+                                      int target_height, Allocator* allocator = 0);
+    // src/mat_pixel.cpp:2773-2806
+    void to_pixels_resize(unsigned char* pixels, int type, int target_width, int target_height, int target_stride = 0) const;
     void clone_from(const Mat& mat, Allocator* allocator = 0);
     Mat reshape(int w, Allocator* allocator = 0) const;
     Mat reshape(int w, int h, Allocator* allocator = 0) const;

@@ -237,3 +237,59 @@ def test_resize_tables_reproduce_reference_resize(ref):
                 got[c] = np.clip(q, 0, 255)
             assert np.array_equal(got, want), (ch, sw, sh, w, h)
     assert L.ncnn_cuda_resize_tables(1, 5, 4, 4, tab) != 0  # the reference reads column sx + 1: a 1-pixel-wide source has none
+
+
+def test_pixels_resize_and_roi_match_reference(ours, ref):
+    """host pre/post-processing with the reference's 8-bit bilinear resize: ncnn_mat_from_pixels_resize / _roi / _roi_resize and
+    ncnn_mat_to_pixels_resize (src/mat_pixel.cpp:2546-2806), bit-exact against the reference: several conversions, up- and
+    down-scaling, row strides, and the equal-size shortcut"""
+    rng = np.random.default_rng(37)
+    RGB, BGR, GRAY, RGBA, BGRA = 1, 2, 3, 4, 5
+    chans = {RGB: 3, BGR: 3, GRAY: 1, RGBA: 4, BGRA: 4}
+    vp, ci = C.c_void_p, C.c_int
+    for api in (ours, ref):
+        l = api.lib
+        l.ncnn_mat_from_pixels_resize.restype = vp
+        l.ncnn_mat_from_pixels_resize.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp]
+        l.ncnn_mat_from_pixels_roi.restype = vp
+        l.ncnn_mat_from_pixels_roi.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        l.ncnn_mat_from_pixels_roi_resize.restype = vp
+        l.ncnn_mat_from_pixels_roi_resize.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        l.ncnn_mat_to_pixels_resize.restype = None
+        l.ncnn_mat_to_pixels_resize.argtypes = [vp, vp, ci, ci, ci, ci]
+
+    def both(fn):
+        out = []
+        for api in (ours, ref):
+            m = fn(api.lib)
+            out.append(api.mat_to_numpy(vp(m)).copy())
+            api.lib.ncnn_mat_destroy(vp(m))
+        return out
+
+    for (a, b) in [(RGB, RGB), (BGR, RGB), (RGB, GRAY), (GRAY, GRAY), (GRAY, BGR), (RGBA, RGBA), (RGBA, BGR), (BGRA, GRAY), (RGB, BGRA)]:
+        ch = chans[a]
+        t = a if a == b else (a | (b << 16))
+        for (w, h, tw, th) in [(41, 29, 24, 24), (24, 24, 41, 29), (33, 33, 33, 33), (160, 90, 64, 64)]:
+            stride = w * ch + 6
+            buf = rng.integers(0, 256, (h, stride), dtype=np.uint8)
+            p = buf.ctypes.data_as(vp)
+            g, r = both(lambda l: l.ncnn_mat_from_pixels_resize(p, t, w, h, stride, tw, th, None))
+            assert g.shape == r.shape == (chans[b], th, tw) and np.array_equal(g, r), ("from_pixels_resize", a, b, w, h, tw, th)
+            rx, ry, rw, rh = 3, 2, w - 7, h - 5
+            g, r = both(lambda l: l.ncnn_mat_from_pixels_roi(p, t, w, h, stride, rx, ry, rw, rh, None))
+            assert g.shape == r.shape == (chans[b], rh, rw) and np.array_equal(g, r), ("from_pixels_roi", a, b)
+            g, r = both(lambda l: l.ncnn_mat_from_pixels_roi_resize(p, t, w, h, stride, rx, ry, rw, rh, tw, th, None))
+            assert g.shape == r.shape == (chans[b], th, tw) and np.array_equal(g, r), ("from_pixels_roi_resize", a, b)
+    for (a, b) in [(RGB, RGB), (GRAY, GRAY), (RGBA, RGBA), (RGB, BGR), (BGR, RGBA), (GRAY, BGRA), (RGBA, BGRA)]:
+        t = a if a == b else (a | (b << 16))
+        for (w, h, tw, th) in [(31, 17, 20, 20), (20, 20, 31, 17), (19, 19, 19, 19)]:
+            x = rng.uniform(-30.0, 290.0, (chans[a], h, w)).astype(np.float32)
+            stride = tw * chans[b] + (0 if (w, h) == (tw, th) else 5)  # the equal-size shortcut of the reference writes tight rows
+            res = []
+            for api in (ours, ref):
+                m = api.mat_from_numpy(x)
+                out = np.full((th, stride), 93, np.uint8)
+                api.lib.ncnn_mat_to_pixels_resize(m, out.ctypes.data_as(vp), t, tw, th, stride)
+                api.lib.ncnn_mat_destroy(m)
+                res.append(out)
+            assert np.array_equal(res[0], res[1]), ("to_pixels_resize", a, b, w, h, tw, th)
