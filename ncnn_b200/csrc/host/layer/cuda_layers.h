@@ -284,6 +284,23 @@ public:
     float alpha, beta, bias;
 };
 
+// src/layer/multiheadattention.cpp -- self / cross attention without mask, kv cache or quantised weights
+class MultiHeadAttention : public Layer
+{
+public:
+    MultiHeadAttention();
+    virtual ~MultiHeadAttention();
+    virtual int load_param(const ParamDict& pd);
+    virtual int load_model(const ModelBin& mb);
+    virtual int create_pipeline(const Option& opt);
+    virtual int destroy_pipeline(const Option& opt);
+    virtual int forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat>& top_blobs, CudaCompute& cmd, const Option& opt) const;
+    int embed_dim, num_heads, weight_data_size, kdim, vdim, attn_mask, kv_cache;
+    float scale;
+    Mat q_weight_data, q_bias_data, k_weight_data, k_bias_data, v_weight_data, v_bias_data, out_weight_data, out_bias_data;
+    ncnn_cuda_linear_t q_fc, k_fc, v_fc, o_fc;
+};
+
 // src/layer/layernorm.cpp
 class LayerNorm : public Layer
 {

@@ -43,6 +43,7 @@ DEFINE_LAYER_CREATOR(Noop)
 DEFINE_LAYER_CREATOR(Crop)
 DEFINE_LAYER_CREATOR(Reduction)
 DEFINE_LAYER_CREATOR(LayerNorm)
+DEFINE_LAYER_CREATOR(MultiHeadAttention)
 DEFINE_LAYER_CREATOR(GELU)
 DEFINE_LAYER_CREATOR(MemoryData)
 DEFINE_LAYER_CREATOR(Deconvolution)
@@ -83,6 +84,7 @@ static const layer_registry_entry cuda_layer_registry[] = {
     {"Crop", Crop_layer_creator},
     {"Reduction", Reduction_layer_creator},
     {"LayerNorm", LayerNorm_layer_creator},
+    {"MultiHeadAttention", MultiHeadAttention_layer_creator},
     {"GELU", GELU_layer_creator},
     {"MemoryData", MemoryData_layer_creator},
     {"Deconvolution", Deconvolution_layer_creator},

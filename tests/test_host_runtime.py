@@ -17,7 +17,7 @@ import pytest
 from netutil import modelzoo
 
 HOT_PATH_LAYERS = ["Convolution", "ConvolutionDepthWise", "Pooling", "InnerProduct", "Gemm", "ReLU", "Eltwise", "BinaryOp", "Concat", "Split", "Softmax",
-                   "Interp", "Swish", "Sigmoid", "Slice", "Reshape", "Permute", "Flatten", "Dropout", "Input", "Padding", "BatchNorm", "Scale", "ShuffleChannel", "LRN", "Noop", "Crop", "Deconvolution", "DeconvolutionDepthWise", "Reduction", "MemoryData", "LayerNorm", "GELU"]
+                   "Interp", "Swish", "Sigmoid", "Slice", "Reshape", "Permute", "Flatten", "Dropout", "Input", "Padding", "BatchNorm", "Scale", "ShuffleChannel", "LRN", "Noop", "Crop", "Deconvolution", "DeconvolutionDepthWise", "Reduction", "MemoryData", "LayerNorm", "GELU", "MultiHeadAttention"]
 
 
 @pytest.fixture(scope="module")

@@ -294,6 +294,33 @@ def test_layernorm_gelu_memorydata_reduction_graph(ref, mode):
         assert nerr(got[o], want[o]) <= TOL[mode], (o, nerr(got[o], want[o]))
 
 
+MHA_PARAM = """7767517
+5 6
+Input               q      0 1 q
+Input               kv     0 1 kv
+Split               skv    1 2 kv kv0 kv1
+MultiHeadAttention  self   1 1 q a0 0=32 1=4 2=768 3=24 4=24
+MultiHeadAttention  cross  3 1 a0 kv0 kv1 out 0=16 1=2 2=384 3=20 4=20
+"""
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_multiheadattention_graph(ref, mode):
+    """MultiHeadAttention, self-attention (one bottom, qdim != embed_dim) feeding cross-attention (q, k, v bottoms, kdim = vdim
+    != qdim, odd sequence lengths), batched, through the Net API against the reference CPU path"""
+    text = MHA_PARAM
+    weights = modelzoo.random_model_bytes(text, seed=23)
+    rng = np.random.default_rng(8)
+    q = rng.uniform(-1, 1, (3, 7, 24)).astype(np.float32)
+    kv = rng.uniform(-1, 1, (3, 11, 20)).astype(np.float32)
+    outs = ["a0", "out"]
+    want = run_ref(ref, text, weights, {"q": q, "kv": kv}, batched=True, outputs=outs)
+    got = run_ours(text, weights, {"q": q, "kv": kv}, mode, batched=True, outputs=outs)
+    for o in outs:
+        assert got[o].shape == want[o].shape == (3, 7, 24), (o, got[o].shape, want[o].shape)
+        assert nerr(got[o], want[o]) <= TOL[mode], (o, nerr(got[o], want[o]))
+
+
 EXTRA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
 EXTRA_MODELS = ["mobilenet", "mobilenet_v3", "shufflenet", "shufflenet_v2", "mnasnet", "proxylessnasnet", "efficientnet_b0", "regnety_400m", "resnet18",
                 "squeezenet", "blazeface", "FastestDet", "alexnet", "googlenet", "nanodet_m", "yolo-fastestv2", "efficientnetv2_b0"]

@@ -394,6 +394,15 @@ def random_model_bytes(text, seed=7767517, bias_scale=0.1, dtype=np.float32):
             chunks.append(rng.uniform(0.5, 1.5, c).astype(np.float32).tobytes())
             if p.get(1, 0):
                 chunks.append(rng.uniform(-0.2, 0.2, c).astype(np.float32).tobytes())
+        elif t == "MultiHeadAttention":
+            # src/layer/multiheadattention.cpp:191-238: q, k, v, out weights (tagged) each followed by its bias (raw)
+            embed, wsize = p[0], p[2]
+            qdim, kdim, vdim = wsize // embed, p.get(3, embed), p.get(4, embed)
+            for (rows, cols) in [(embed, qdim), (embed, kdim), (embed, vdim), (qdim, embed)]:
+                a = np.sqrt(3.0 / cols)
+                chunks.append(np.zeros(1, np.uint32).tobytes())
+                chunks.append(rng.uniform(-a, a, rows * cols).astype(np.float32).tobytes())
+                chunks.append(rng.uniform(-bias_scale, bias_scale, rows).astype(np.float32).tobytes())
         elif t == "LayerNorm":
             # src/layer/layernorm.cpp:23-36: gamma, beta raw fp32 when affine (id 2, default 1)
             if p.get(2, 1):
