@@ -457,6 +457,9 @@ static int run_axis_copy(const ncnn_cuda_tensor* small_t, const ncnn_cuda_tensor
     a.offset = offset;
     a.to_big = to_big;
     int n = big_t->n < 1 ? 1 : big_t->n;
+    // concat of an unbatched blob into a batched one: every sample reads the same source
+    if (to_big && small_t->n <= 1 && n > 1) a.s_nstep = 0;
+    NC_REQUIRE(to_big ? (small_t->n <= 1 || small_t->n == n) : ((small_t->n < 1 ? 1 : small_t->n) == n), "concat/slice: batch mismatch");
     const bool chan_ok = (a.axis_kind != 0) || (offset % VEC == 0);
     // vector path: whole 16-byte channel groups, writing pad lanes of the destination is harmless only when the
     // destination's lanes [q, q+VEC) all belong to this copy: require sc % VEC == 0 unless it is the last slab

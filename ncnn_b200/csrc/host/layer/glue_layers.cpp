@@ -302,7 +302,13 @@ int Concat::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMa
     int w = b0.w, h = b0.h, d = b0.d, c = b0.c;
     set_axis_extent(dims, positive_axis, total, w, h, d, c);
     CudaMat& top = top_blobs[0];
-    top.create_dims(dims, w, h, d, c, b0.elemtype, b0.n, cmd.blob_allocator(opt));
+    // an unbatched bottom (a MemoryData constant such as a transformer's class token) is repeated for every sample of the batch
+    int batch = b0.n;
+    for (size_t i = 1; i < bottom_blobs.size(); i++)
+        if (bottom_blobs[i].n > batch) batch = bottom_blobs[i].n;
+    for (size_t i = 0; i < bottom_blobs.size(); i++)
+        if (bottom_blobs[i].n != batch && bottom_blobs[i].n > 1) return -1;
+    top.create_dims(dims, w, h, d, c, b0.elemtype, batch, cmd.blob_allocator(opt));
     if (top.empty()) return -100;
     ncnn_cuda_tensor t = top.view();
     int offset = 0;

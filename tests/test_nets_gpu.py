@@ -323,8 +323,8 @@ def test_multiheadattention_graph(ref, mode):
 
 EXTRA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
 EXTRA_MODELS = ["mobilenet", "mobilenet_v3", "shufflenet", "shufflenet_v2", "mnasnet", "proxylessnasnet", "efficientnet_b0", "regnety_400m", "resnet18",
-                "squeezenet", "blazeface", "FastestDet", "alexnet", "googlenet", "nanodet_m", "yolo-fastestv2", "efficientnetv2_b0"]
-EXTRA_INPUT = {"blazeface": 128, "FastestDet": 352, "squeezenet": 227, "alexnet": 227, "nanodet_m": 320, "yolo-fastestv2": 352}
+                "squeezenet", "blazeface", "FastestDet", "alexnet", "googlenet", "nanodet_m", "yolo-fastestv2", "efficientnetv2_b0", "vision_transformer"]
+EXTRA_INPUT = {"vision_transformer": 384, "blazeface": 128, "FastestDet": 352, "squeezenet": 227, "alexnet": 227, "nanodet_m": 320, "yolo-fastestv2": 352}
 # The detection graphs (FastestDet, yolo-fastestv2, nanodet_m) only expose the concatenation of its sigmoid / softmax heads (no linear blob to assert on) after ~70 stored
 # fp16 activations: measured 2.1e-3, so its 16-bit bound is 4e-3; its fp32 bound stays 1e-5 like every other graph.
 EXTRA_TOL16 = {"FastestDet": 4e-3, "yolo-fastestv2": 4e-3, "nanodet_m": 1e-2}  # nanodet_m: ~100 stored layers, measured 2.8e-3 .. 5.4e-3 over its six heads

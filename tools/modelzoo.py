@@ -414,7 +414,22 @@ def random_model_bytes(text, seed=7767517, bias_scale=0.1, dtype=np.float32):
             if p.get(21, 1) != 1:
                 raise NotImplementedError("MemoryData load_type %d" % p.get(21, 1))
             chunks.append(rng.uniform(0.5, 1.5, count).astype(np.float32).tobytes())
-        elif t in ("PReLU", "Gemm"):
+        elif t == "Gemm":
+            # src/layer/gemm.cpp:160-212: constant A / B / C in that order, each tagged (ModelBin type 0)
+            M, N, K = p.get(7, 0), p.get(8, 0), p.get(9, 0)
+            if p.get(4, 0):
+                chunks.append(np.zeros(1, np.uint32).tobytes())
+                chunks.append(rng.uniform(-1, 1, M * K).astype(np.float32).tobytes())
+            if p.get(5, 0):
+                a = np.sqrt(3.0 / K)
+                chunks.append(np.zeros(1, np.uint32).tobytes())
+                chunks.append(rng.uniform(-a, a, N * K).astype(np.float32).tobytes())
+            bt = p.get(10, 0)
+            if p.get(6, 0) and bt != -1:
+                count = {0: 1, 1: M, 2: M, 3: N * M, 4: N}[bt]
+                chunks.append(np.zeros(1, np.uint32).tobytes())
+                chunks.append(rng.uniform(-bias_scale, bias_scale, count).astype(np.float32).tobytes())
+        elif t in ("PReLU",):
             raise NotImplementedError("random weights for " + t)
     return b"".join(chunks)
 
