@@ -95,6 +95,39 @@ def test_load_param_matches_reference(ours, ref, name):
     assert seen[0] == seen[1] and seen[0][0] and seen[0][1]
 
 
+def _extra_graphs():
+    import glob
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
+    return sorted(glob.glob(os.path.join(d, "*.param")))
+
+
+@pytest.mark.parametrize("path", _extra_graphs(), ids=lambda p: p.split("/")[-1][:-6])
+def test_load_param_benchmark_set_matches_reference(ours, ref, path):
+    """every fp32 graph of the reference's benchmark set kept under models/extra/ parses in the product runtime to the same input /
+    output blob names as in the reference; graphs that end in host-side detection post-processing are refused by the product
+    (no creator for PriorBox / DetectionOutput / Yolo*DetectionOutput: a graph never falls back to the CPU silently)"""
+    text = open(path).read()
+    types = set(l.split()[0] for l in text.splitlines()[2:] if l.strip())
+    post = types & {"PriorBox", "DetectionOutput", "YoloDetectionOutput", "Yolov3DetectionOutput"}
+    seen = []
+    for api in (ours, ref):
+        L = api.lib
+        net = L.ncnn_net_create()
+        r = L.ncnn_net_load_param_memory(net, text.encode())
+        if api is ours and post:
+            assert r != 0, "a graph with %s must be refused" % sorted(post)
+            L.ncnn_net_destroy(net)
+            continue
+        assert r == 0
+        ins = [L.ncnn_net_get_input_name(net, i) for i in range(L.ncnn_net_get_input_count(net))]
+        outs = [L.ncnn_net_get_output_name(net, i) for i in range(L.ncnn_net_get_output_count(net))]
+        seen.append((ins, outs))
+        L.ncnn_net_destroy(net)
+    if not post:
+        assert seen[0] == seen[1] and seen[0][0] and seen[0][1]
+
+
 def test_load_param_rejects_garbage(ours):
     L = ours.lib
     for bad in (b"", b"1234\n1 1\n", b"7767517\n2 2\nInput data 0 1 data\n"):
@@ -293,3 +326,27 @@ def test_pixels_resize_and_roi_match_reference(ours, ref):
                 api.lib.ncnn_mat_destroy(m)
                 res.append(out)
             assert np.array_equal(res[0], res[1]), ("to_pixels_resize", a, b, w, h, tw, th)
+
+
+@pytest.mark.parametrize("which", ["DECONV_PARAM", "NORM_PARAM", "MHA_PARAM", "UNFUSED_PARAM", "efficientnetv2_b0"])
+def test_seeded_weight_stream_of_neighbour_layers_is_consumed_exactly(ref, which):
+    """same for the graphs that carry the later-added weight-bearing layers (Deconvolution[DepthWise], LayerNorm, MemoryData,
+    MultiHeadAttention, BatchNorm, Scale): tools/modelzoo.py writes exactly the bytes the reference's load_model reads"""
+    import os
+    from ncnn_b200 import capi
+    import test_nets_gpu as tn
+    if hasattr(tn, which):
+        text = getattr(tn, which)
+    else:
+        text = open(os.path.join(tn.EXTRA, which + ".param")).read()
+    weights = modelzoo.random_model_bytes(text, seed=7)
+    L = ref.lib
+    opt = ref.strict_fp32_option()
+    net = L.ncnn_net_create()
+    L.ncnn_net_set_option(net, opt)
+    assert L.ncnn_net_load_param_memory(net, text.encode()) == 0
+    rd = capi.MemoryReader(ref, weights)
+    assert L.ncnn_net_load_model_datareader(net, rd.dr) == 0
+    assert rd.pos == len(weights), (rd.pos, len(weights))
+    rd.close()
+    L.ncnn_net_destroy(net)
