@@ -100,6 +100,19 @@ NCNN_C_API void ncnn_mat_fill_float(ncnn_mat_t mat, float v);
 #define NCNN_MAT_PIXEL_RGBA      4
 #define NCNN_MAT_PIXEL_BGRA      5
 #define NCNN_MAT_PIXEL_X2Y(X, Y) (X | (Y << 16))
+/* src/c_api.h:124-137: Mats of another element size / packing (fp16, int8, packed storage made by the caller) */
+NCNN_C_API ncnn_mat_t ncnn_mat_create_1d_elem(int w, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_2d_elem(int w, int h, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_3d_elem(int w, int h, int c, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_4d_elem(int w, int h, int d, int c, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_1d_elem_batch(int w, size_t elemsize, int elempack, int n, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_2d_elem_batch(int w, int h, size_t elemsize, int elempack, int n, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_3d_elem_batch(int w, int h, int c, size_t elemsize, int elempack, int n, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_4d_elem_batch(int w, int h, int d, int c, size_t elemsize, int elempack, int n, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_external_1d_elem(int w, void* data, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_external_2d_elem(int w, int h, void* data, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_external_3d_elem(int w, int h, int c, void* data, size_t elemsize, int elempack, ncnn_allocator_t allocator);
+NCNN_C_API ncnn_mat_t ncnn_mat_create_external_4d_elem(int w, int h, int d, int c, void* data, size_t elemsize, int elempack, ncnn_allocator_t allocator);
 NCNN_C_API ncnn_mat_t ncnn_mat_from_pixels(const unsigned char* pixels, int type, int w, int h, int stride, ncnn_allocator_t allocator);
 NCNN_C_API void ncnn_mat_substract_mean_normalize(ncnn_mat_t mat, const float* mean_vals, const float* norm_vals);
 /* src/c_api.h:180 */
@@ -223,6 +236,8 @@ NCNN_C_API int ncnn_net_load_param(ncnn_net_t net, const char* path);
 NCNN_C_API int ncnn_net_load_param_bin(ncnn_net_t net, const char* path);
 NCNN_C_API int ncnn_net_load_model(ncnn_net_t net, const char* path);
 NCNN_C_API int ncnn_net_load_param_memory(ncnn_net_t net, const char* mem);
+/* src/c_api.h:373: a .param.bin image in memory; returns the bytes consumed (0 on failure) */
+NCNN_C_API size_t ncnn_net_load_param_bin_memory(ncnn_net_t net, const unsigned char* mem);
 NCNN_C_API size_t ncnn_net_load_model_memory(ncnn_net_t net, const unsigned char* mem);
 NCNN_C_API int ncnn_net_load_param_datareader(ncnn_net_t net, const ncnn_datareader_t dr);
 NCNN_C_API int ncnn_net_load_param_bin_datareader(ncnn_net_t net, const ncnn_datareader_t dr);

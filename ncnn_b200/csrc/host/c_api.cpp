@@ -199,6 +199,86 @@ ncnn_mat_t ncnn_mat_create_external_4d(int w, int h, int d, int c, void* data, n
 {
     return (ncnn_mat_t)(new Mat(w, h, d, c, data, (size_t)4u, alloc_of(a)));
 }
+ncnn_mat_t ncnn_mat_create_1d_elem(int w, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, elemsize, elempack, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_2d_elem(int w, int h, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, h, elemsize, elempack, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_3d_elem(int w, int h, int c, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, h, c, elemsize, elempack, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_4d_elem(int w, int h, int d, int c, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, h, d, c, elemsize, elempack, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_1d_elem_batch(int w, size_t elemsize, int elempack, int n, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, elemsize, elempack, n, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_2d_elem_batch(int w, int h, size_t elemsize, int elempack, int n, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, h, elemsize, elempack, n, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_3d_elem_batch(int w, int h, int c, size_t elemsize, int elempack, int n, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, h, c, elemsize, elempack, n, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_4d_elem_batch(int w, int h, int d, int c, size_t elemsize, int elempack, int n, ncnn_allocator_t a)
+{
+    Mat* m = new Mat;
+    m->create(w, h, d, c, elemsize, elempack, n, alloc_of(a));
+    m->elempack = elempack; // the layout depends on elemsize only (src/mat.cpp:299-861); the field is carried for the caller
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_external_1d_elem(int w, void* data, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat(w, data, elemsize, alloc_of(a));
+    m->elempack = elempack;
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_external_2d_elem(int w, int h, void* data, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat(w, h, data, elemsize, alloc_of(a));
+    m->elempack = elempack;
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_external_3d_elem(int w, int h, int c, void* data, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat(w, h, c, data, elemsize, alloc_of(a));
+    m->elempack = elempack;
+    return (ncnn_mat_t)m;
+}
+ncnn_mat_t ncnn_mat_create_external_4d_elem(int w, int h, int d, int c, void* data, size_t elemsize, int elempack, ncnn_allocator_t a)
+{
+    Mat* m = new Mat(w, h, d, c, data, elemsize, alloc_of(a));
+    m->elempack = elempack;
+    return (ncnn_mat_t)m;
+}
 void ncnn_mat_destroy(ncnn_mat_t mat)
 {
     delete (Mat*)mat;
@@ -965,6 +1045,10 @@ int ncnn_net_load_model(ncnn_net_t net, const char* path)
 int ncnn_net_load_param_memory(ncnn_net_t net, const char* mem)
 {
     return ((Net*)net->pthis)->load_param_mem(mem);
+}
+size_t ncnn_net_load_param_bin_memory(ncnn_net_t net, const unsigned char* mem)
+{
+    return ((Net*)net->pthis)->load_param_bin_mem(mem);
 }
 size_t ncnn_net_load_model_memory(ncnn_net_t net, const unsigned char* mem)
 {

@@ -551,6 +551,14 @@ int Net::load_model(const char* modelpath)
     return ret;
 }
 
+size_t Net::load_param_bin_mem(const unsigned char* _mem)
+{
+    const unsigned char* mem = _mem;
+    DataReaderFromMemory dr(mem);
+    if (load_param_bin(dr) != 0) return 0;
+    return mem - _mem;
+}
+
 size_t Net::load_model(const unsigned char* _mem)
 {
     const unsigned char* mem = _mem;

@@ -50,6 +50,8 @@ public:
     int load_model(FILE* fp);
     int load_model(const char* modelpath);
     // returns bytes consumed
+    // src/net.cpp:2337-2343 (Net::load_param(const unsigned char*)): a .param.bin image in memory, returns the bytes consumed
+    size_t load_param_bin_mem(const unsigned char* mem);
     size_t load_model(const unsigned char* mem);
 
     void clear();

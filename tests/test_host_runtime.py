@@ -350,3 +350,168 @@ def test_seeded_weight_stream_of_neighbour_layers_is_consumed_exactly(ref, which
     assert rd.pos == len(weights), (rd.pos, len(weights))
     rd.close()
     L.ncnn_net_destroy(net)
+
+
+def test_mat_elem_constructors_match_reference(ours, ref):
+    """ncnn_mat_create_*_elem[_batch] / create_external_*_elem (src/c_api.h:124-137): element size and packing other than fp32 x 1,
+    same dims / elemsize / elempack / cstep / nstep as the reference"""
+    keys = ("dims", "w", "h", "d", "c", "n", "elemsize", "elempack", "cstep", "nstep")
+    for (elemsize, elempack) in [(2, 1), (1, 1), (16, 4), (8, 4), (32, 8), (4, 1)]:
+        for shp in [(7,), (5, 3), (13, 13, 6), (3, 5, 7, 2)]:
+            for n in (0, 3):
+                desc = []
+                for api in (ours, ref):
+                    L = api.lib
+                    f = getattr(L, "ncnn_mat_create_%dd_elem%s" % (len(shp), "_batch" if n else ""))
+                    f.restype = C.c_void_p
+                    f.argtypes = [C.c_int] * len(shp) + [C.c_size_t, C.c_int] + ([C.c_int] if n else []) + [C.c_void_p]
+                    m = C.c_void_p(f(*shp, elemsize, elempack, *([n] if n else []), None))
+                    desc.append(tuple(int(getattr(L, "ncnn_mat_get_" + k)(m)) for k in keys))
+                    L.ncnn_mat_destroy(m)
+                assert desc[0] == desc[1], (elemsize, elempack, shp, n, desc)
+            buf = np.zeros(4096, np.uint8)
+            desc = []
+            for api in (ours, ref):
+                L = api.lib
+                f = getattr(L, "ncnn_mat_create_external_%dd_elem" % len(shp))
+                f.restype = C.c_void_p
+                f.argtypes = [C.c_int] * len(shp) + [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+                m = C.c_void_p(f(*shp, buf.ctypes.data_as(C.c_void_p), elemsize, elempack, None))
+                desc.append(tuple(int(getattr(L, "ncnn_mat_get_" + k)(m)) for k in keys) + (int(L.ncnn_mat_get_data(m)) == buf.ctypes.data,))
+                L.ncnn_mat_destroy(m)
+            assert desc[0] == desc[1] and desc[0][-1], (elemsize, elempack, shp, desc)
+
+
+def _ref_type_index(ref, text):
+    """typeindex of every operator of a graph in the ORACLE build (its registry only holds the operators it was built with, so
+    its numbering differs from the stock one the product uses)"""
+    L = ref.lib
+    out = {}
+    for t in sorted(set(l.split()[0] for l in text.splitlines()[2:] if l.strip())):
+        layer = L.ncnn_layer_create_by_type(t.encode())  # typed by ncnn_b200/capi.py
+        assert layer, t
+        out[t] = int(L.ncnn_layer_get_typeindex(layer))
+        L.ncnn_layer_destroy(layer)
+    return out
+
+
+@pytest.mark.parametrize("name", ["squeezenet_v1_1", "mobilenet_v2", "yolov8s"])
+def test_param_bin_format(ours, ref, name):
+    """the binary graph format.  tools/param2bin.py writes it; (1) the REFERENCE loads that image and computes
+    exactly what it computes from the text form (so the writer's understanding of src/net.cpp:1667-1940 is right), (2) the product
+    parses the stock-typeindex image -- from a DataReader and from memory -- to the same layers, blob wiring and input / output
+    indices as from the text form, and refuses truncated images"""
+    import param2bin
+    from ncnn_b200 import capi
+    size = 64 if name != "squeezenet_v1_1" else 227
+    text = modelzoo.param_text(name)
+    lines = text.splitlines()
+    text = "\n".join(((" ".join(("0=%d" % size) if t.startswith("0=") else (("1=%d" % size) if t.startswith("1=") else t) for t in l.split())) if l.startswith("Input") else l)
+                     for l in lines) + "\n"
+    weights = modelzoo.random_model_bytes(text, seed=3)
+    x = np.random.default_rng(1).uniform(-1, 1, (3, size, size)).astype(np.float32)
+    # (1) the reference: text vs binary
+    L = ref.lib
+    res = []
+    for form in ("text", "bin"):
+        opt = ref.strict_fp32_option()
+        net = L.ncnn_net_create()
+        L.ncnn_net_set_option(net, opt)
+        if form == "text":
+            assert L.ncnn_net_load_param_memory(net, text.encode()) == 0
+        else:
+            image = param2bin.convert(text, _ref_type_index(ref, text))
+            rd = capi.MemoryReader(ref, image)
+            assert L.ncnn_net_load_param_bin_datareader(net, rd.dr) == 0
+            assert rd.pos == len(image)
+            rd.close()
+        rd = capi.MemoryReader(ref, weights)
+        assert L.ncnn_net_load_model_datareader(net, rd.dr) == 0 and rd.pos == len(weights)
+        rd.close()
+        i_in, i_out = L.ncnn_net_get_input_index(net, 0), L.ncnn_net_get_output_index(net, 0)
+        ex = L.ncnn_extractor_create(net)
+        m = ref.mat_from_numpy(x)
+        assert L.ncnn_extractor_input_index(ex, i_in, m) == 0
+        out = C.c_void_p()
+        assert L.ncnn_extractor_extract_index(ex, i_out, C.byref(out)) == 0
+        res.append((i_in, i_out, ref.mat_to_numpy(out).copy()))
+        L.ncnn_mat_destroy(out)
+        L.ncnn_mat_destroy(m)
+        L.ncnn_extractor_destroy(ex)
+        L.ncnn_net_destroy(net)
+        L.ncnn_option_destroy(opt)
+    assert res[0][:2] == res[1][:2] and np.array_equal(res[0][2], res[1][2])
+    # (2) the product: structure from the binary image == structure from the text
+    P = ours.lib
+    P.ncnn_net_get_layer_type.restype = C.c_char_p
+    P.ncnn_net_load_param_bin_memory.restype = C.c_size_t
+    P.ncnn_net_load_param_bin_memory.argtypes = [C.c_void_p, C.c_void_p]
+    image = param2bin.convert(text)
+
+    def structure(net):
+        return ([P.ncnn_net_get_layer_type(net, i) for i in range(P.ncnn_net_get_layer_count(net))],
+                [P.ncnn_net_get_input_index(net, i) for i in range(P.ncnn_net_get_input_count(net))],
+                [P.ncnn_net_get_output_index(net, i) for i in range(P.ncnn_net_get_output_count(net))])
+
+    net = P.ncnn_net_create()
+    assert P.ncnn_net_load_param_memory(net, text.encode()) == 0
+    want = structure(net)
+    P.ncnn_net_destroy(net)
+    net = P.ncnn_net_create()
+    rd = capi.MemoryReader(ours, image)
+    assert P.ncnn_net_load_param_bin_datareader(net, rd.dr) == 0 and rd.pos == len(image)
+    rd.close()
+    assert structure(net) == want
+    P.ncnn_net_destroy(net)
+    net = P.ncnn_net_create()
+    buf = np.frombuffer(image, np.uint8).copy()
+    assert P.ncnn_net_load_param_bin_memory(net, buf.ctypes.data_as(C.c_void_p)) == len(image)
+    assert structure(net) == want
+    assert want[1] == [res[1][0]] and want[2] == [res[1][1]]  # same blob numbering as the reference
+    P.ncnn_net_destroy(net)
+    net = P.ncnn_net_create()
+    rd = capi.MemoryReader(ours, image[:len(image) // 2])
+    assert P.ncnn_net_load_param_bin_datareader(net, rd.dr) != 0
+    rd.close()
+    P.ncnn_net_destroy(net)
+
+
+def test_modelbin_storage_tags_match_reference(ours, ref):
+    """SURVEY 8f row f1, weight side: ModelBinFromDataReader (src/modelbin.cpp:75-151) on one byte stream -- a tag-0 fp32 blob, an
+    fp16-tagged blob (0x01306B47, odd length: its 4-byte alignment padding must be skipped), a raw (type 1) blob and a type-0 scalar
+    -- decoded to identical Mats by the product and the reference, and consumed to the same position"""
+    import struct
+    from ncnn_b200 import capi
+    rng = np.random.default_rng(41)
+    a = rng.uniform(-1, 1, 37).astype(np.float32)
+    h = rng.uniform(-4, 4, 21).astype(np.float16)          # 42 bytes -> padded to 44
+    r = rng.uniform(-1, 1, 9).astype(np.float32)
+    stream = (struct.pack("<I", 0) + a.tobytes() + struct.pack("<I", 0x01306B47) + h.tobytes() + b"\0" * 2 + r.tobytes()
+              + struct.pack("<I", 0) + struct.pack("<f", 0.75) + b"tail")
+
+    class ModelBin(C.Structure):
+        pass
+    ModelBin._fields_ = [("pthis", C.c_void_p), ("load_1d", C.CFUNCTYPE(C.c_void_p, C.POINTER(ModelBin), C.c_int, C.c_int)),
+                         ("load_2d", C.c_void_p), ("load_3d", C.c_void_p)]
+    got = []
+    for api in (ours, ref):
+        L = api.lib
+        rd = capi.MemoryReader(api, stream)
+        f = L.ncnn_modelbin_create_from_datareader
+        f.restype = C.POINTER(ModelBin)
+        f.argtypes = [C.c_void_p]
+        mb = f(rd.dr)
+        mats = []
+        for (w, t) in [(37, 0), (21, 0), (9, 1), (1, 0)]:
+            m = C.c_void_p(mb.contents.load_1d(mb, w, t))
+            assert m
+            mats.append(api.mat_to_numpy(m).copy())
+            L.ncnn_mat_destroy(m)
+        got.append((mats, rd.pos))
+        L.ncnn_modelbin_destroy.argtypes = [C.c_void_p]
+        L.ncnn_modelbin_destroy(C.cast(mb, C.c_void_p))
+        rd.close()
+    for x, y in zip(got[0][0], got[1][0]):
+        assert x.shape == y.shape and np.array_equal(x, y)
+    assert np.array_equal(got[0][0][1], h.astype(np.float32)) and got[0][0][3][0] == np.float32(0.75)
+    assert got[0][1] == got[1][1] == len(stream) - 4
