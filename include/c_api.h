@@ -211,6 +211,22 @@ NCNN_C_API int ncnn_layer_get_support_bf16_storage(const ncnn_layer_t layer);
 NCNN_C_API int ncnn_layer_get_support_fp16_storage(const ncnn_layer_t layer);
 NCNN_C_API void ncnn_layer_set_one_blob_only(ncnn_layer_t layer, int enable);
 NCNN_C_API void ncnn_layer_set_support_inplace(ncnn_layer_t layer, int enable);
+/* src/c_api.h:294-306: the remaining capability flags.  This runtime keeps host Mats unpacked and has no Vulkan path, so the three
+ * *_packing / vulkan getters always report 0 and their setters only exist so that a custom layer written against the reference's
+ * C API links and runs unchanged (the values are ignored). */
+NCNN_C_API int ncnn_layer_get_support_vulkan_packing(const ncnn_layer_t layer);
+NCNN_C_API int ncnn_layer_get_support_any_packing(const ncnn_layer_t layer);
+NCNN_C_API int ncnn_layer_get_support_vulkan_any_packing(const ncnn_layer_t layer);
+NCNN_C_API void ncnn_layer_set_support_vulkan(ncnn_layer_t layer, int enable);
+NCNN_C_API void ncnn_layer_set_support_packing(ncnn_layer_t layer, int enable);
+NCNN_C_API void ncnn_layer_set_support_bf16_storage(ncnn_layer_t layer, int enable);
+NCNN_C_API void ncnn_layer_set_support_fp16_storage(ncnn_layer_t layer, int enable);
+NCNN_C_API void ncnn_layer_set_support_vulkan_packing(ncnn_layer_t layer, int enable);
+NCNN_C_API void ncnn_layer_set_support_any_packing(ncnn_layer_t layer, int enable);
+NCNN_C_API void ncnn_layer_set_support_vulkan_any_packing(ncnn_layer_t layer, int enable);
+/* src/c_api.h:313-314: the shape hints of a layer's i-th bottom / top blob (dims 0 when the .param carries none) */
+NCNN_C_API void ncnn_blob_get_bottom_shape(const ncnn_layer_t layer, int i, int* dims, int* w, int* h, int* c);
+NCNN_C_API void ncnn_blob_get_top_shape(const ncnn_layer_t layer, int i, int* dims, int* w, int* h, int* c);
 NCNN_C_API int ncnn_layer_get_bottom_count(const ncnn_layer_t layer);
 NCNN_C_API int ncnn_layer_get_bottom(const ncnn_layer_t layer, int i);
 NCNN_C_API int ncnn_layer_get_top_count(const ncnn_layer_t layer);
@@ -320,6 +336,12 @@ NCNN_C_API int ncnn_extractor_input_pixels_resize(ncnn_extractor_t ex, const cha
  * surviving rows and applies NMS as the example does. */
 NCNN_C_API int ncnn_extractor_extract_yolov8_proposals(ncnn_extractor_t ex, const char* name, const int* strides, int num_strides, int in_w, int in_h,
                                                        float prob_threshold, ncnn_mat_t* proposals);
+/* Host-side Mat helpers of the reference's C API (src/c_api.h:188, :413-415), for the letterbox / crop steps around a network
+ * (examples/yolov8.cpp:331-335 pads with 114).  fp32 Mats of 1 to 3 dims; border type 0 constant `v`, 1 replicate, 2 reflect
+ * (src/layer/padding.cpp:21-260).  `opt` supplies the blob allocator (may be NULL). */
+NCNN_C_API void ncnn_copy_make_border(const ncnn_mat_t src, ncnn_mat_t dst, int top, int bottom, int left, int right, int type, float v, const ncnn_option_t opt);
+NCNN_C_API void ncnn_copy_cut_border(const ncnn_mat_t src, ncnn_mat_t dst, int top, int bottom, int left, int right, const ncnn_option_t opt);
+NCNN_C_API void ncnn_flatten(const ncnn_mat_t src, ncnn_mat_t* dst, const ncnn_option_t opt);
 /* PCIe bytes of the last ncnn_extractor_extract call */
 NCNN_C_API size_t ncnn_extractor_get_last_h2d_bytes(const ncnn_extractor_t ex);
 NCNN_C_API size_t ncnn_extractor_get_last_d2h_bytes(const ncnn_extractor_t ex);

@@ -933,6 +933,59 @@ void ncnn_layer_set_support_inplace(ncnn_layer_t layer, int enable)
 {
     ((Layer*)layer->pthis)->support_inplace = enable != 0;
 }
+int ncnn_layer_get_support_vulkan_packing(const ncnn_layer_t)
+{
+    return 0;
+}
+int ncnn_layer_get_support_any_packing(const ncnn_layer_t)
+{
+    return 0;
+}
+int ncnn_layer_get_support_vulkan_any_packing(const ncnn_layer_t)
+{
+    return 0;
+}
+void ncnn_layer_set_support_vulkan(ncnn_layer_t, int)
+{
+}
+void ncnn_layer_set_support_packing(ncnn_layer_t, int)
+{
+}
+void ncnn_layer_set_support_bf16_storage(ncnn_layer_t layer, int enable)
+{
+    ((Layer*)layer->pthis)->support_bf16_storage = enable != 0;
+}
+void ncnn_layer_set_support_fp16_storage(ncnn_layer_t layer, int enable)
+{
+    ((Layer*)layer->pthis)->support_fp16_storage = enable != 0;
+}
+void ncnn_layer_set_support_vulkan_packing(ncnn_layer_t, int)
+{
+}
+void ncnn_layer_set_support_any_packing(ncnn_layer_t, int)
+{
+}
+void ncnn_layer_set_support_vulkan_any_packing(ncnn_layer_t, int)
+{
+}
+static void shape_of(const std::vector<Mat>& shapes, int i, int* dims, int* w, int* h, int* c)
+{
+    *dims = *w = *h = *c = 0;
+    if (i < 0 || i >= (int)shapes.size()) return;
+    const Mat& shape = shapes[i];
+    *dims = shape.dims;
+    *w = shape.w;
+    *h = shape.h;
+    *c = shape.c;
+}
+void ncnn_blob_get_bottom_shape(const ncnn_layer_t layer, int i, int* dims, int* w, int* h, int* c)
+{
+    shape_of(((const Layer*)layer->pthis)->bottom_shapes, i, dims, w, h, c);
+}
+void ncnn_blob_get_top_shape(const ncnn_layer_t layer, int i, int* dims, int* w, int* h, int* c)
+{
+    shape_of(((const Layer*)layer->pthis)->top_shapes, i, dims, w, h, c);
+}
 int ncnn_layer_get_bottom_count(const ncnn_layer_t layer)
 {
     return (int)((const Layer*)layer->pthis)->bottoms.size();
@@ -1123,6 +1176,119 @@ int ncnn_extractor_input_pixels(ncnn_extractor_t ex, const char* name, const uns
                                 const float* mean_vals, const float* norm_vals)
 {
     return ((Extractor*)ex)->input_pixels(name, pixels, type, w, h, stride, n, nstride, mean_vals, norm_vals);
+}
+// ---- host-side Mat helpers (src/mat.cpp copy_make_border / copy_cut_border / flatten run the Padding / Crop / Flatten layers on
+// the host; here they are plain loops over fp32 Mats)
+static int border_index(int i, int n, int type)
+{
+    if (i >= 0 && i < n) return i;
+    if (type == 1) return i < 0 ? 0 : n - 1;             // replicate
+    if (type == 2) return i < 0 ? -i : 2 * (n - 1) - i;  // reflect without repeating the edge (padding.cpp:185-260)
+    return -1;                                           // constant
+}
+void ncnn_copy_make_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, int type, float v, const ncnn_option_t opt)
+{
+    const Mat& src = *(const Mat*)_src;
+    Mat& dst = *(Mat*)_dst;
+    Allocator* alloc = opt ? ((const Option*)opt)->blob_allocator : 0;
+    if (src.empty() || src.elemsize != 4u || src.dims < 1 || src.dims > 3 || type < 0 || type > 2 || top < 0 || bottom < 0 || left < 0 || right < 0)
+    {
+        dst.release();
+        return;
+    }
+    if (src.dims == 1) top = bottom = 0;
+    if (top == 0 && bottom == 0 && left == 0 && right == 0)
+    {
+        dst = src;
+        return;
+    }
+    if (type == 2 && (left >= src.w || right >= src.w || (src.dims >= 2 && (top >= src.h || bottom >= src.h))))
+    {
+        dst.release();
+        return;
+    }
+    Mat out;
+    const int ow = src.w + left + right, oh = src.h + top + bottom;
+    if (src.dims == 1) out.create(ow, (size_t)4u, alloc);
+    if (src.dims == 2) out.create(ow, oh, (size_t)4u, alloc);
+    if (src.dims == 3) out.create(ow, oh, src.c, (size_t)4u, alloc);
+    if (out.empty())
+    {
+        dst.release();
+        return;
+    }
+    const int chs = src.dims == 3 ? src.c : 1;
+    for (int q = 0; q < chs; q++)
+    {
+        const float* sp = src.dims == 3 ? (const float*)src.channel(q) : (const float*)src.data;
+        float* dp = src.dims == 3 ? (float*)out.channel(q) : (float*)out.data;
+        for (int y = 0; y < (src.dims == 1 ? 1 : oh); y++)
+        {
+            const int sy = src.dims == 1 ? 0 : border_index(y - top, src.h, type);
+            for (int x = 0; x < ow; x++)
+            {
+                const int sx = border_index(x - left, src.w, type);
+                dp[(size_t)y * ow + x] = (sx < 0 || sy < 0) ? v : sp[(size_t)sy * src.w + sx];
+            }
+        }
+    }
+    dst = out;
+}
+void ncnn_copy_cut_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, const ncnn_option_t opt)
+{
+    const Mat& src = *(const Mat*)_src;
+    Mat& dst = *(Mat*)_dst;
+    Allocator* alloc = opt ? ((const Option*)opt)->blob_allocator : 0;
+    if (src.empty() || src.elemsize != 4u || src.dims < 1 || src.dims > 3 || top < 0 || bottom < 0 || left < 0 || right < 0)
+    {
+        dst.release();
+        return;
+    }
+    if (src.dims == 1) top = bottom = 0;
+    const int ow = src.w - left - right, oh = src.h - top - bottom;
+    if (ow <= 0 || oh <= 0)
+    {
+        dst.release();
+        return;
+    }
+    if (ow == src.w && oh == src.h)
+    {
+        dst = src;
+        return;
+    }
+    Mat out;
+    if (src.dims == 1) out.create(ow, (size_t)4u, alloc);
+    if (src.dims == 2) out.create(ow, oh, (size_t)4u, alloc);
+    if (src.dims == 3) out.create(ow, oh, src.c, (size_t)4u, alloc);
+    if (out.empty())
+    {
+        dst.release();
+        return;
+    }
+    const int chs = src.dims == 3 ? src.c : 1;
+    for (int q = 0; q < chs; q++)
+    {
+        const float* sp = src.dims == 3 ? (const float*)src.channel(q) : (const float*)src.data;
+        float* dp = src.dims == 3 ? (float*)out.channel(q) : (float*)out.data;
+        for (int y = 0; y < oh; y++) memcpy(dp + (size_t)y * ow, sp + (size_t)(y + top) * src.w + left, (size_t)ow * sizeof(float));
+    }
+    dst = out;
+}
+void ncnn_flatten(const ncnn_mat_t _src, ncnn_mat_t* _dst, const ncnn_option_t opt)
+{
+    const Mat& src = *(const Mat*)_src;
+    Allocator* alloc = opt ? ((const Option*)opt)->blob_allocator : 0;
+    Mat* out = new Mat;
+    if (!src.empty() && src.elemsize == 4u)
+    {
+        const size_t plane = (size_t)src.w * src.h * src.d;
+        const int chs = src.dims >= 3 ? src.c : 1;
+        out->create((int)(plane * chs), (size_t)4u, alloc);
+        if (!out->empty())
+            for (int q = 0; q < chs; q++)
+                memcpy((float*)out->data + plane * q, src.dims >= 3 ? (const float*)src.channel(q) : (const float*)src.data, plane * sizeof(float));
+    }
+    *_dst = (ncnn_mat_t)out;
 }
 int ncnn_extractor_input_pixels_resize(ncnn_extractor_t ex, const char* name, const unsigned char* pixels, int type, int w, int h, int stride, int n, size_t nstride,
                                        int target_w, int target_h, const float* mean_vals, const float* norm_vals)

@@ -515,3 +515,42 @@ def test_modelbin_storage_tags_match_reference(ours, ref):
         assert x.shape == y.shape and np.array_equal(x, y)
     assert np.array_equal(got[0][0][1], h.astype(np.float32)) and got[0][0][3][0] == np.float32(0.75)
     assert got[0][1] == got[1][1] == len(stream) - 4
+
+
+def test_host_border_and_flatten_helpers_match_reference(ours, ref):
+    """ncnn_copy_make_border (constant / replicate / reflect), ncnn_copy_cut_border and ncnn_flatten on host Mats of 1 to 3 dims
+    (src/c_api.h:188, :413-415), bit-exact against the reference (which runs its Padding / Crop / Flatten layers on the host)"""
+    rng = np.random.default_rng(43)
+    vp, ci = C.c_void_p, C.c_int
+    for api in (ours, ref):
+        l = api.lib
+        l.ncnn_copy_make_border.restype = None
+        l.ncnn_copy_make_border.argtypes = [vp, vp, ci, ci, ci, ci, ci, C.c_float, vp]
+        l.ncnn_copy_cut_border.restype = None
+        l.ncnn_copy_cut_border.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        l.ncnn_flatten.restype = None
+        l.ncnn_flatten.argtypes = [vp, vp, vp]
+    for shape in [(19,), (7, 13), (3, 9, 14), (5, 4, 4)]:
+        x = rng.uniform(-1, 1, shape).astype(np.float32)
+        for (t, b, lft, r) in [(1, 2, 3, 1), (0, 0, 2, 0), (3, 0, 0, 3)]:
+            for typ in (0, 1, 2):
+                got = []
+                for api in (ours, ref):
+                    opt = api.strict_fp32_option() if hasattr(api, "strict_fp32_option") else None
+                    src = api.mat_from_numpy(x)
+                    dst = vp(api.lib.ncnn_mat_create())
+                    api.lib.ncnn_copy_make_border(src, dst, t, b, lft, r, typ, 0.5, opt)
+                    padded = api.mat_to_numpy(dst).copy()
+                    cut = vp(api.lib.ncnn_mat_create())
+                    api.lib.ncnn_copy_cut_border(dst, cut, t if len(shape) > 1 else 0, b if len(shape) > 1 else 0, lft, r, opt)
+                    back = api.mat_to_numpy(cut).copy()
+                    flat = vp()
+                    api.lib.ncnn_flatten(dst, C.byref(flat), opt)
+                    got.append((padded, back, api.mat_to_numpy(flat).copy()))
+                    for m in (src, dst, cut, flat):
+                        api.lib.ncnn_mat_destroy(m)
+                    if opt:
+                        api.lib.ncnn_option_destroy(opt)
+                for a, bb in zip(got[0], got[1]):
+                    assert a.shape == bb.shape and np.array_equal(a, bb), (shape, (t, b, lft, r), typ)
+                assert np.array_equal(got[0][1], x)  # cutting the border off gives the source back
