@@ -340,6 +340,9 @@ NCNN_C_API int ncnn_extractor_extract_yolov8_proposals(ncnn_extractor_t ex, cons
  * (examples/yolov8.cpp:331-335 pads with 114).  fp32 Mats of 1 to 3 dims; border type 0 constant `v`, 1 replicate, 2 reflect
  * (src/layer/padding.cpp:21-260).  `opt` supplies the blob allocator (may be NULL). */
 NCNN_C_API void ncnn_copy_make_border(const ncnn_mat_t src, ncnn_mat_t dst, int top, int bottom, int left, int right, int type, float v, const ncnn_option_t opt);
+/* src/c_api.h:414: also pads the channel axis of a 3-D Mat (front / behind) */
+NCNN_C_API void ncnn_copy_make_border_3d(const ncnn_mat_t src, ncnn_mat_t dst, int top, int bottom, int left, int right, int front, int behind, int type, float v,
+                                         const ncnn_option_t opt);
 NCNN_C_API void ncnn_copy_cut_border(const ncnn_mat_t src, ncnn_mat_t dst, int top, int bottom, int left, int right, const ncnn_option_t opt);
 NCNN_C_API void ncnn_flatten(const ncnn_mat_t src, ncnn_mat_t* dst, const ncnn_option_t opt);
 /* PCIe bytes of the last ncnn_extractor_extract call */

@@ -1186,43 +1186,49 @@ static int border_index(int i, int n, int type)
     if (type == 2) return i < 0 ? -i : 2 * (n - 1) - i;  // reflect without repeating the edge (padding.cpp:185-260)
     return -1;                                           // constant
 }
-void ncnn_copy_make_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, int type, float v, const ncnn_option_t opt)
+static void make_border(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int front, int behind, int type, float v, Allocator* alloc)
 {
-    const Mat& src = *(const Mat*)_src;
-    Mat& dst = *(Mat*)_dst;
-    Allocator* alloc = opt ? ((const Option*)opt)->blob_allocator : 0;
-    if (src.empty() || src.elemsize != 4u || src.dims < 1 || src.dims > 3 || type < 0 || type > 2 || top < 0 || bottom < 0 || left < 0 || right < 0)
+    if (src.empty() || src.elemsize != 4u || src.dims < 1 || src.dims > 3 || type < 0 || type > 2 || top < 0 || bottom < 0 || left < 0 || right < 0 || front < 0 || behind < 0)
     {
         dst.release();
         return;
     }
     if (src.dims == 1) top = bottom = 0;
-    if (top == 0 && bottom == 0 && left == 0 && right == 0)
+    if (src.dims != 3) front = behind = 0;
+    if (top == 0 && bottom == 0 && left == 0 && right == 0 && front == 0 && behind == 0)
     {
         dst = src;
         return;
     }
-    if (type == 2 && (left >= src.w || right >= src.w || (src.dims >= 2 && (top >= src.h || bottom >= src.h))))
+    if (type == 2 && (left >= src.w || right >= src.w || (src.dims >= 2 && (top >= src.h || bottom >= src.h)) || (src.dims == 3 && (front >= src.c || behind >= src.c))))
     {
         dst.release();
         return;
     }
     Mat out;
-    const int ow = src.w + left + right, oh = src.h + top + bottom;
+    const int ow = src.w + left + right, oh = src.h + top + bottom, oc = src.c + front + behind;
     if (src.dims == 1) out.create(ow, (size_t)4u, alloc);
     if (src.dims == 2) out.create(ow, oh, (size_t)4u, alloc);
-    if (src.dims == 3) out.create(ow, oh, src.c, (size_t)4u, alloc);
+    if (src.dims == 3) out.create(ow, oh, oc, (size_t)4u, alloc);
     if (out.empty())
     {
         dst.release();
         return;
     }
-    const int chs = src.dims == 3 ? src.c : 1;
+    const int chs = src.dims == 3 ? oc : 1;
     for (int q = 0; q < chs; q++)
     {
-        const float* sp = src.dims == 3 ? (const float*)src.channel(q) : (const float*)src.data;
+        // channel padding (src/layer/padding.cpp:333-372): a constant plane, or the replicated / reflected source channel
+        const int sq = src.dims == 3 ? border_index(q - front, src.c, type) : 0;
         float* dp = src.dims == 3 ? (float*)out.channel(q) : (float*)out.data;
-        for (int y = 0; y < (src.dims == 1 ? 1 : oh); y++)
+        const int rows = src.dims == 1 ? 1 : oh;
+        if (sq < 0)
+        {
+            for (size_t i = 0; i < (size_t)rows * ow; i++) dp[i] = v;
+            continue;
+        }
+        const float* sp = src.dims == 3 ? (const float*)src.channel(sq) : (const float*)src.data;
+        for (int y = 0; y < rows; y++)
         {
             const int sy = src.dims == 1 ? 0 : border_index(y - top, src.h, type);
             for (int x = 0; x < ow; x++)
@@ -1233,6 +1239,15 @@ void ncnn_copy_make_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int 
         }
     }
     dst = out;
+}
+void ncnn_copy_make_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, int type, float v, const ncnn_option_t opt)
+{
+    make_border(*(const Mat*)_src, *(Mat*)_dst, top, bottom, left, right, 0, 0, type, v, opt ? ((const Option*)opt)->blob_allocator : 0);
+}
+void ncnn_copy_make_border_3d(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, int front, int behind, int type, float v,
+                              const ncnn_option_t opt)
+{
+    make_border(*(const Mat*)_src, *(Mat*)_dst, top, bottom, left, right, front, behind, type, v, opt ? ((const Option*)opt)->blob_allocator : 0);
 }
 void ncnn_copy_cut_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, const ncnn_option_t opt)
 {

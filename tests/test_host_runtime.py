@@ -554,3 +554,21 @@ def test_host_border_and_flatten_helpers_match_reference(ours, ref):
                 for a, bb in zip(got[0], got[1]):
                     assert a.shape == bb.shape and np.array_equal(a, bb), (shape, (t, b, lft, r), typ)
                 assert np.array_equal(got[0][1], x)  # cutting the border off gives the source back
+    # channel padding of 3-D Mats (ncnn_copy_make_border_3d)
+    for api in (ours, ref):
+        api.lib.ncnn_copy_make_border_3d.restype = None
+        api.lib.ncnn_copy_make_border_3d.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, C.c_float, vp]
+    x = rng.uniform(-1, 1, (4, 6, 9)).astype(np.float32)
+    for (t, b, lft, r, f, bh) in [(1, 0, 2, 1, 2, 1), (0, 0, 0, 0, 1, 3), (2, 2, 0, 0, 0, 2)]:
+        for typ in (0, 1, 2):
+            got = []
+            for api in (ours, ref):
+                opt = api.strict_fp32_option()
+                src = api.mat_from_numpy(x)
+                dst = vp(api.lib.ncnn_mat_create())
+                api.lib.ncnn_copy_make_border_3d(src, dst, t, b, lft, r, f, bh, typ, -0.25, opt)
+                got.append(api.mat_to_numpy(dst).copy())
+                api.lib.ncnn_mat_destroy(src)
+                api.lib.ncnn_mat_destroy(dst)
+                api.lib.ncnn_option_destroy(opt)
+            assert got[0].shape == got[1].shape == (4 + f + bh, 6 + t + b, 9 + lft + r) and np.array_equal(got[0], got[1]), ((t, b, lft, r, f, bh), typ)
