@@ -1249,24 +1249,22 @@ void ncnn_copy_make_border_3d(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, i
 {
     make_border(*(const Mat*)_src, *(Mat*)_dst, top, bottom, left, right, front, behind, type, v, opt ? ((const Option*)opt)->blob_allocator : 0);
 }
-void ncnn_copy_cut_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, const ncnn_option_t opt)
+static void cut_border(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int front, int behind, Allocator* alloc)
 {
-    const Mat& src = *(const Mat*)_src;
-    Mat& dst = *(Mat*)_dst;
-    Allocator* alloc = opt ? ((const Option*)opt)->blob_allocator : 0;
-    if (src.empty() || src.elemsize != 4u || src.dims < 1 || src.dims > 3 || top < 0 || bottom < 0 || left < 0 || right < 0)
+    if (src.empty() || src.elemsize != 4u || src.dims < 1 || src.dims > 3 || top < 0 || bottom < 0 || left < 0 || right < 0 || front < 0 || behind < 0)
     {
         dst.release();
         return;
     }
     if (src.dims == 1) top = bottom = 0;
-    const int ow = src.w - left - right, oh = src.h - top - bottom;
-    if (ow <= 0 || oh <= 0)
+    if (src.dims != 3) front = behind = 0;
+    const int ow = src.w - left - right, oh = src.h - top - bottom, oc = src.c - front - behind;
+    if (ow <= 0 || oh <= 0 || oc <= 0)
     {
         dst.release();
         return;
     }
-    if (ow == src.w && oh == src.h)
+    if (ow == src.w && oh == src.h && oc == src.c)
     {
         dst = src;
         return;
@@ -1274,20 +1272,24 @@ void ncnn_copy_cut_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int b
     Mat out;
     if (src.dims == 1) out.create(ow, (size_t)4u, alloc);
     if (src.dims == 2) out.create(ow, oh, (size_t)4u, alloc);
-    if (src.dims == 3) out.create(ow, oh, src.c, (size_t)4u, alloc);
+    if (src.dims == 3) out.create(ow, oh, oc, (size_t)4u, alloc);
     if (out.empty())
     {
         dst.release();
         return;
     }
-    const int chs = src.dims == 3 ? src.c : 1;
+    const int chs = src.dims == 3 ? oc : 1;
     for (int q = 0; q < chs; q++)
     {
-        const float* sp = src.dims == 3 ? (const float*)src.channel(q) : (const float*)src.data;
+        const float* sp = src.dims == 3 ? (const float*)src.channel(q + front) : (const float*)src.data;
         float* dp = src.dims == 3 ? (float*)out.channel(q) : (float*)out.data;
         for (int y = 0; y < oh; y++) memcpy(dp + (size_t)y * ow, sp + (size_t)(y + top) * src.w + left, (size_t)ow * sizeof(float));
     }
     dst = out;
+}
+void ncnn_copy_cut_border(const ncnn_mat_t _src, ncnn_mat_t _dst, int top, int bottom, int left, int right, const ncnn_option_t opt)
+{
+    cut_border(*(const Mat*)_src, *(Mat*)_dst, top, bottom, left, right, 0, 0, opt ? ((const Option*)opt)->blob_allocator : 0);
 }
 void ncnn_flatten(const ncnn_mat_t _src, ncnn_mat_t* _dst, const ncnn_option_t opt)
 {
