@@ -54,6 +54,17 @@ int tc_pick_block_k(int inch)
 
 int tc_pick_block_n(int outch)
 {
+    // NCNN_B200_TC_BN caps the tile width (experiments on wave quantisation)
+    static int cap = -1;
+    if (cap < 0)
+    {
+        const char* e = getenv("NCNN_B200_TC_BN");
+        cap = e ? atoi(e) : 256;
+    }
+    if (outch > 128 && cap >= 256) return 256;
+    if (outch > 64 && cap >= 128) return 128;
+    if (outch > 32 && cap >= 64) return 64;
+    if (cap < 64) return 32;
     if (outch > 128) return 256;
     if (outch > 64) return 128;
     if (outch > 32) return 64;
@@ -202,6 +213,11 @@ int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int kernel_w
         tc_plan_destroy(plan);
         return -1;
     }
+    // CTA-pair variant (cta_group::2): each CTA of the pair stages block_n / 2 weight rows per k-block
+    plan->pair_ok = 0;
+    if (plan->block_k == 64 && plan->block_n >= 128 &&
+            encode_weights(&plan->tmap_b_half, elemtype, plan->w_packed, plan->Kp, outch, plan->block_k, plan->block_n / 2) == 0)
+        plan->pair_ok = 1;
     if (plan->rows_ok && encode_weights(&plan->tmap_b_rows, elemtype, plan->w_rows, plan->rows_Kp, outch, plan->rows_block_k, plan->block_n) != 0)
     {
         cudaFree(plan->w_rows);
@@ -378,12 +394,34 @@ int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
     return 1;
 }
 
-template<typename T, int BLOCK_N, int BLOCK_K, int AMODE>
+// launch with the programmatic-stream-serialization attribute AND a cluster of `cluster_x` CTAs (CTA pairs)
+template<typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_x, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned int)cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles, cudaStream_t stream)
 {
-    using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K>;
+    using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K, CG>;
     static_assert(Plan::stages_for(true) >= 2, "not enough shared memory for a 2-stage pipeline");
-    auto kern = tc::tc_gemm_kernel<T, BLOCK_N, BLOCK_K, AMODE>;
+    auto kern = tc::tc_gemm_kernel<T, BLOCK_N, BLOCK_K, AMODE, CG>;
     static bool attr_set = false;
     if (!attr_set)
     {
@@ -419,10 +457,39 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
         p.num_stages = Plan::stages_for(has_res);
         smem_bytes = Plan::total_for(has_res);
     }
-    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    // experiment knobs: NCNN_B200_TC_STAGES caps the ring depth, NCNN_B200_TC_GRID the number of CTAs
+    static int stage_cap = -1, grid_cap = -1;
+    if (stage_cap < 0)
+    {
+        const char* e = getenv("NCNN_B200_TC_STAGES");
+        stage_cap = e ? atoi(e) : 64;
+        e = getenv("NCNN_B200_TC_GRID");
+        grid_cap = e ? atoi(e) : 1 << 20;
+    }
+    if (p.num_stages > stage_cap && stage_cap >= 2) p.num_stages = stage_cap;
+    const int sms = sm_count() < grid_cap ? sm_count() : grid_cap;
+    if (CG == 2)
+    {
+        // `tiles` counts pair tiles: one cluster of two CTAs (the two SMs of a TPC) per tile, persistent
+        const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
+        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, p));
+        NC_LAUNCH_CHECK();
+        return 0;
+    }
+    int grid = (int)(tiles < sms ? tiles : sms);
     NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, p));
     NC_LAUNCH_CHECK();
     return 0;
+}
+
+// the CTA-pair instances: 64-element k-blocks, 128 / 256-wide tiles, tiled and im2col operands
+template<typename T, int AMODE>
+static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles, cudaStream_t stream)
+{
+    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, p, tiles, stream);
+    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, p, tiles, stream);
+    set_last_error_msg("tc_gemm: no CTA-pair kernel instance for this tile shape");
+    return -1;
 }
 
 template<typename T, int AMODE>
@@ -619,6 +686,25 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     p.div_outw = make_fastdiv((unsigned int)(c->outw > 0 ? c->outw : 1));
     p.div_chunks = make_fastdiv((unsigned int)p.chunks_per_row);
     p.div_outh = make_fastdiv((unsigned int)(c->outh > 0 ? c->outh : 1));
+
+    // CTA pairs (cta_group::2): halves the weight bytes every SM pulls through L2 -> SM, the limiter of the 128-row tiles
+    // (NCNN_B200_TC_PAIR=0 turns them off, =1 (default) uses them wherever an instance exists and the layer has >= 2 m-blocks)
+    static int pair_mode = -1;
+    if (pair_mode < 0)
+    {
+        const char* e = getenv("NCNN_B200_TC_PAIR");
+        pair_mode = e ? atoi(e) : 1;
+    }
+    const bool use_pair = pair_mode != 0 && plan->pair_ok && (amode == tc::A_TILED || amode == tc::A_IM2COL) && block_k == 64 && M > tc::BLOCK_M;
+    if (use_pair)
+    {
+        const long long pair_tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M + 1) / 2 * ((plan->outch + plan->block_n - 1) / plan->block_n);
+        if (plan->elemtype == NCNN_CUDA_BF16)
+            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream)
+                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream);
+        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream)
+                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream);
+    }
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row
                                : (amode == tc::A_SHIFT ? (long long)c->n * p.sh_tiles_y * p.sh_chunks_x : (M + tc::BLOCK_M - 1) / tc::BLOCK_M);

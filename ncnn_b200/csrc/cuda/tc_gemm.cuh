@@ -208,6 +208,63 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
                  : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants.  A pair of CTAs on the two SMs of one TPC works on one 256-row tile: each CTA stages
+// its own 128 rows of A and HALF of the B tile, one tcgen05.mma.cta_group::2 issued by the leader (cluster rank 0) reads
+// both halves from both shared memories (so every SM receives only half of the weights through L2 -> SM), each CTA's TMEM
+// holds its own 128 accumulator rows.  The pair's TMA loads complete on the LEADER's full barrier; the MMA's commits are
+// multicast to the barriers of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// the shared::cluster address of `addr` (a shared address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// arrive on an mbarrier of another CTA of the cluster (shared::cluster address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
+{
+    // default (CTA-scope) semantics: a cluster-scope release compiles to MEMBAR.ALL.GPU, which waits for every store the
+    // warp has in flight -- the epilogue's output stores -- before each arrive (measured: -15..-40 % on the HBM-bound layers).
+    // The hand-over only has to order this warp's TMEM reads (tcgen05.wait::ld + fence::before_thread_sync) before the MMA.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_im2col_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c, int w, int h, int n, uint16_t off_w,
+                                                       uint16_t off_h)
+{
+    asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+                 : "memory");
+}
+
 // contiguous global -> shared bulk copy (16-byte granularity), completion on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
@@ -254,6 +311,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before()
 {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,6 +342,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// commit of the pair's MMAs, arriving on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -398,11 +484,11 @@ enum
     A_SHIFT = 3
 };
 
-template<int BLOCK_N, int BLOCK_K>
+template<int BLOCK_N, int BLOCK_K, int CG = 1>
 struct SmemPlan
 {
     static constexpr int a_bytes = BLOCK_M * BLOCK_K * 2;
-    static constexpr int b_bytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int b_bytes = (BLOCK_N / CG) * BLOCK_K * 2; // a CTA of a pair (CG = 2) stages half of the B tile
     static constexpr int stage_bytes = a_bytes + b_bytes; // both multiples of 1024 for the tile sizes used
     // The accumulator tile leaves the SM straight from registers (one output pixel per lane, 32-byte vector stores), so
     // the only epilogue staging is the fused residual: it arrives by TMA in EPI_N-column slots, a ring of kResSlots.
@@ -515,11 +601,16 @@ static __device__ __noinline__ float apply_activation_call(float v, int type, fl
 // The residual tensor map is rank 3: (channels, columns, rows)
 //   A_TILED / A_IM2COL : (C, M, 1)            tile rows m0 .. m0+127 are consecutive output pixels
 //   A_ROWS             : (C, outw, n*outh)    tile rows are 128 consecutive columns of one output row
-template<typename T, int BLOCK_N, int BLOCK_K, int AMODE>
+//
+// CG = 2 (A_TILED / A_IM2COL): launched as clusters of two CTAs; tile = 256 output pixels x BLOCK_N, CTA `rank` of the pair
+// owns m-block 2 * pair + rank (A rows, accumulator rows, epilogue, residual) and stages rows [rank * BLOCK_N / 2, +BLOCK_N / 2)
+// of the B tile.  Only the leader's MMA warp runs.
+template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_res, const Params p)
 {
-    using Plan = SmemPlan<BLOCK_N, BLOCK_K>;
+    static_assert(CG == 1 || AMODE == A_TILED || AMODE == A_IM2COL, "CTA pairs: tiled and im2col operand modes only");
+    using Plan = SmemPlan<BLOCK_N, BLOCK_K, CG>;
     constexpr int EPI_N = Plan::EPI_N;
     constexpr int NCHUNK = BLOCK_N / EPI_N;    // residual slots per tile
     constexpr int SUBS = EPI_N / 32;           // 32-column TMEM loads per slot (1 or 2)
@@ -565,7 +656,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         num_m_blocks = (int)(p.M / ((long long)p.outw * p.outh)) * p.sh_tiles_y * p.sh_chunks_x; // images * row groups * column chunks
     else
         num_m_blocks = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
-    const int num_tiles = num_m_blocks * num_n_blocks;
+    // CTA pairs walk (pair of m-blocks, n-block) tiles; this CTA's m-block inside the pair is its cluster rank
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = (CG == 2 ? (num_m_blocks + 1) / 2 : num_m_blocks) * num_n_blocks;
 
     if (warp == 0 && lane == 0)
     {
@@ -583,7 +678,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < kAccStages; i++)
         {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[i]), kEpilogueWarps);
+            mbar_init(smem_u32(&tmem_empty_bar[i]), kEpilogueWarps * CG); // the leader's barrier counts the epilogue warps of both CTAs
         }
         mbar_init(smem_u32(bres_bar), 1);
         for (int i = 0; i < kResSlots; i++)
@@ -597,7 +692,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     if (warp == 2)
     {
-        tmem_alloc(smem_u32(tmem_base_slot), kTmemCols);
+        if (CG == 2)
+            tmem_alloc_cg2(smem_u32(tmem_base_slot), kTmemCols);
+        else
+            tmem_alloc(smem_u32(tmem_base_slot), kTmemCols);
     }
     // the layer's (padded) bias vector: resident in shared memory when it fits
     const int bias_count = ((p.N + BLOCK_N - 1) / BLOCK_N) * BLOCK_N;
@@ -605,7 +703,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (bias_in_smem)
         for (int i = threadIdx.x; i < bias_count; i += kNumThreads) smem_bias[i] = __ldg(p.bias + i);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2)
+        cluster_sync_all(); // the peer's barriers must be initialised before any remote arrive / TMA completion reaches them
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
     // everything above touched only constants (bias, descriptors) and on-chip state; activations of the previous layer are
@@ -625,6 +726,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t rphase = 0;
             const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
             const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+            const uint32_t full0_leader = CG == 2 ? mapa_shared(full0, 0) : full0;
             if (AMODE == A_ROWS || AMODE == A_SHIFT)
             {
                 // the layer's weights (one n-block, every k-block): resident behind the A ring for the whole kernel
@@ -633,13 +735,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_expect_tx(bb, (uint32_t)(nres * Plan::b_bytes));
                 for (int kb = 0; kb < nres; kb++) tma_load_2d(smem_u32(smem_res) + kb * Plan::b_bytes, &tmap_b, bb, kb * BLOCK_K, 0);
             }
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step)
             {
-                const int m_blk = fast_div(tile, p.div_n_blocks);
-                const int n_blk = tile - m_blk * num_n_blocks;
-                const int n_coord = n_blk * BLOCK_N;
+                const int m_grp = fast_div(tile, p.div_n_blocks);
+                const int n_blk = tile - m_grp * num_n_blocks;
+                const int m_blk = CG == 2 ? 2 * m_grp + (int)cta_rank : m_grp;
+                const int n_coord = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG); // this CTA's rows of the B tile
                 int base_w = 0, base_h = 0, base_n = 0;
-                int m0 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
+                int m0 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host (a pair's odd m-block past the end loads zeros)
                 if (AMODE == A_IM2COL)
                 {
                     base_n = fast_div(m0, p.div_opix);
@@ -659,10 +762,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 auto load_kblock = [&](int kcoord_b, auto&& issue_a) {
                     mbar_wait(empty0 + stage * 8, phase ^ 1);
+                    // pair: both CTAs' loads complete on the LEADER's barrier, armed by the leader for the bytes of both
                     const uint32_t fb = full0 + stage * 8;
-                    mbar_expect_tx(fb, Plan::stage_bytes);
+                    if (CG == 1 || cta_rank == 0) mbar_expect_tx(fb, Plan::stage_bytes * CG);
                     issue_a(smem_a0 + stage * Plan::a_bytes, fb);
-                    tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord_b, n_coord);
+                    if (CG == 2)
+                        tma_load_2d_cg2(smem_b0 + stage * Plan::b_bytes, &tmap_b, full0_leader + stage * 8, kcoord_b, n_coord);
+                    else
+                        tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord_b, n_coord);
                     if (++stage == kStages)
                     {
                         stage = 0;
@@ -697,7 +804,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int kx = 0; kx < p.taps_w; kx++)
                             for (int cb = 0; cb < p.cblocks; cb++, kcoord += BLOCK_K)
                                 load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) {
-                                    tma_load_im2col_4d(dst, &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
+                                    if (CG == 2)
+                                        tma_load_im2col_4d_cg2(dst, &tmap_a, full0_leader + (fb - full0), cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w),
+                                                               (uint16_t)(ky * p.dil_h));
+                                    else
+                                        tma_load_im2col_4d(dst, &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
                                 });
                 }
                 else if (AMODE == A_ROWS)
@@ -720,7 +831,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 else
                 {
                     for (int kb = 0, kcoord = 0; kb < p.num_k_blocks; kb++, kcoord += BLOCK_K)
-                        load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) { tma_load_2d(dst, &tmap_a, fb, kcoord, m0); });
+                        load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) {
+                            if (CG == 2)
+                                tma_load_2d_cg2(dst, &tmap_a, full0_leader + (fb - full0), kcoord, m0);
+                            else
+                                tma_load_2d(dst, &tmap_a, fb, kcoord, m0);
+                        });
                 }
                 if (has_res)
                 {
@@ -760,7 +876,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================== MMA issuer =====================
         // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform registers); one elected
         // lane issues tcgen05.mma / tcgen05.commit.
-        constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M, BLOCK_N);
+        // pair: one 256 x BLOCK_N MMA per K step, issued by the leader only (the peer's MMA warp idles)
+        constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M * CG, BLOCK_N);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -769,7 +886,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
         const uint64_t adesc0 = make_smem_desc<BLOCK_K>(smem_a0), bdesc0 = make_smem_desc<BLOCK_K>(smem_b0);
         if (AMODE == A_ROWS || AMODE == A_SHIFT) mbar_wait(smem_u32(bres_bar), 0);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int tile = tile_first; tile < (CG == 2 && cta_rank != 0 ? 0 : num_tiles); tile += tile_step)
         {
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
             tc_fence_after();
@@ -849,9 +966,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         const uint64_t adesc = adesc0 + (uint64_t)((uint32_t)(stage * Plan::a_bytes) >> 4);
                         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)(stage * Plan::b_bytes) >> 4);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; k++) umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
-                        umma_commit(empty0 + stage * 8); // frees the smem slot when these MMAs retire
-                        if (kb == p.num_k_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                        for (int k = 0; k < BLOCK_K / 16; k++)
+                        {
+                            if (CG == 2)
+                                umma_f16_cg2(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                            else
+                                umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        // frees the smem slot (of both CTAs of a pair) when these MMAs retire
+                        if (CG == 2)
+                        {
+                            umma_commit_cg2(empty0 + stage * 8);
+                            if (kb == p.num_k_blocks - 1) umma_commit_cg2(smem_u32(&tmem_full_bar[acc]));
+                        }
+                        else
+                        {
+                            umma_commit(empty0 + stage * 8);
+                            if (kb == p.num_k_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                        }
                     }
                     __syncwarp();
                     if (++stage == kStages)
@@ -888,11 +1020,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int sw_row = (EPI_CHUNKS16 == 8) ? (row & 7) : ((row >> 1) & 3);
         const bool v8ok = p.v8_ok != 0;
         const int N = p.N;
+        // the MMA warp that reuses the accumulator stage is the leader's: a pair's epilogue warps all arrive there
+        const uint32_t tmem_empty_leader = CG == 2 ? mapa_shared(smem_u32(tmem_empty_bar), 0) : smem_u32(tmem_empty_bar);
+        auto arrive_tmem_empty = [&](int a) {
+            if (CG == 2)
+                mbar_arrive_cluster(tmem_empty_leader + a * 8);
+            else
+                mbar_arrive(tmem_empty_leader + a * 8);
+        };
 
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step)
         {
-            const int m_blk = fast_div(tile, p.div_n_blocks);
-            const int n_blk = tile - m_blk * num_n_blocks;
+            const int m_grp = fast_div(tile, p.div_n_blocks);
+            const int n_blk = tile - m_grp * num_n_blocks;
+            const int m_blk = CG == 2 ? 2 * m_grp + (int)cta_rank : m_grp;
             const int n0 = n_blk * BLOCK_N;
             long long pix;
             bool row_ok;
@@ -965,7 +1106,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // nothing to read for this half: hand the accumulator stage back right away
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+                if (lane == 0) arrive_tmem_empty(acc);
                 // single-chunk tiles count all eight warps as readers of the residual slot
                 if (has_res && NCHUNK == 1 && SUBS == 2 && lane == 0) mbar_arrive(smem_u32(&res_empty_bar[slots_seen % kResSlots]));
             }
@@ -1001,7 +1142,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     // every column group of this half sits in registers: the accumulator stage can be overwritten
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+                    if (lane == 0) arrive_tmem_empty(acc);
                 }
                 float v[32];
 #pragma unroll
@@ -1089,11 +1230,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
+    __syncwarp(); // (warp 0 / warp 1: the single working lane rejoins its warp before the aligned barrier)
+    if (CG == 2)
+        cluster_sync_all(); // neither CTA may exit (or free its TMEM) while the pair's MMAs / remote arrivals are in flight
+    else
+        __syncthreads();
     if (warp == 2)
     {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2)
+            tmem_dealloc_cg2(tmem_base, kTmemCols);
+        else
+            tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -1112,6 +1260,8 @@ struct TcPlan
     void* w_packed;    // device, [outch][Kp] 16-bit
     float* bias_pad;   // device, [outch_pad + 256] fp32 (zeros when no bias)
     CUtensorMap tmap_b;
+    CUtensorMap tmap_b_half; // box of block_n / 2 rows: what one CTA of a cta_group::2 pair stages (valid when pair_ok)
+    int pair_ok;
     // A_ROWS variant (small-channel stems), valid when rows_ok
     int rows_ok;
     int rows_cp, rows_wp, rows_shift; // channels per pixel of the padded copy, window width in pixels, zero taps on the left

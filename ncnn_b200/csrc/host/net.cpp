@@ -313,17 +313,114 @@ int Net::load_param_text(const std::string& text)
     return 0;
 }
 
+// Text params arrive through DataReader::scan, exactly the formats the reference pulls them with (src/net.cpp:1305-1400
+// SCAN_VALUE, src/paramdict.cpp:263-480): a memory reader has no length to drain with read(), and a custom reader may
+// implement scan() only.  The tokens are re-assembled into the line form load_param_text parses.
+static bool scan_param_value(const DataReader& dr, int id, std::string& out)
+{
+    char tmp[32];
+    if (id <= -23300)
+    {
+        // old style array: -233xx=len,v0,v1,...
+        int len = 0;
+        if (dr.scan("%d", &len) != 1 || len < 0) return false;
+        sprintf(tmp, "%d", len);
+        out += tmp;
+        for (int j = 0; j < len; j++)
+        {
+            char v[16];
+            if (dr.scan(",%15[^,\n ]", v) != 1) return false;
+            out += ',';
+            out += v;
+        }
+        return true;
+    }
+    char v[16];
+    if (dr.scan("%15[^,\n ]", v) != 1) return false;
+    out += v;
+    const bool is_string = v[0] == '"' || isalpha((unsigned char)v[0]);
+    if (is_string)
+    {
+        // the rest of a string longer than the first 15 characters
+        char rest[256];
+        size_t n = strlen(v);
+        if (v[0] == '"')
+        {
+            if (n < 2 || v[n - 1] != '"')
+            {
+                if (dr.scan("%255[^\"\n]\"", rest) == 1) out += rest;
+                out += '"';
+            }
+        }
+        else if (dr.scan("%255[^\n ]", rest) == 1)
+            out += rest;
+        return true;
+    }
+    // new style array: v0,v1,...
+    char comma[4];
+    while (dr.scan("%1[,]", comma) == 1)
+    {
+        if (dr.scan("%15[^,\n ]", v) != 1) return false;
+        out += ',';
+        out += v;
+    }
+    return true;
+}
+
 int Net::load_param(const DataReader& dr)
 {
-    // pull the whole text through the reader, then parse it line by line
-    std::string text;
-    char buf[4096];
-    for (;;)
+    int magic = 0, layer_count = 0, blob_count = 0;
+    if (dr.scan("%d", &magic) != 1 || dr.scan("%d", &layer_count) != 1 || dr.scan("%d", &blob_count) != 1)
     {
-        size_t n = dr.read(buf, sizeof(buf));
-        if (n == 0) break;
-        text.append(buf, n);
-        if (n < sizeof(buf)) break;
+        NCNN_LOGE("parse magic / layer_count / blob_count failed");
+        return -1;
+    }
+    if (layer_count <= 0 || blob_count <= 0 || layer_count > (1 << 24))
+    {
+        NCNN_LOGE("invalid layer_count or blob_count");
+        return -1;
+    }
+    char tmp[64];
+    sprintf(tmp, "%d\n%d %d\n", magic, layer_count, blob_count);
+    std::string text(tmp);
+    for (int i = 0; i < layer_count; i++)
+    {
+        char layer_type[256], layer_name[256];
+        int bottom_count = 0, top_count = 0;
+        if (dr.scan("%255s", layer_type) != 1 || dr.scan("%255s", layer_name) != 1 || dr.scan("%d", &bottom_count) != 1 || dr.scan("%d", &top_count) != 1
+                || bottom_count < 0 || top_count < 0)
+        {
+            NCNN_LOGE("parse layer %d failed", i);
+            return -1;
+        }
+        text += layer_type;
+        text += ' ';
+        text += layer_name;
+        sprintf(tmp, " %d %d", bottom_count, top_count);
+        text += tmp;
+        for (int j = 0; j < bottom_count + top_count; j++)
+        {
+            char blob_name[256];
+            if (dr.scan("%255s", blob_name) != 1)
+            {
+                NCNN_LOGE("parse blob name of layer %d failed", i);
+                return -1;
+            }
+            text += ' ';
+            text += blob_name;
+        }
+        int id = 0;
+        while (dr.scan("%d=", &id) == 1)
+        {
+            sprintf(tmp, " %d=", id);
+            text += tmp;
+            if (!scan_param_value(dr, id, text))
+            {
+                NCNN_LOGE("ParamDict read value failed (layer %d id %d)", i, id);
+                return -1;
+            }
+        }
+        text += '\n';
     }
     return load_param_text(text);
 }

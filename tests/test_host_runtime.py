@@ -128,6 +128,64 @@ def test_load_param_benchmark_set_matches_reference(ours, ref, path):
         assert seen[0] == seen[1] and seen[0][0] and seen[0][1]
 
 
+def _graph_signature(L, net):
+    ins = [L.ncnn_net_get_input_name(net, i) for i in range(L.ncnn_net_get_input_count(net))]
+    outs = [L.ncnn_net_get_output_name(net, i) for i in range(L.ncnn_net_get_output_count(net))]
+    return ins, outs
+
+
+@pytest.mark.parametrize("name", ["squeezenet_v1_1", "mobilenet_v2", "resnet50", "vgg16", "yolov8s"])
+def test_load_param_through_datareader_scan(ours, ref, name):
+    """text params come through DataReader::scan (src/net.cpp:1305 SCAN_VALUE, src/paramdict.cpp:263-480): (1) the stock memory
+    reader, which has no length to drain with read(); (2) a custom C-API reader that implements scan() ONLY (read returns 0).
+    Both must give the graph ncnn_net_load_param_memory gives, in the product as in the reference."""
+    from ncnn_b200 import capi
+    text = modelzoo.param_text(name).encode() + b"\0"
+    libc = C.CDLL(None)
+    for api in (ours, ref):
+        L = api.lib
+        net = L.ncnn_net_create()
+        assert L.ncnn_net_load_param_memory(net, text) == 0
+        want = _graph_signature(L, net)
+        L.ncnn_net_destroy(net)
+
+        # (1) ncnn_datareader_create_from_memory
+        buf = C.create_string_buffer(text, len(text))
+        cursor = C.c_void_p(C.addressof(buf))
+        L.ncnn_datareader_create_from_memory.restype = C.POINTER(capi._DataReader)
+        L.ncnn_datareader_create_from_memory.argtypes = [C.POINTER(C.c_void_p)]
+        dr = L.ncnn_datareader_create_from_memory(C.byref(cursor))
+        net = L.ncnn_net_create()
+        assert L.ncnn_net_load_param_datareader(net, dr) == 0
+        assert _graph_signature(L, net) == want
+        assert 0 < cursor.value - C.addressof(buf) <= len(text)  # the reader consumed the text and stopped inside it
+        L.ncnn_net_destroy(net)
+        L.ncnn_datareader_destroy(dr)
+
+        # (2) scan-only custom reader (sscanf with %n over a Python-held buffer, as DataReaderFromMemory::scan does)
+        state = {"pos": 0}
+        base = C.addressof(buf)
+
+        def _scan(dr_, fmt, out):
+            consumed = C.c_int(0)
+            n = libc.sscanf(C.c_void_p(base + state["pos"]), fmt + b"%n", C.c_void_p(out), C.byref(consumed))
+            state["pos"] += consumed.value
+            return n if consumed.value > 0 else 0
+
+        def _read(dr_, b, size):
+            return 0
+
+        dr = L.ncnn_datareader_create()
+        scan_cb, read_cb = capi._SCAN_FN(_scan), capi._READ_FN(_read)
+        dr.contents.scan = scan_cb
+        dr.contents.read = read_cb
+        net = L.ncnn_net_create()
+        assert L.ncnn_net_load_param_datareader(net, dr) == 0
+        assert _graph_signature(L, net) == want
+        L.ncnn_net_destroy(net)
+        L.ncnn_datareader_destroy(dr)
+
+
 def test_load_param_rejects_garbage(ours):
     L = ours.lib
     for bad in (b"", b"1234\n1 1\n", b"7767517\n2 2\nInput data 0 1 data\n"):
