@@ -657,7 +657,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     else
         num_m_blocks = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     // CTA pairs walk (pair of m-blocks, n-block) tiles; this CTA's m-block inside the pair is its cluster rank
-    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = CG == 2 ? (blockIdx.x & 1u) : 0u; // = %cluster_ctarank of a (2,1,1) cluster, as a value ptxas knows to be warp-uniform
     const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int num_tiles = (CG == 2 ? (num_m_blocks + 1) / 2 : num_m_blocks) * num_n_blocks;
@@ -715,157 +715,182 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     if (warp == 0)
     {
-        if (lane == 0)
+        // ===================== TMA producer =====================
+        // The whole warp walks the loops (warp-uniform control flow: tile / k-block coordinates and shared-memory addresses
+        // live in uniform registers, which is where the TMA instructions take their operands from); one elected lane issues
+        // the arrive.expect_tx and the copies.  Issued from a `lane == 0` branch instead, every copy costs an ELECT /
+        // R2UR.BROADCAST loop over the "divergent" lanes -- measured: the producer then never finds a free slot to wait for,
+        // i.e. ITS instruction stream paces the 64-cycle MMAs of the 128-wide tiles.  No integer division in the loop: tiles
+        // are decoded with multiply-shift, k-blocks by nested counters.
+        int stage = 0;
+        uint32_t phase = 0;
+        int rslot = 0;
+        uint32_t rphase = 0;
+        const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
+        const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        const uint32_t full0_leader = CG == 2 ? mapa_shared(full0, 0) : full0;
+        if (AMODE == A_ROWS || AMODE == A_SHIFT)
         {
-            // ===================== TMA producer =====================
-            // One lane issues every load of the CTA.  Its instruction stream is the critical path of small-K tiles, so the
-            // loop carries no integer division: tiles are decoded with multiply-shift, k-blocks by nested counters.
-            int stage = 0;
-            uint32_t phase = 0;
-            int rslot = 0;
-            uint32_t rphase = 0;
-            const uint32_t smem_a0 = smem_u32(smem_a), smem_b0 = smem_u32(smem_b);
-            const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
-            const uint32_t full0_leader = CG == 2 ? mapa_shared(full0, 0) : full0;
-            if (AMODE == A_ROWS || AMODE == A_SHIFT)
+            // the layer's weights (one n-block, every k-block): resident behind the A ring for the whole kernel
+            const int nres = AMODE == A_ROWS ? p.taps_h : p.num_k_blocks;
+            const uint32_t bb = smem_u32(bres_bar);
+            if (elect_one())
             {
-                // the layer's weights (one n-block, every k-block): resident behind the A ring for the whole kernel
-                const int nres = AMODE == A_ROWS ? p.taps_h : p.num_k_blocks;
-                const uint32_t bb = smem_u32(bres_bar);
                 mbar_expect_tx(bb, (uint32_t)(nres * Plan::b_bytes));
                 for (int kb = 0; kb < nres; kb++) tma_load_2d(smem_u32(smem_res) + kb * Plan::b_bytes, &tmap_b, bb, kb * BLOCK_K, 0);
             }
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step)
+            __syncwarp();
+        }
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step)
+        {
+            const int m_grp = fast_div(tile, p.div_n_blocks);
+            const int n_blk = tile - m_grp * num_n_blocks;
+            const int m_blk = CG == 2 ? 2 * m_grp + (int)cta_rank : m_grp;
+            const int n_coord = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG); // this CTA's rows of the B tile
+            int base_w = 0, base_h = 0, base_n = 0;
+            int m0 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host (a pair's odd m-block past the end loads zeros)
+            if (AMODE == A_IM2COL)
             {
-                const int m_grp = fast_div(tile, p.div_n_blocks);
-                const int n_blk = tile - m_grp * num_n_blocks;
-                const int m_blk = CG == 2 ? 2 * m_grp + (int)cta_rank : m_grp;
-                const int n_coord = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / CG); // this CTA's rows of the B tile
-                int base_w = 0, base_h = 0, base_n = 0;
-                int m0 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host (a pair's odd m-block past the end loads zeros)
-                if (AMODE == A_IM2COL)
+                base_n = fast_div(m0, p.div_opix);
+                const int rem = m0 - base_n * (int)p.div_opix.d;
+                const int oy = fast_div(rem, p.div_outw);
+                const int ox = rem - oy * p.outw;
+                base_w = ox * p.stride_w - p.pad_left;
+                base_h = oy * p.stride_h - p.pad_top;
+            }
+            else if (AMODE == A_ROWS)
+            {
+                const int row = fast_div(m_blk, p.div_chunks); // img * outh + oy
+                const int chunk = m_blk - row * p.chunks_per_row;
+                base_n = fast_div(row, p.div_outh);
+                base_h = (row - base_n * p.outh) * p.stride_h; // physical row of filter row 0 (top padding is materialised)
+                base_w = chunk * BLOCK_M;                      // first output column of the chunk
+            }
+            auto advance_stage = [&]() {
+                if (++stage == kStages)
                 {
-                    base_n = fast_div(m0, p.div_opix);
-                    const int rem = m0 - base_n * (int)p.div_opix.d;
-                    const int oy = fast_div(rem, p.div_outw);
-                    const int ox = rem - oy * p.outw;
-                    base_w = ox * p.stride_w - p.pad_left;
-                    base_h = oy * p.stride_h - p.pad_top;
+                    stage = 0;
+                    phase ^= 1;
                 }
-                else if (AMODE == A_ROWS)
+            };
+            if (AMODE == A_SHIFT)
+            {
+                // tile = (image, row group, column chunk); one box per 64-channel slab
+                const int t1 = fast_div(m_blk, p.div_sh_chunks_x);
+                const int cx = m_blk - t1 * p.sh_chunks_x;
+                const int img = fast_div(t1, p.div_sh_tiles_y);
+                const int ty = t1 - img * p.sh_tiles_y;
+                const int w0 = cx * p.sh_colstep - p.pad_left, h0 = ty * p.sh_rows - p.pad_top;
+                for (int cb = 0; cb < p.cblocks; cb++)
                 {
-                    const int row = fast_div(m_blk, p.div_chunks); // img * outh + oy
-                    const int chunk = m_blk - row * p.chunks_per_row;
-                    base_n = fast_div(row, p.div_outh);
-                    base_h = (row - base_n * p.outh) * p.stride_h; // physical row of filter row 0 (top padding is materialised)
-                    base_w = chunk * BLOCK_M;                      // first output column of the chunk
-                }
-                auto load_kblock = [&](int kcoord_b, auto&& issue_a) {
                     mbar_wait(empty0 + stage * 8, phase ^ 1);
-                    // pair: both CTAs' loads complete on the LEADER's barrier, armed by the leader for the bytes of both
-                    const uint32_t fb = full0 + stage * 8;
-                    if (CG == 1 || cta_rank == 0) mbar_expect_tx(fb, Plan::stage_bytes * CG);
-                    issue_a(smem_a0 + stage * Plan::a_bytes, fb);
-                    if (CG == 2)
-                        tma_load_2d_cg2(smem_b0 + stage * Plan::b_bytes, &tmap_b, full0_leader + stage * 8, kcoord_b, n_coord);
-                    else
-                        tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord_b, n_coord);
-                    if (++stage == kStages)
+                    if (elect_one())
                     {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                };
-                if (AMODE == A_SHIFT)
-                {
-                    // tile = (image, row group, column chunk); one box per 64-channel slab
-                    const int t1 = fast_div(m_blk, p.div_sh_chunks_x);
-                    const int cx = m_blk - t1 * p.sh_chunks_x;
-                    const int img = fast_div(t1, p.div_sh_tiles_y);
-                    const int ty = t1 - img * p.sh_tiles_y;
-                    const int w0 = cx * p.sh_colstep - p.pad_left, h0 = ty * p.sh_rows - p.pad_top;
-                    for (int cb = 0; cb < p.cblocks; cb++)
-                    {
-                        mbar_wait(empty0 + stage * 8, phase ^ 1);
                         const uint32_t fb = full0 + stage * 8;
                         mbar_expect_tx(fb, (uint32_t)p.sh_box_bytes);
                         tma_load_4d(smem_a0 + stage * p.sh_stage_bytes, &tmap_a, fb, cb * BLOCK_K, w0, h0, img);
-                        if (++stage == kStages)
-                        {
-                            stage = 0;
-                            phase ^= 1;
-                        }
                     }
+                    advance_stage();
                 }
-                else if (AMODE == A_IM2COL)
+            }
+            else if (AMODE == A_IM2COL)
+            {
+                int kcoord = 0;
+                for (int ky = 0; ky < p.taps_h; ky++)
+                    for (int kx = 0; kx < p.taps_w; kx++)
+                        for (int cb = 0; cb < p.cblocks; cb++, kcoord += BLOCK_K)
+                        {
+                            mbar_wait(empty0 + stage * 8, phase ^ 1);
+                            if (elect_one())
+                            {
+                                // pair: both CTAs' loads complete on the LEADER's barrier, armed by the leader for the bytes of both
+                                const uint32_t fb = full0 + stage * 8;
+                                if (CG == 1 || cta_rank == 0) mbar_expect_tx(fb, Plan::stage_bytes * CG);
+                                if (CG == 2)
+                                {
+                                    tma_load_im2col_4d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_a, full0_leader + stage * 8, cb * BLOCK_K, base_w, base_h, base_n,
+                                                           (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
+                                    tma_load_2d_cg2(smem_b0 + stage * Plan::b_bytes, &tmap_b, full0_leader + stage * 8, kcoord, n_coord);
+                                }
+                                else
+                                {
+                                    tma_load_im2col_4d(smem_a0 + stage * Plan::a_bytes, &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w),
+                                                       (uint16_t)(ky * p.dil_h));
+                                    tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord, n_coord);
+                                }
+                            }
+                            advance_stage();
+                        }
+            }
+            else if (AMODE == A_ROWS)
+            {
+                // one stage = the tile's kh row segments (output column j's window starts 16*j bytes into each): one barrier
+                // round trip per tile, kh contiguous bulk copies
+                const unsigned char* src = p.rows_src + (long long)base_n * p.rows_img_bytes + (long long)base_h * p.rows_row_bytes + (long long)base_w * 16;
+                mbar_wait(empty0 + stage * 8, phase ^ 1);
+                if (elect_one())
                 {
-                    int kcoord = 0;
-                    for (int ky = 0; ky < p.taps_h; ky++)
-                        for (int kx = 0; kx < p.taps_w; kx++)
-                            for (int cb = 0; cb < p.cblocks; cb++, kcoord += BLOCK_K)
-                                load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) {
-                                    if (CG == 2)
-                                        tma_load_im2col_4d_cg2(dst, &tmap_a, full0_leader + (fb - full0), cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w),
-                                                               (uint16_t)(ky * p.dil_h));
-                                    else
-                                        tma_load_im2col_4d(dst, &tmap_a, fb, cb * BLOCK_K, base_w, base_h, base_n, (uint16_t)(kx * p.dil_w), (uint16_t)(ky * p.dil_h));
-                                });
-                }
-                else if (AMODE == A_ROWS)
-                {
-                    // one stage = the tile's kh row segments (output column j's window starts 16*j bytes into each): one barrier
-                    // round trip per tile, kh contiguous bulk copies
-                    const unsigned char* src = p.rows_src + (long long)base_n * p.rows_img_bytes + (long long)base_h * p.rows_row_bytes + (long long)base_w * 16;
-                    mbar_wait(empty0 + stage * 8, phase ^ 1);
                     const uint32_t fb = full0 + stage * 8;
                     mbar_expect_tx(fb, (uint32_t)(p.taps_h * p.rows_seg_bytes));
                     uint32_t dst = smem_a0 + stage * p.rows_stage_bytes;
                     for (int ky = 0; ky < p.taps_h; ky++, src += (long long)p.dil_h * p.rows_row_bytes, dst += p.rows_seg_pitch)
                         bulk_load(dst, src, (uint32_t)p.rows_seg_bytes, fb);
-                    if (++stage == kStages)
+                }
+                advance_stage();
+            }
+            else
+            {
+                for (int kb = 0, kcoord = 0; kb < p.num_k_blocks; kb++, kcoord += BLOCK_K)
+                {
+                    mbar_wait(empty0 + stage * 8, phase ^ 1);
+                    if (elect_one())
                     {
-                        stage = 0;
-                        phase ^= 1;
+                        const uint32_t fb = full0 + stage * 8;
+                        if (CG == 1 || cta_rank == 0) mbar_expect_tx(fb, Plan::stage_bytes * CG);
+                        if (CG == 2)
+                        {
+                            tma_load_2d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_a, full0_leader + stage * 8, kcoord, m0);
+                            tma_load_2d_cg2(smem_b0 + stage * Plan::b_bytes, &tmap_b, full0_leader + stage * 8, kcoord, n_coord);
+                        }
+                        else
+                        {
+                            tma_load_2d(smem_a0 + stage * Plan::a_bytes, &tmap_a, fb, kcoord, m0);
+                            tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord, n_coord);
+                        }
                     }
+                    advance_stage();
+                }
+            }
+            if (has_res)
+            {
+                // the fused residual of this tile, EPI_N columns per ring slot; issued after the tile's operand loads so
+                // that waiting for a free slot (the epilogue is at most one tile behind) never delays the MMA feed
+                int c1, c2;
+                if (AMODE == A_ROWS)
+                {
+                    c2 = fast_div(m_blk, p.div_chunks);
+                    c1 = (m_blk - c2 * p.chunks_per_row) * BLOCK_M;
                 }
                 else
                 {
-                    for (int kb = 0, kcoord = 0; kb < p.num_k_blocks; kb++, kcoord += BLOCK_K)
-                        load_kblock(kcoord, [&](uint32_t dst, uint32_t fb) {
-                            if (CG == 2)
-                                tma_load_2d_cg2(dst, &tmap_a, full0_leader + (fb - full0), kcoord, m0);
-                            else
-                                tma_load_2d(dst, &tmap_a, fb, kcoord, m0);
-                        });
+                    c1 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
+                    c2 = 0;
                 }
-                if (has_res)
+                for (int cc = 0; cc < NCHUNK; cc++)
                 {
-                    // the fused residual of this tile, EPI_N columns per ring slot; issued after the tile's operand loads so
-                    // that waiting for a free slot (the epilogue is at most one tile behind) never delays the MMA feed
-                    int c1, c2;
-                    if (AMODE == A_ROWS)
+                    const int c0 = n_blk * BLOCK_N + cc * EPI_N;
+                    if (c0 >= p.N) break;
+                    mbar_wait(smem_u32(&res_empty_bar[rslot]), rphase ^ 1);
+                    if (elect_one())
                     {
-                        c2 = fast_div(m_blk, p.div_chunks);
-                        c1 = (m_blk - c2 * p.chunks_per_row) * BLOCK_M;
-                    }
-                    else
-                    {
-                        c1 = m_blk * BLOCK_M; // < 2^31: M is bounded by the host
-                        c2 = 0;
-                    }
-                    for (int cc = 0; cc < NCHUNK; cc++)
-                    {
-                        const int c0 = n_blk * BLOCK_N + cc * EPI_N;
-                        if (c0 >= p.N) break;
-                        mbar_wait(smem_u32(&res_empty_bar[rslot]), rphase ^ 1);
                         const uint32_t rb = smem_u32(&res_full_bar[rslot]);
                         mbar_expect_tx(rb, Plan::res_slot_bytes);
                         tma_load_3d(smem_u32(smem_res + rslot * Plan::res_slot_bytes), &tmap_res, rb, c0, c1, c2);
-                        if (++rslot == kResSlots)
-                        {
-                            rslot = 0;
-                            rphase ^= 1;
-                        }
+                    }
+                    if (++rslot == kResSlots)
+                    {
+                        rslot = 0;
+                        rphase ^= 1;
                     }
                 }
             }
@@ -919,31 +944,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             else if (AMODE == A_SHIFT)
             {
-                // per 64-channel slab: every tap reads the same staged pixels, shifted by ky * BW + kx rows of 128 bytes
-                const uint32_t b_base = smem_u32(smem_res);
+                // per 64-channel slab: every tap reads the same staged pixels, shifted by ky * BW + kx rows of 128 bytes.
+                // Only the 14-bit (address >> 4) field of the two descriptors changes from MMA to MMA; everything is computed
+                // warp-uniformly OUTSIDE the elected branch (uniform registers), and the 3 x 3 case is fully unrolled: 36
+                // MMAs per slab cost one 32-bit add each.  (Measured before: ~20 instructions per MMA, the issuing lane --
+                // not the tensor pipe, the loads or the epilogue -- paced the 64 -> 64 layers.)
+                // (the descriptor's base-offset field stays 0: measured on B200, the 128B swizzle is applied to the
+                // absolute shared-memory address, so a start that is not 1024-byte aligned needs no correction --
+                // setting the field to (start >> 7) & 7 produces wrong results)
+                const uint64_t desc_hi = make_smem_desc<BLOCK_K>(0) & 0xFFFFFFFF00000000ull;
+                const uint32_t desc_lo_flags = (uint32_t)(make_smem_desc<BLOCK_K>(0) & 0xFFFFC000ull); // LBO field
+                const uint32_t b_lo0 = ((smem_u32(smem_res) & 0x3FFFF) >> 4) | desc_lo_flags;
+                const uint32_t bw8 = (uint32_t)p.sh_bw * 8u;                  // one buffer row of pixels, in 16-byte units
+                const uint32_t tap_b_step = (uint32_t)(p.cblocks * (Plan::b_bytes >> 4));
+                auto issue_tap = [&](uint32_t a_lo, uint32_t b_lo, uint32_t first) {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; k++)
+                        umma_f16(tmem_d, desc_hi | (uint64_t)(a_lo + (uint32_t)(k * 2)), desc_hi | (uint64_t)(b_lo + (uint32_t)(k * 2)), idesc, (k == 0) ? first : 1u);
+                };
                 for (int cb = 0; cb < p.cblocks; cb++)
                 {
                     mbar_wait(full0 + stage * 8, phase);
                     tc_fence_after();
-                    if (elect_one())
+                    const uint32_t a_lo0 = (((smem_a0 + (uint32_t)(stage * p.sh_stage_bytes)) & 0x3FFFF) >> 4) | desc_lo_flags;
+                    const uint32_t b_lo_cb = b_lo0 + (uint32_t)(cb * (Plan::b_bytes >> 4));
+                    const uint32_t commit_bar = empty0 + stage * 8;
+                    const bool last_cb = cb == p.cblocks - 1;
+                    if (p.taps_h == 3 && p.taps_w == 3)
                     {
-                        const uint32_t a_base = smem_a0 + stage * p.sh_stage_bytes;
-                        int tap = 0;
-                        for (int ky = 0; ky < p.taps_h; ky++)
-                            for (int kx = 0; kx < p.taps_w; kx++, tap++)
-                            {
-                                const uint32_t shift_px = (uint32_t)(ky * p.sh_bw + kx);
-                                // (the descriptor's base-offset field stays 0: measured on B200, the 128B swizzle is applied to the
-                                // absolute shared-memory address, so a start that is not 1024-byte aligned needs no correction --
-                                // setting the field to (start >> 7) & 7 produces wrong results)
-                                const uint64_t adesc = make_smem_desc<BLOCK_K>(a_base + shift_px * 128u);
-                                const uint64_t bdesc = make_smem_desc<BLOCK_K>(b_base + (tap * p.cblocks + cb) * Plan::b_bytes);
+                        if (elect_one())
+                        {
 #pragma unroll
-                                for (int k = 0; k < BLOCK_K / 16; k++)
-                                    umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((cb | tap | k) != 0));
-                            }
-                        umma_commit(empty0 + stage * 8);
-                        if (cb == p.cblocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                            for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                                for (int kx = 0; kx < 3; kx++)
+                                    issue_tap(a_lo0 + (uint32_t)ky * bw8 + (uint32_t)(kx * 8), b_lo_cb + (uint32_t)(ky * 3 + kx) * tap_b_step, (uint32_t)((cb | ky | kx) != 0));
+                            umma_commit(commit_bar);
+                            if (last_cb) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                        }
+                    }
+                    else
+                    {
+                        if (elect_one())
+                        {
+                            uint32_t a_row = a_lo0, b_tap = b_lo_cb;
+                            for (int ky = 0; ky < p.taps_h; ky++, a_row += bw8)
+                                for (int kx = 0; kx < p.taps_w; kx++, b_tap += tap_b_step) issue_tap(a_row + (uint32_t)(kx * 8), b_tap, (uint32_t)((cb | ky | kx) != 0));
+                            umma_commit(commit_bar);
+                            if (last_cb) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                        }
                     }
                     __syncwarp();
                     if (++stage == kStages)
