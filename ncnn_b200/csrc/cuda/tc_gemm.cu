@@ -417,7 +417,7 @@ static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid
 }
 
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles, cudaStream_t stream)
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p, long long tiles, cudaStream_t stream)
 {
     using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K, CG>;
     static_assert(Plan::stages_for(true) >= 2, "not enough shared memory for a 2-stage pipeline");
@@ -435,7 +435,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     p.bias_smem_bytes = Plan::bias_bytes; // the general modes reserve the worst case
     if (AMODE == tc::A_ROWS)
     {
-        const int aux = p.taps_h * Plan::b_bytes; // resident weights
+        const int aux = p.taps_h * Plan::b_bytes + (p.tma_store ? Plan::kStageSlots * Plan::res_slot_bytes : 0); // resident weights (+ output staging slots)
         p.bias_smem_bytes = bias_need <= Plan::bias_bytes ? bias_need : 0;
         p.num_stages = Plan::stages_with_aux(aux, p.rows_stage_bytes, p.bias_smem_bytes);
         smem_bytes = Plan::total_with_aux(aux, p.rows_stage_bytes, p.bias_smem_bytes);
@@ -454,8 +454,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     }
     else
     {
-        p.num_stages = Plan::stages_for(has_res);
-        smem_bytes = Plan::total_for(has_res);
+        p.num_stages = Plan::stages_for(has_res, p.tma_store != 0);
+        smem_bytes = Plan::total_for(has_res, p.tma_store != 0);
     }
     // experiment knobs: NCNN_B200_TC_STAGES caps the ring depth, NCNN_B200_TC_GRID the number of CTAs
     static int stage_cap = -1, grid_cap = -1;
@@ -472,32 +472,33 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     {
         // `tiles` counts pair tiles: one cluster of two CTAs (the two SMs of a TPC) per tile, persistent
         const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, p));
+        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, to, p));
         NC_LAUNCH_CHECK();
         return 0;
     }
     int grid = (int)(tiles < sms ? tiles : sms);
-    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, p));
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, to, p));
     NC_LAUNCH_CHECK();
     return 0;
 }
 
 // the CTA-pair instances: 64-element k-blocks, 128 / 256-wide tiles, tiled and im2col operands
 template<typename T, int AMODE>
-static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles, cudaStream_t stream)
+static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p, long long tiles,
+                            cudaStream_t stream)
 {
-    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, p, tiles, stream);
-    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, p, tiles, stream);
+    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, to, p, tiles, stream);
+    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, to, p, tiles, stream);
     set_last_error_msg("tc_gemm: no CTA-pair kernel instance for this tile shape");
     return -1;
 }
 
 template<typename T, int AMODE>
-static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, tc::Params& p, long long tiles,
-                       cudaStream_t stream)
+static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p,
+                       long long tiles, cudaStream_t stream)
 {
 #define NC_TC(BN, BK) \
-    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, p, tiles, stream)
+    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, to, p, tiles, stream)
     NC_TC(256, 64);
     NC_TC(128, 64);
     NC_TC(64, 64);
@@ -519,11 +520,11 @@ static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CU
 }
 
 // (channels, columns, rows) map of a channel-innermost blob for the epilogue's TMA store / residual load
-static int encode_out(CUtensorMap* map, int elemtype, const void* ptr, int C, int cpitch, long long cols, long long rows, int epi_n)
+static int encode_out(CUtensorMap* map, int elemtype, const void* ptr, int C, int cpitch, long long cols, long long rows, int epi_n, int box_rows = tc::BLOCK_M)
 {
     cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[2] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * (cuuint64_t)cols};
-    cuuint32_t box[3] = {(cuuint32_t)epi_n, (cuuint32_t)tc::BLOCK_M, 1};
+    cuuint32_t box[3] = {(cuuint32_t)epi_n, (cuuint32_t)box_rows, 1};
     cuuint32_t estride[3] = {1, 1, 1};
     CUresult r = g_encodeTiled(map, dtype_for(elemtype), 3, (void*)ptr, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(epi_n * 2),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -659,6 +660,26 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     }
     else
         tr = ta;
+    // output map of the TMA-store epilogue: per-warp boxes of 32 rows x epi_n channels; the channel extent is the blob's padded
+    // run (padding lanes up to the next 16-byte unit may be written, as by the per-lane stores)
+    CUtensorMap to;
+    static int tma_store_mode = -1;
+    if (tma_store_mode < 0)
+    {
+        const char* e = getenv("NCNN_B200_TC_TMASTORE");
+        tma_store_mode = e ? atoi(e) : 0;
+    }
+    p.tma_store = 0;
+    to = ta;
+    if (tma_store_mode && amode != tc::A_SHIFT)
+    {
+        int cn = (plan->outch + 7) & ~7;
+        if (cn > c->out_cpitch) cn = c->out_cpitch;
+        if (encode_out(&to, plan->elemtype, c->out, cn, c->out_cpitch, cols, rows, epi_n, 32) == 0)
+            p.tma_store = 1;
+        else
+            to = ta;
+    }
 
     p.M = M;
     p.N = plan->outch;
@@ -700,10 +721,10 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     {
         const long long pair_tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M + 1) / 2 * ((plan->outch + plan->block_n - 1) / plan->block_n);
         if (plan->elemtype == NCNN_CUDA_BF16)
-            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream)
-                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream);
-        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream)
-                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, p, pair_tiles, stream);
+            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream)
+                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream);
+        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream)
+                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream);
     }
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row
@@ -711,10 +732,10 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);
 
 #define NC_MODE(T)                                                                                                            \
-    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream);  \
-    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream);  \
-    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream); \
-    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, p, tiles, stream)
+    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream);  \
+    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream);  \
+    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream); \
+    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream)
     if (plan->elemtype == NCNN_CUDA_BF16)
     {
         NC_MODE(__nv_bfloat16);

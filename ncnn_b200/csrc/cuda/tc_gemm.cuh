@@ -75,6 +75,7 @@ struct Params
     int num_stages; // depth of the A/B ring (SmemPlan::stages_for(residual != NULL))
     int bias_smem_bytes; // shared memory reserved for the bias vector (multiple of 1024; 0 = read it from global memory)
     int v8_ok;      // output rows are 32-byte aligned: 256-bit stores
+    int tma_store;  // the tile leaves through shared-memory staging + per-warp TMA stores (tmap_out) instead of per-lane sector stores
     int taps_h;     // kernel_h (A_IM2COL / A_ROWS k-block nest: filter row, filter column, channel slab)
     // A_ROWS: the zero-padded small-channel copy and its pitches (bytes)
     const unsigned char* rows_src;
@@ -276,6 +277,22 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+// the two epilogue warps of one TMEM lane quarter (64 threads), barrier ids 2..5
+__device__ __forceinline__ void quarter_bar_sync(int lane_group)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(lane_group + 2) : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint32_t* o)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_commit()
@@ -502,14 +519,22 @@ struct SmemPlan
     static constexpr int barrier_bytes = 512;
     static constexpr int bias_bytes = kBiasSmemFloats * 4; // worst case; A_ROWS / A_SHIFT reserve only what the layer needs
     static constexpr int budget = 227 * 1024 - barrier_bytes - bias_bytes - 1024; // - alignment slack
-    static constexpr int stages_for(bool has_res)
+    // Output staging of the TMA-store epilogue: with a fused residual the tile is written back IN PLACE into the residual slot
+    // it was read from (each 16-byte unit of a slot is read and written by one warp only); without one, kStageSlots slots of
+    // the same [BLOCK_M][EPI_N] shape sit where the residual ring would be (one per column half).
+    static constexpr int kStageSlots = 2;
+    static constexpr int aux_for(bool has_res, bool tma_store = false)
     {
-        int s = (budget - (has_res ? kResSlots * res_slot_bytes : 0)) / stage_bytes;
+        return (has_res ? kResSlots : (tma_store ? kStageSlots : 0)) * res_slot_bytes;
+    }
+    static constexpr int stages_for(bool has_res, bool tma_store = false)
+    {
+        int s = (budget - aux_for(has_res, tma_store)) / stage_bytes;
         return s > kMaxStages ? kMaxStages : s;
     }
-    static constexpr int total_for(bool has_res)
+    static constexpr int total_for(bool has_res, bool tma_store = false)
     {
-        return stages_for(has_res) * stage_bytes + (has_res ? kResSlots * res_slot_bytes : 0) + bias_bytes + barrier_bytes + 1024;
+        return stages_for(has_res, tma_store) * stage_bytes + aux_for(has_res, tma_store) + bias_bytes + barrier_bytes + 1024;
     }
     // A_ROWS: `aux` bytes of resident weights behind the ring
     static int stages_with_aux(int aux, int stage_sz, int bias_sz)
@@ -590,6 +615,68 @@ struct Pack8<__half>
     static constexpr int ab_format = 0;
 };
 
+// two fp32 additions in one instruction (add.rn.f32x2, FADD2 on sm_100): the epilogue's bias / residual adds
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1)
+{
+    asm("{\n"
+        ".reg .b64 x, y;\n"
+        "mov.b64 x, {%0, %1};\n"
+        "mov.b64 y, {%2, %3};\n"
+        "add.rn.f32x2 x, x, y;\n"
+        "mov.b64 {%0, %1}, x;\n"
+        "}\n"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+
+// ReLU / clip on the PACKED 16-bit pair: rounding to the storage type is monotonic, so
+// round(max(x, 0)) == max(round(x), 0) and round(clamp(x, lo, hi)) == clamp(round(x), round(lo), round(hi)) exactly;
+// one packed min / max replaces two fp32 ones
+template<typename T>
+struct Packed2;
+template<>
+struct Packed2<__half>
+{
+    static __device__ __forceinline__ uint32_t relu(uint32_t v)
+    {
+        __half2 h = *reinterpret_cast<__half2*>(&v);
+        h = __hmax2(h, __float2half2_rn(0.f));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ uint32_t splat(float f)
+    {
+        __half2 h = __float2half2_rn(f);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ uint32_t clip(uint32_t v, uint32_t lo, uint32_t hi)
+    {
+        __half2 h = *reinterpret_cast<__half2*>(&v);
+        h = __hmin2(__hmax2(h, *reinterpret_cast<__half2*>(&lo)), *reinterpret_cast<__half2*>(&hi));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+template<>
+struct Packed2<__nv_bfloat16>
+{
+    static __device__ __forceinline__ uint32_t relu(uint32_t v)
+    {
+        __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+        h = __hmax2(h, __float2bfloat162_rn(0.f));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ uint32_t splat(float f)
+    {
+        __nv_bfloat162 h = __float2bfloat162_rn(f);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ uint32_t clip(uint32_t v, uint32_t lo, uint32_t hi)
+    {
+        __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+        h = __hmin2(__hmax2(h, *reinterpret_cast<__nv_bfloat162*>(&lo)), *reinterpret_cast<__nv_bfloat162*>(&hi));
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+
 // the rare activations (sigmoid, mish, hardswish) as an out-of-line call: keeps the unrolled epilogue small and its
 // accumulators in registers
 static __device__ __noinline__ float apply_activation_call(float v, int type, float p0, float p1)
@@ -607,7 +694,8 @@ static __device__ __noinline__ float apply_activation_call(float v, int type, fl
 // of the B tile.  Only the leader's MMA warp runs.
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_res, const Params p)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_res,
+               const __grid_constant__ CUtensorMap tmap_out, const Params p)
 {
     static_assert(CG == 1 || AMODE == A_TILED || AMODE == A_IM2COL, "CTA pairs: tiled and im2col operand modes only");
     using Plan = SmemPlan<BLOCK_N, BLOCK_K, CG>;
@@ -632,7 +720,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // stages hold a whole tile's row segments instead of A/B k-block pairs)
     uint8_t* smem_res = smem + kStages * (AMODE == A_ROWS ? p.rows_stage_bytes : (AMODE == A_SHIFT ? p.sh_stage_bytes : Plan::stage_bytes));
     // (A_ROWS keeps the resident weights where the residual slots would be; the two never coexist)
-    const int aux_bytes = AMODE == A_ROWS ? p.taps_h * Plan::b_bytes : (AMODE == A_SHIFT ? p.num_k_blocks * Plan::b_bytes : (has_res ? kResSlots * Plan::res_slot_bytes : 0));
+    // A_ROWS: resident weights, then the output staging slots; A_SHIFT: resident weights (direct stores); tiled / im2col:
+    // the residual ring, or the output staging slots when nothing is fused
+    const int weights_bytes = AMODE == A_ROWS ? p.taps_h * Plan::b_bytes : (AMODE == A_SHIFT ? p.num_k_blocks * Plan::b_bytes : 0);
+    const int aux_bytes = AMODE == A_ROWS ? weights_bytes + (p.tma_store ? Plan::kStageSlots * Plan::res_slot_bytes : 0)
+                                          : (AMODE == A_SHIFT ? weights_bytes : Plan::aux_for(has_res, p.tma_store != 0));
+    uint8_t* smem_stage = smem_res + weights_bytes; // output staging slots (!has_res)
     float* smem_bias = reinterpret_cast<float*>(smem_res + aux_bytes); // [kBiasSmemFloats]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_bias) + p.bias_smem_bytes);
     uint64_t* full_bar = bars;                  // [16]
@@ -667,6 +760,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         if (has_res) prefetch_tmap(&tmap_res);
+        if (p.tma_store) prefetch_tmap(&tmap_out);
     }
     if (warp == 1 && lane == 0)
     {
@@ -1069,6 +1163,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int sw_row = (EPI_CHUNKS16 == 8) ? (row & 7) : ((row >> 1) & 3);
         const bool v8ok = p.v8_ok != 0;
         const int N = p.N;
+        const uint32_t clip_lo2 = Packed2<T>::splat(act_p0), clip_hi2 = Packed2<T>::splat(act_p1);
+        // Optional TMA-store epilogue (NCNN_B200_TC_TMASTORE=1; tiled / im2col / rows operands).  A lane that stores its own
+        // pixel's 32-byte sectors touches 32 different 128-byte lines per instruction and the L1 data pipe spends ~2 cycles on
+        // each (64 -> 256 layer: lsu data-pipe wavefronts at 83 % of peak).  Here the warp writes its 32 rows x EPI_N columns into
+        // 128B-swizzled shared memory (conflict-free STS.128) and one lane issues a TMA tensor store of the box; rows / columns
+        // outside the blob are clipped by the TMA unit; with a fused residual the rows go back into the slot they were read from.
+        // MEASURED (profiles/r2/tma_store_vs_direct.txt): the data-pipe load disappears but the write-dominated layers only gain
+        // 3-4 % (they sit at the HBM write rate, tools/hbm_probe.py), while the 32 KB of staging cost the compute-bound layers a
+        // ring stage: ResNet-50 convs 3221 us against 3133 us with direct stores.  Kept selectable, off by default.
+        const bool use_tma_store = AMODE != A_SHIFT && p.tma_store != 0;
+        constexpr bool kSharedChunk = (NCHUNK == 1 && SUBS == 2); // both halves of a lane quarter fill one 64-column box
+        int pending_release = -2; // -2: no store in flight; -1: a store is reading the staging slot; >= 0: ... a residual slot to release
+        auto flush_store = [&]() {
+            // the bulk store(s) this warp has issued must have READ their shared-memory source before it is overwritten / recycled
+            if (pending_release != -2)
+            {
+                if (lane == 0)
+                {
+                    tma_store_wait_read<0>();
+                    if (pending_release >= 0) mbar_arrive(smem_u32(&res_empty_bar[pending_release]));
+                }
+                __syncwarp();
+                pending_release = -2;
+            }
+        };
         // the MMA warp that reuses the accumulator stage is the leader's: a pair's epilogue warps all arrive there
         const uint32_t tmem_empty_leader = CG == 2 ? mapa_shared(smem_u32(tmem_empty_bar), 0) : smem_u32(tmem_empty_bar);
         auto arrive_tmem_empty = [&](int a) {
@@ -1112,6 +1231,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             T* const orow = reinterpret_cast<T*>(p.out) + pix * p.out_cpitch + n0;
             const bool fast_store = row_ok && v8ok && (n0 + BLOCK_N <= n8);
+            // TMA-store coordinates of this warp's 32 rows: (channel, column, row) as in the residual map
+            int store_c1, store_c2;
+            if (AMODE == A_ROWS)
+            {
+                store_c2 = fast_div(m_blk, p.div_chunks);
+                store_c1 = (m_blk - store_c2 * p.chunks_per_row) * BLOCK_M + lane_group * 32;
+            }
+            else
+            {
+                store_c1 = m_blk * BLOCK_M + lane_group * 32;
+                store_c2 = 0;
+            }
 
             // bias of this tile's columns in shared memory: the layer's resident copy, or -- for the rare layer whose bias vector
             // does not fit -- a per-warp copy of the tile's BLOCK_N values made here, so that the group loop has ONE bias path
@@ -1156,48 +1287,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_tmem_empty(acc);
-                // single-chunk tiles count all eight warps as readers of the residual slot
-                if (has_res && NCHUNK == 1 && SUBS == 2 && lane == 0) mbar_arrive(smem_u32(&res_empty_bar[slots_seen % kResSlots]));
+                // single-chunk tiles count all eight warps as readers of the residual slot (TMA-store mode: the storing warp
+                // arrives for both halves of its lane quarter once the box has been read)
+                if (has_res && kSharedChunk && !use_tma_store && lane == 0) mbar_arrive(smem_u32(&res_empty_bar[slots_seen % kResSlots]));
             }
-            // owned groups: g_begin, +1 within a chunk, then the chunk after next
-#pragma unroll 1
-            for (int g = g_begin; g <= g_last; g = (NCHUNK == 1 || (g % SUBS) != SUBS - 1) ? g + 1 : g + 1 + SUBS)
-            {
+            // owned groups: g_begin, +1 within a chunk, then the chunk after next.  The TMEM load of the NEXT owned group is
+            // issued before the current one is processed (two register buffers, ping-pong), so its latency hides behind the
+            // arithmetic and the stores; the accumulator stage goes back to the MMA warp as soon as the last load has landed.
+            auto next_group = [&](int g) { return (NCHUNK == 1 || (g % SUBS) != SUBS - 1) ? g + 1 : g + 1 + SUBS; };
+            auto release_acc = [&]() {
+                // every column group of this half sits in registers: the accumulator stage can be overwritten
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_tmem_empty(acc);
+            };
+            auto process_group = [&](uint32_t (&r)[32], const int g) {
                 const int cc = g / SUBS;         // chunk = residual slot of the tile
                 const int slot_sub = g % SUBS;   // which 32-column half of the slot
                 const int col0 = g * 32;
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + (uint32_t)col0, r);
-                // bias of the group while the TMEM load is in flight: always an LDS broadcast (bias_base, see the tile set-up)
-                float bv[32];
+                flush_store(); // (the store issued one group ago has long read its box: no wait in practice)
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                // + bias: LDS broadcasts (bias_base, see the tile set-up), packed fp32 adds
                 {
                     const float* bs = smem_bias + bias_base + col0;
 #pragma unroll
                     for (int q = 0; q < 8; q++)
                     {
                         const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * q);
-                        bv[4 * q + 0] = b4.x;
-                        bv[4 * q + 1] = b4.y;
-                        bv[4 * q + 2] = b4.z;
-                        bv[4 * q + 3] = b4.w;
+                        add2(v[4 * q + 0], v[4 * q + 1], b4.x, b4.y);
+                        add2(v[4 * q + 2], v[4 * q + 3], b4.z, b4.w);
                     }
                 }
-                const uint32_t slot_no = slots_seen + (uint32_t)cc;
-                const int rslot = (int)(slot_no % kResSlots);
-                if (has_res && (slot_sub == 0 || NCHUNK == 1)) mbar_wait(smem_u32(&res_full_bar[rslot]), (slot_no / kResSlots) & 1);
-                tmem_wait_ld_pin(r);
-                if (g == g_last)
-                {
-                    // every column group of this half sits in registers: the accumulator stage can be overwritten
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) arrive_tmem_empty(acc);
-                }
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + bv[j];
                 if (has_res)
                 {
+                    const uint32_t slot_no = slots_seen + (uint32_t)cc;
+                    const int rslot = (int)(slot_no % kResSlots);
+                    if (slot_sub == 0 || NCHUNK == 1) mbar_wait(smem_u32(&res_full_bar[rslot]), (slot_no / kResSlots) & 1);
                     const uint8_t* rbuf = smem_res + rslot * Plan::res_slot_bytes + row * EPI_ROW_BYTES;
 #pragma unroll
                     for (int u = 0; u < 4; u++)
@@ -1207,38 +1334,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         const uint4 ru = *reinterpret_cast<const uint4*>(rbuf + ((unit ^ sw_row) * 16));
                         Pack8<T>::unpack(ru, rv);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) v[u * 8 + j] += rv[j];
+                        for (int j = 0; j < 8; j += 2) add2(v[u * 8 + j], v[u * 8 + j + 1], rv[j], rv[j + 1]);
                     }
                     // last read of the slot by this warp: after its final 32-column group (or the only one it owns)
                     const bool slot_done = (NCHUNK == 1) || (slot_sub == SUBS - 1) || (g + 1 >= ngroups);
-                    if (slot_done)
+                    if (slot_done && !use_tma_store)
                     {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&res_empty_bar[rslot]));
                     }
                 }
-                // activation: one uniform branch per group, not per element
-                if (act == 1)
-                {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
-                }
-                else if (act == 7)
+                // activation: one uniform branch per group, not per element; ReLU and clip run on the packed pairs below
+                if (act == 7)
                 {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
-                }
-                else if (act == 3)
-                {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fminf(fmaxf(v[j], act_p0), act_p1);
                 }
                 else if (act == 2)
                 {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = v[j] > 0.f ? v[j] : v[j] * act_p0;
                 }
-                else if (act != 0)
+                else if (act > 3)
                 {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = apply_activation_call(v[j], act, act_p0, act_p1);
@@ -1246,7 +1363,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t o[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) o[j] = Pack8<T>::pack2(v[2 * j], v[2 * j + 1]);
-                if (fast_store)
+                if (act == 1)
+                {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) o[j] = Packed2<T>::relu(o[j]);
+                }
+                else if (act == 3)
+                {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) o[j] = Packed2<T>::clip(o[j], clip_lo2, clip_hi2);
+                }
+                if (use_tma_store)
+                {
+                    // this lane's row of the staging box: the residual slot it just read (in place), or the staging slot of its half
+                    const uint32_t slot_no = slots_seen + (uint32_t)cc;
+                    const int rslot = (int)(slot_no % kResSlots);
+                    const uint32_t slot_base = has_res ? smem_u32(smem_res + rslot * Plan::res_slot_bytes)
+                                                       : smem_u32(smem_stage + (kSharedChunk ? 0 : half) * Plan::res_slot_bytes);
+                    const uint32_t srow = slot_base + (uint32_t)(row * EPI_ROW_BYTES);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) st_shared_v4(srow + (uint32_t)((((slot_sub * 4 + u) ^ sw_row)) * 16), &o[u * 4]);
+                    const bool chunk_done = (NCHUNK == 1) || (slot_sub == SUBS - 1) || (g + 1 >= ngroups);
+                    if (chunk_done && !kSharedChunk)
+                    {
+                        fence_proxy_async(); // generic-proxy writes -> visible to the TMA unit
+                        __syncwarp();
+                        if (lane == 0)
+                        {
+                            tma_store_3d(&tmap_out, slot_base + (uint32_t)(lane_group * 32 * EPI_ROW_BYTES), n0 + cc * EPI_N, store_c1, store_c2);
+                            tma_store_commit();
+                        }
+                        pending_release = has_res ? rslot : -1;
+                    }
+                }
+                else if (fast_store)
                 {
                     // the whole tile is inside the blob and 32-byte aligned: two unconditional sector stores
                     st_global_v8(orow + col0, &o[0]);
@@ -1268,6 +1418,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                     }
                 }
+            };
+            if (g_begin <= g_last)
+            {
+                uint32_t ra[32], rb[32];
+                int g = g_begin;
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 32), ra);
+#pragma unroll 1
+                while (true)
+                {
+                    tmem_wait_ld_pin(ra);
+                    const int g1 = next_group(g);
+                    if (g1 <= g_last)
+                        tmem_ld_32x32b_x32(taddr + (uint32_t)(g1 * 32), rb);
+                    else
+                        release_acc();
+                    process_group(ra, g);
+                    if (g1 > g_last) break;
+                    tmem_wait_ld_pin(rb);
+                    g = next_group(g1);
+                    if (g <= g_last)
+                        tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 32), ra);
+                    else
+                        release_acc();
+                    process_group(rb, g1);
+                    if (g > g_last) break;
+                }
+            }
+            if (use_tma_store)
+            {
+                if (kSharedChunk)
+                {
+                    // both halves have staged their 32 columns of the quarter's 32 rows: one box, stored by half 0
+                    const uint32_t slot_no = slots_seen;
+                    const int rslot = (int)(slot_no % kResSlots);
+                    const uint32_t slot_base = has_res ? smem_u32(smem_res + rslot * Plan::res_slot_bytes) : smem_u32(smem_stage);
+                    fence_proxy_async();
+                    quarter_bar_sync(lane_group);
+                    if (half == 0 && lane == 0)
+                    {
+                        tma_store_3d(&tmap_out, slot_base + (uint32_t)(lane_group * 32 * EPI_ROW_BYTES), n0, store_c1, store_c2);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                        if (has_res)
+                        {
+                            // all eight warps count as readers of a single-chunk slot: this lane arrives for both halves
+                            mbar_arrive(smem_u32(&res_empty_bar[rslot]));
+                            mbar_arrive(smem_u32(&res_empty_bar[rslot]));
+                        }
+                    }
+                    quarter_bar_sync(lane_group); // the box is free again (next tile's staging / the producer's next load)
+                }
+                else
+                    flush_store(); // do not sit on a residual slot while waiting for the next tile's accumulator
             }
             slots_seen += (uint32_t)((ngroups + SUBS - 1) / SUBS);
             if (++acc == kAccStages)
@@ -1278,6 +1481,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     }
 
+    if (warp >= kEpilogueWarp0 && lane == 0 && p.tma_store) tma_store_wait<0>(); // bulk stores issued by this lane have completed
     tc_fence_before();
     __syncwarp(); // (warp 0 / warp 1: the single working lane rejoins its warp before the aligned barrier)
     if (CG == 2)

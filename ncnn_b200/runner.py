@@ -108,15 +108,16 @@ class Session(object):
         self.L._view(m, force_batch=True)[...] = x
         return m
 
-    def extract_host(self, mat):
-        """one reference-style call: Extractor.input(host Mat) + extract(host Mat); H2D and D2H inside"""
+    def extract_host(self, mat, blob=None):
+        """one reference-style call: Extractor.input(host Mat) + extract(host Mat); H2D and D2H inside.
+        blob: name of the blob to extract (default: the graph's first output)"""
         lib = self.L.lib
         ex = lib.ncnn_extractor_create(self.net)
         out = C.c_void_p()
         try:
             if lib.ncnn_extractor_input(ex, self.input_name, mat) != 0:
                 raise RuntimeError("input failed")
-            r = lib.ncnn_extractor_extract(ex, self.output_name, C.byref(out))
+            r = lib.ncnn_extractor_extract(ex, blob.encode() if isinstance(blob, str) else (blob or self.output_name), C.byref(out))
             if r != 0:
                 raise RuntimeError("extract returned %d: %s" % (r, lib.ncnn_cuda_last_error().decode()))
             self.last_h2d = lib.ncnn_extractor_get_last_h2d_bytes(ex)
@@ -170,9 +171,9 @@ class Session(object):
             lib.ncnn_extractor_destroy(ex)
         return out
 
-    def run_host(self, x):
+    def run_host(self, x, blob=None):
         m = self.pinned_input(x)
-        out = self.extract_host(m)
+        out = self.extract_host(m, blob)
         res = self.L.mat_to_numpy(out, force_batch=True)
         self.L.lib.ncnn_mat_destroy(out)
         self.L.lib.ncnn_mat_destroy(m)

@@ -10,9 +10,12 @@ input/extract) against the reference's own CPU path on identical .param text, .b
     The bound is asserted on the last linear blob (logits / detection head).  A Softmax output p = softmax(z) turns an
     ABSOLUTE logit error dz into a RELATIVE probability error (dp/p ~ dz), so for the softmax blob the same bound is
     scaled by max(1, max|z|) -- the propagated form of the same tolerance, not a looser one.
-  * bf16 storage (opt.use_bf16_storage) is measured and reported too.  Its 8-bit mantissa (unit roundoff 2^-8 = 3.9e-3
-    per stored activation) cannot meet 2e-3 through 20-60 stacked layers no matter how the arithmetic is done -- the
-    per-layer arithmetic bound IS met (tests/test_kernels_gpu.py) -- so the network-level bf16 check is 2e-2 and says so.
+  * fp16 storage is the CONTRACT dtype: it is what bench.py reports by default (BENCH line "dtype": "f16") and every
+    BASELINE.json configuration at its full bench batch / resolution is held to 2e-3 in it (test_full_size_configs).
+  * bf16 storage (opt.use_bf16_storage) is measured and reported too, NOT benched as the headline.  Its 8-bit mantissa (unit
+    roundoff 2^-8 = 3.9e-3 per stored activation) cannot meet 2e-3 through 20-60 stacked layers no matter how the arithmetic
+    is done -- the per-layer arithmetic bound IS met (tests/test_kernels_gpu.py) -- so the network-level bf16 check is the
+    storage-limited 2e-2 and says so; nothing quoted against the north-star tolerance uses it.
 """
 import json
 import os
@@ -143,8 +146,11 @@ def test_model_parity(ref, name, mode):
                 assert int(np.argmax(g[b])) == int(np.argmax(w[b]))
 
 
-FULL_CONFIGS = [("mobilenet_v2", 128, 224, "bf16"), ("resnet50", 256, 224, "bf16"), ("resnet50", 256, 224, "fp16"), ("resnet50", 256, 224, "fp32"),
-                ("yolov8s", 64, 640, "bf16"), ("vgg16", 256, 224, "bf16"), ("vgg16", 256, 224, "fp16")]
+# fp16 storage is the dtype bench.py reports (its default): every BASELINE.json config at full size must meet the north-star
+# 2e-3 in it.  bf16 storage is kept as a measured, storage-limited variant (see the module docstring), fp32 as the 1e-5 path.
+FULL_CONFIGS = [("mobilenet_v2", 128, 224, "fp16"), ("resnet50", 256, 224, "fp16"), ("yolov8s", 64, 640, "fp16"), ("vgg16", 256, 224, "fp16"),
+                ("squeezenet_v1_1", 1, 227, "fp16"), ("resnet50", 256, 224, "fp32"),
+                ("mobilenet_v2", 128, 224, "bf16"), ("resnet50", 256, 224, "bf16"), ("yolov8s", 64, 640, "bf16"), ("vgg16", 256, 224, "bf16")]
 
 
 @pytest.mark.parametrize("name,n,size,mode", FULL_CONFIGS)
@@ -158,13 +164,14 @@ def test_full_size_configs(ref, name, n, size, mode):
     text = netutil.with_input_size(modelzoo.param_text(name), size)
     weights = modelzoo.random_model_bytes(text, seed=netutil.WEIGHT_SEED)
     x = netutil.random_input(name, n, size, seed=2)
-    x[n - 1] = x[0]
+    if n > 1:
+        x[n - 1] = x[0]
     in_name = "in0" if name == "yolov8s" else "data"
     key = "out0" if name == "yolov8s" else logits_blob(name)
     got = run_ours(text, weights, {in_name: x}, mode, batched=True, outputs=[key])[key]
     assert got.shape[0] == n and np.isfinite(got).all()
     assert np.array_equal(got[0], got[n - 1]), "batch position changes the result"
-    picked = [0, 1, n // 2, n - 2]
+    picked = sorted(set(i for i in (0, 1, n // 2, n - 2) if 0 <= i < n))
     want = run_ref(ref, text, weights, {in_name: x[picked]}, batched=True, outputs=[key])[key]
     e = nerr(got[picked], want)
     print("\n[full size] %-14s n=%d %dx%d %-5s err=%.3g" % (name, n, size, size, mode, e))
@@ -173,6 +180,7 @@ def test_full_size_configs(ref, name, n, size, mode):
         top = np.sort(want, axis=1)
         margin = (top[:, -1] - top[:, -2]) / np.abs(want).max()
         for j, b in enumerate(picked):
+            # identical top-1 wherever the reference's own margin exceeds what twice the bound can move (4e-3 for the fp16 contract dtype)
             if margin[j] > 2 * TOL[mode]:
                 assert int(np.argmax(got[b])) == int(np.argmax(want[j]))
 
