@@ -105,6 +105,8 @@ NCNN_CUDA_API int ncnn_cuda_graph_destroy(void* graph_exec);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 NCNN_CUDA_API unsigned long long ncnn_cuda_launch_count(void);
+/* of those, launches of the tcgen05 implicit-GEMM kernel (tests: which Convolution / InnerProduct / Gemm forms reach the tensor cores) */
+NCNN_CUDA_API unsigned long long ncnn_cuda_tc_launch_count(void);
 
 /* ------------------------------------------------------------------ layout conversion
  * pack: planar fp32 (host layout, but `src->data` must be DEVICE memory: the caller has

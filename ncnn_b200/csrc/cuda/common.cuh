@@ -18,6 +18,7 @@ namespace ncnn_cuda {
 void set_last_error(const char* what, cudaError_t e, const char* file, int line);
 void set_last_error_msg(const char* msg);
 void count_launch(int n = 1);
+void count_tc_launch();
 
 #define NC_CHECK(expr)                                                   \
     do                                                                   \

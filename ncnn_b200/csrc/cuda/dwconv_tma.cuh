@@ -75,6 +75,19 @@ struct Vec16<__half>
         for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[i].x, v[i].y);
         *reinterpret_cast<uint4*>(p) = u;
     }
+    static __device__ __forceinline__ void store_clamped(void* p, const float2 (&v)[4], float lo, float hi, bool relu_only)
+    {
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+        const __half2 l2 = __float2half2_rn(lo), h2 = __float2half2_rn(hi);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            __half2 t = __hmax2(__floats2half2_rn(v[i].x, v[i].y), l2);
+            h[i] = relu_only ? t : __hmin2(t, h2);
+        }
+        *reinterpret_cast<uint4*>(p) = u;
+    }
 };
 template<>
 struct Vec16<__nv_bfloat16>
@@ -100,6 +113,19 @@ struct Vec16<__nv_bfloat16>
         for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[i].x, v[i].y);
         *reinterpret_cast<uint4*>(p) = u;
     }
+    static __device__ __forceinline__ void store_clamped(void* p, const float2 (&v)[4], float lo, float hi, bool relu_only)
+    {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+        const __nv_bfloat162 l2 = __float2bfloat162_rn(lo), h2 = __float2bfloat162_rn(hi);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            __nv_bfloat162 t = __hmax2(__floats2bfloat162_rn(v[i].x, v[i].y), l2);
+            h[i] = relu_only ? t : __hmin2(t, h2);
+        }
+        *reinterpret_cast<uint4*>(p) = u;
+    }
 };
 template<>
 struct Vec16<float>
@@ -114,6 +140,10 @@ struct Vec16<float>
     static __device__ __forceinline__ void store(void* p, const float2 (&v)[2])
     {
         *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    }
+    static __device__ __forceinline__ void store_clamped(void* p, const float2 (&v)[2], float, float, bool)
+    {
+        store(p, v); // (fp32 blobs clamp in registers)
     }
 };
 
@@ -131,7 +161,10 @@ struct Cfg
     // two CTAs per SM: each gets half of the 227 KB
     static constexpr int cta_budget = 111 * 1024;
     static constexpr int fixed_bytes = 128 /*alignment*/ + 128 /*barriers*/;
-    static_assert(CV * TW * TY == kConsumers, "one consumer thread per (channel vector, column, thread row)");
+    // one consumer thread per (channel vector, column, thread row); channel counts that are not a power of two times 8 (144 = 2 x 72)
+    // use CV = 9 and leave the last few threads of the CTA idle (they still take part in the barriers)
+    static constexpr int kActive = CV * TW * TY;
+    static_assert(kActive <= kConsumers && kActive > kConsumers - 32, "consumer mapping must fill all eight warps");
     // this CTA's slice of the filter bank: 9 taps + bias for its CB channels
     static constexpr int w_bytes = 10 * CB * 4;
     static constexpr int stages_fit = (cta_budget - fixed_bytes - w_bytes) / stage_bytes;
@@ -175,11 +208,34 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
     const int cb = blockIdx.x % cblocks;
     const int sp_first = blockIdx.x / cblocks;
     const int sp_step = gridDim.x / cblocks;
-    for (int i = tid; i < 10 * C::CB; i += kThreads)
     {
-        const int t = i / C::CB, c = cb * C::CB + (i - t * C::CB);
-        // (the last channel block may be partial: its missing channels read as zeros from the TMA and are never stored)
-        smem_w[i] = c < p.C ? (t < 9 ? p.w[(long long)t * p.cpad + c] : (p.bias ? p.bias[c] : 0.f)) : 0.f;
+        // this CTA's filter slice, 16 bytes per load, every load of a thread issued before its first store (the slice is a few KB:
+        // a load -> store -> load chain here costs several microseconds of the 10-20 us a small layer takes)
+        constexpr int V4 = 10 * C::CB / 4;                       // float4 units: [10][CB / 4]
+        constexpr int PER = (V4 + kThreads - 1) / kThreads;
+        float4 tmp[PER];
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+        {
+            const int i = tid + j * kThreads;
+            const int t = i / (C::CB / 4), c = cb * C::CB + (i - t * (C::CB / 4)) * 4;
+            tmp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // (the last channel block may be partial: its missing channels read as zeros from the TMA and are never stored;
+            //  C and cpad are multiples of 4 floats on this path)
+            if (i < V4 && c < p.C)
+            {
+                if (t < 9)
+                    tmp[j] = __ldg(reinterpret_cast<const float4*>(p.w + (long long)t * p.cpad + c));
+                else if (p.bias)
+                    tmp[j] = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PER; j++)
+        {
+            const int i = tid + j * kThreads;
+            if (i < V4) reinterpret_cast<float4*>(smem_w)[i] = tmp[j];
+        }
     }
     __syncthreads();
     tc::pdl_wait(); // the filter slice above is a constant; the previous layer's blob is touched only from here on
@@ -212,9 +268,11 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
     }
 
     // ===================== consumers =====================
-    const int cv = tid % CV;
-    const int tx = (tid / CV) % TW;
-    const int ty = tid / (CV * TW);
+    const bool active = tid < C::kActive;
+    const int mt = active ? tid : 0; // idle threads shadow thread 0 (they never store)
+    const int cv = mt % CV;
+    const int tx = (mt / CV) % TW;
+    const int ty = mt / (CV * TW);
     const int lane = tid & 31;
 
     int stage = 0;
@@ -290,8 +348,14 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
             phase ^= 1;
         }
 
-        // activation on the whole register tile (one uniform branch), then the stores
-        if (act == 1)
+        // activation on the whole register tile (one uniform branch), then the stores.  For 16-bit blobs ReLU and clip run on the
+        // PACKED pairs inside the store (round(clamp(x)) == clamp(round(x), round(lo), round(hi)): rounding is monotonic), one
+        // packed min / max per two elements instead of two fp32 ones each
+        constexpr bool kPackedAct = sizeof(T) == 2;
+        if (kPackedAct && (act == 1 || act == 3))
+        {
+        }
+        else if (act == 1)
         {
 #pragma unroll
             for (int r = 0; r < R; r++)
@@ -316,13 +380,21 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv3x3_tma_kernel(const __grid
         }
         const int ox = txi * TW + tx;
         const int oy0 = tyi * C::TH + ty * R;
-        if (ox < p.outw && c0 < p.C)
+        if (active && ox < p.outw && c0 < p.C)
         {
             T* op = out + ((long long)b * p.out_nstep + ((long long)oy0 * p.outw + ox) * p.out_cpitch + c0);
 #pragma unroll
             for (int r = 0; r < R; r++)
             {
-                if (oy0 + r < p.outh) Vec16<T>::store(op, acc[r]);
+                if (oy0 + r < p.outh)
+                {
+                    if (kPackedAct && act == 1)
+                        Vec16<T>::store_clamped(op, acc[r], 0.f, 3.0e38f, true);
+                    else if (kPackedAct && act == 3)
+                        Vec16<T>::store_clamped(op, acc[r], p.act_p0, p.act_p1, false);
+                    else
+                        Vec16<T>::store(op, acc[r]);
+                }
                 op += p.out_row_stride;
             }
         }
@@ -434,6 +506,9 @@ static int forward(const Call& c, cudaStream_t stream)
         return launch_dw_tma<T, S_, CV_, TW_, TY_, R_>(tm, (T*)c.out, p, stream);               \
     } while (0)
 
+    // (tried for C = 144 = 2 x 72: CV = 9 channel vectors x 28 columns instead of 32-byte channel blocks -- 71.8 us against 69.3 us
+    //  at 56 x 56 stride 1, 39.4 against 34.0 at stride 2: the stride-1 layers are bound by the consumers' dependent
+    //  LDS -> convert -> FFMA2 chains at ~0.3 instructions per cycle per scheduler, not by the TMA box shape; profiles/r2)
     if (c.stride == 1)
     {
         // maps of 7k rows up to 32 columns wide (7x7, 14x14, 28x28): one column x seven rows per thread -- each staged pixel is
@@ -442,6 +517,8 @@ static int forward(const Call& c, cudaStream_t stream)
         if (c.outh % 7 == 0 && c.C >= 8 * VEC)
         {
             if (c.outw <= 8 && c.C >= 24 * VEC) NC_DW(1, 32, 8, 1, 7);
+            // whole 14 x 14 images per tile in 64-channel blocks when those divide C and 128-channel blocks do not (576 = 9 x 64)
+            if (c.outw <= 16 && c.outw > 8 && c.outh == 14 && c.C % (8 * VEC) == 0 && c.C % (16 * VEC) != 0) NC_DW(1, 8, 16, 2, 7);
             if (c.outw <= 16 && c.outw > 8 && c.C >= 12 * VEC) NC_DW(1, 16, 16, 1, 7);
             if (c.outw <= 32 && c.outw > 16) NC_DW(1, 8, 32, 1, 7);
         }

@@ -12,6 +12,7 @@ namespace ncnn_cuda {
 static std::mutex g_err_mutex;
 static char g_err[1024] = "";
 static std::atomic<unsigned long long> g_launches(0);
+std::atomic<unsigned long long> g_tc_launches(0); // launches of the tcgen05 implicit-GEMM kernel (tc_gemm.cu)
 
 void set_last_error(const char* what, cudaError_t e, const char* file, int line)
 {
@@ -30,6 +31,11 @@ void set_last_error_msg(const char* msg)
 void count_launch(int n)
 {
     g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed);
+}
+
+void count_tc_launch()
+{
+    g_tc_launches.fetch_add(1ull, std::memory_order_relaxed);
 }
 
 int sm_count()
@@ -260,6 +266,11 @@ int ncnn_cuda_graph_destroy(void* graph_exec)
 unsigned long long ncnn_cuda_launch_count(void)
 {
     return g_launches.load(std::memory_order_relaxed);
+}
+
+unsigned long long ncnn_cuda_tc_launch_count(void)
+{
+    return ncnn_cuda::g_tc_launches.load(std::memory_order_relaxed);
 }
 
 } // extern "C"

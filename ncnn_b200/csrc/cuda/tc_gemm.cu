@@ -474,11 +474,13 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
         const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
         NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, to, p));
         NC_LAUNCH_CHECK();
+        count_tc_launch();
         return 0;
     }
     int grid = (int)(tiles < sms ? tiles : sms);
     NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, to, p));
     NC_LAUNCH_CHECK();
+    count_tc_launch();
     return 0;
 }
 

@@ -163,7 +163,8 @@ public:
     int output_N1M, output_elempack, output_elemtype, output_transpose;
     Mat A_data, B_data, C_data;
     CudaMat A_dev, B_dev, C_dev; // constants as device matrices (fp32 for C, storage type for A/B)
-    ncnn_cuda_linear_t linear;   // tcgen05 fast path: Y = X * W^T + b with constant W
+    ncnn_cuda_linear_t linear;   // tcgen05 path: rows(X) * W^T + b with the constant operand as W (see gemm_layer.cpp)
+    int linear_mode;             // 0 none; 1 constant B: Y = A W^T (rows of A are the activations); 2 constant A: Y^T = B^T W^T
     int elemtype;
 };
 

@@ -1,7 +1,13 @@
-// gemm_layer.cpp -- Gemm (src/layer/gemm.cpp:67-248 params/weights, :579-740 forward) on 2-D operands.
-// Y = alpha * (op(A) * op(B) + beta * C).  The nn.Linear form pnnx emits (constant B stored transposed, optional
-// per-column constant C, alpha = beta = 1) runs on the tcgen05 path as an InnerProduct over the rows of A; every other
-// combination goes through the strided CUDA-core kernel, transposes and C broadcasting expressed as strides.
+// gemm_layer.cpp -- Gemm (src/layer/gemm.cpp:67-248 params/weights, :579-740 forward).
+// Y = alpha * (op(A) * op(B) + beta * C), operands 2-D (w, h) or the 3-D (w, 1, c) form the reference accepts (:608-650).
+//
+// tcgen05 routes (the constant operand becomes the re-packed weight matrix of the implicit-GEMM kernel, tc_gemm.cuh; alpha is
+// folded into the weights, alpha * beta * C into the epilogue bias when C is constant and broadcasts along the weight rows):
+//   constant B, any transB   : Y[m][n]   = sum_k A[m][k] W[n][k],  W = alpha * op(B)^T      (the nn.Linear form and its transposes)
+//   constant A, runtime B^T  : Y^T[n][m] = sum_k B^T[n][k] W[m][k], W = alpha * op(A)       (transB = 1: B arrives as [N][K])
+// followed by one tiled transpose when the requested output orientation is the other one.  Everything else -- two runtime
+// operands, transposed runtime activations, C broadcasts across the weight rows, 3-D operands -- goes through the strided
+// CUDA-core kernel with transposes and broadcasts expressed as strides.
 #include "cuda_layers.h"
 
 #include <vector>
@@ -13,6 +19,7 @@ Gemm::Gemm()
     one_blob_only = false;
     support_inplace = false;
     linear = 0;
+    linear_mode = 0;
     elemtype = NCNN_CUDA_F32;
 }
 
@@ -95,21 +102,64 @@ int upload_const(const Mat& src, int elemtype, CudaMat& dst)
     return ret;
 }
 
+// logical matrix view of a constant host Mat: 2-D (w, h) rows = h, or 3-D (w, 1, c) rows = c (src/layer/gemm.cpp:617-650)
+static void host_matrix(const Mat& m, int& rows, int& cols, size_t& rstep)
+{
+    cols = m.w;
+    if (m.dims == 3)
+    {
+        rows = m.c;
+        rstep = m.cstep;
+    }
+    else
+    {
+        rows = m.h;
+        rstep = (size_t)m.w;
+    }
+}
+
 int Gemm::create_pipeline(const Option& opt)
 {
     elemtype = opt.cuda_elemtype();
     const bool has_c = constantC == 1 && constant_broadcast_type_C != -1;
-    const bool linear_form = constantA == 0 && constantB == 1 && transA == 0 && transB == 1 && alpha == 1.f && output_transpose == 0 && output_N1M == 0
-                             && (!has_c ? constantC == 1 : (constant_broadcast_type_C == 4 && beta == 1.f));
-    if (linear_form)
+    const int bt = constant_broadcast_type_C;
+    linear_mode = 0;
+    // ---- constant-operand routes (tcgen05 for 16-bit blobs, the strict-fp32 implicit-GEMM kernel for fp32 blobs): 2-D results,
+    // constant C (or none) that broadcasts along the weight rows
+    if (output_N1M == 0 && constantC == 1)
     {
+        const bool c_cols_ok = !has_c || bt == 0 || bt == 4;              // scalar / per column n
+        const bool c_rows_ok = !has_c || bt == 0 || bt == 1 || bt == 2;   // scalar / per row m
+        if (constantB == 1 && constantA == 0 && transA == 0 && c_cols_ok && B_data.dims == 2)
+            linear_mode = 1;
+        else if (constantA == 1 && constantB == 0 && transB == 1 && c_rows_ok && A_data.dims == 2)
+            linear_mode = 2;
+    }
+    if (linear_mode)
+    {
+        // W[out][k]: mode 1 out = n, W = alpha * op(B)^T; mode 2 out = m, W = alpha * op(A)
+        const Mat& Wsrc = linear_mode == 1 ? B_data : A_data;
+        const int out = linear_mode == 1 ? constantN : constantM;
+        // stored [out][K] when (mode 1, transB = 1) or (mode 2, transA = 0); otherwise stored [K][out]
+        const bool stored_out_major = linear_mode == 1 ? transB == 1 : transA == 0;
+        std::vector<float> W((size_t)out * constantK), bias;
+        const float* src = (const float*)Wsrc.data;
+        for (int o = 0; o < out; o++)
+            for (int k = 0; k < constantK; k++)
+                W[(size_t)o * constantK + k] = alpha * (stored_out_major ? src[(size_t)o * Wsrc.w + k] : src[(size_t)k * Wsrc.w + o]);
+        if (has_c)
+        {
+            bias.resize(out);
+            const float* c = (const float*)C_data.data;
+            for (int o = 0; o < out; o++) bias[o] = alpha * beta * (bt == 0 ? c[0] : c[o]);
+        }
         ncnn_cuda_linear_desc d;
         memset(&d, 0, sizeof(d));
         d.num_input = constantK;
-        d.num_output = constantN;
+        d.num_output = out;
         d.bias_term = has_c ? 1 : 0;
         d.elemtype = elemtype;
-        int ret = ncnn_cuda_linear_create(&linear, &d, (const float*)B_data.data, has_c ? (const float*)C_data.data : 0, 0);
+        int ret = ncnn_cuda_linear_create(&linear, &d, W.data(), has_c ? bias.data() : 0, 0);
         if (ret != 0) return ret;
         return 0;
     }
@@ -149,30 +199,84 @@ int Gemm::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cm
     return ret;
 }
 
+// rows x cols view of a device operand: a 2-D blob (w, h) is h pixels of w channels, a 3-D blob (w, 1, c) is w pixels of c
+// channels -- the same logical matrix (rows = c) with the strides swapped
+struct DevMatrix
+{
+    int rows, cols;
+    long long rs, cs;
+    bool ok;
+};
+
+static DevMatrix dev_matrix(const CudaMat& m)
+{
+    DevMatrix v;
+    v.ok = true;
+    if (m.dims == 2)
+    {
+        v.rows = m.h;
+        v.cols = m.w;
+        v.rs = m.cpitch;
+        v.cs = 1;
+    }
+    else if (m.dims == 3 && m.h == 1)
+    {
+        v.rows = m.c;
+        v.cols = m.w;
+        v.rs = 1;
+        v.cs = m.cpitch;
+    }
+    else if (m.dims == 1)
+    {
+        v.rows = 1;
+        v.cols = m.w;
+        v.rs = m.cpitch;
+        v.cs = 1;
+    }
+    else
+        v.ok = false;
+    return v;
+}
+
 int Gemm::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat>& top_blobs, CudaCompute& cmd, const Option& opt) const
 {
     CudaMat& top = top_blobs[0];
+    if (linear && bottom_blobs[0].dims == 2 && bottom_blobs[0].w == constantK && bottom_blobs[0].elemtype == elemtype)
+    {
+        // rows of the runtime operand x W^T: mode 1 gives Y (M x N), mode 2 gives Y^T (N x M)
+        const CudaMat& X = bottom_blobs[0];
+        const int out = linear_mode == 1 ? constantN : constantM;
+        const bool want_transposed = linear_mode == 1 ? output_transpose != 0 : output_transpose == 0;
+        CudaMat direct;
+        CudaMat& first = want_transposed ? direct : top;
+        first.create(out, X.h, X.elemtype, X.n, want_transposed ? cmd.workspace_allocator(opt) : cmd.blob_allocator(opt));
+        if (first.empty()) return -100;
+        ncnn_cuda_tensor b = X.view(), t = first.view();
+        int ret = ncnn_cuda_linear_forward(linear, &b, &t, cmd.stream());
+        if (ret != 0 || !want_transposed) return ret;
+        top.create(X.h, out, X.elemtype, X.n, cmd.blob_allocator(opt));
+        if (top.empty()) return -100;
+        ncnn_cuda_tensor s = direct.view(), d = top.view();
+        return ncnn_cuda_permute(&s, &d, 1, cmd.stream());
+    }
     if (linear)
     {
-        const CudaMat& X = bottom_blobs[0];
-        if (X.dims != 2 || X.w != constantK) return -1;
-        top.create(constantN, X.h, X.elemtype, X.n, cmd.blob_allocator(opt));
-        if (top.empty()) return -100;
-        ncnn_cuda_tensor b = X.view(), t = top.view();
-        return ncnn_cuda_linear_forward(linear, &b, &t, cmd.stream());
+        NCNN_LOGE("Gemm %s: runtime operand does not match the constant-operand pipeline (dims %d w %d, K %d)", name.c_str(), bottom_blobs[0].dims, bottom_blobs[0].w, constantK);
+        return -1;
     }
 
     const CudaMat& A0 = constantA ? A_dev : bottom_blobs[0];
     const CudaMat& B0 = constantB ? B_dev : (constantA ? bottom_blobs[0] : bottom_blobs[1]);
-    if (A0.dims != 2 || B0.dims != 2)
+    const DevMatrix Am = dev_matrix(A0), Bm = dev_matrix(B0);
+    if (!Am.ok || !Bm.ok)
     {
-        NCNN_LOGE("Gemm %s: only 2-D operands are supported by the CUDA backend", name.c_str());
+        NCNN_LOGE("Gemm %s: operands must be 2-D or (w, 1, c) blobs", name.c_str());
         return -1;
     }
-    const int M = transA ? A0.w : A0.h;
-    const int K = transA ? A0.h : A0.w;
-    const int N = transB ? B0.h : B0.w;
-    if ((transB ? B0.w : B0.h) != K) return -1;
+    const int M = transA ? Am.cols : Am.rows;
+    const int K = transA ? Am.rows : Am.cols;
+    const int N = transB ? Bm.rows : Bm.cols;
+    if ((transB ? Bm.cols : Bm.rows) != K) return -1;
 
     CudaMat C;
     int bt = 0;
@@ -231,12 +335,12 @@ int Gemm::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat>
     g.K = K;
     g.batch = n;
     g.a = A0.data;
-    g.a_rs = transA ? 1 : A0.cpitch;
-    g.a_cs = transA ? A0.cpitch : 1;
+    g.a_rs = transA ? Am.cs : Am.rs; // A(i, k)
+    g.a_cs = transA ? Am.rs : Am.cs;
     g.a_bs = (constantA || A0.n <= 1) ? 0 : (long long)A0.nstep;
     g.b = B0.data;
-    g.b_rs = transB ? 1 : B0.cpitch; // B(k, j)
-    g.b_cs = transB ? B0.cpitch : 1;
+    g.b_rs = transB ? Bm.cs : Bm.rs; // B(k, j)
+    g.b_cs = transB ? Bm.rs : Bm.cs;
     g.b_bs = (constantB || B0.n <= 1) ? 0 : (long long)B0.nstep;
     if (!C.empty())
     {

@@ -72,7 +72,7 @@ KERNEL_ABI_SYMBOLS = [
     "ncnn_cuda_memcpy_d2d_async", "ncnn_cuda_memset_async", "ncnn_cuda_stream_create", "ncnn_cuda_stream_destroy", "ncnn_cuda_stream_sync",
     "ncnn_cuda_device_sync", "ncnn_cuda_event_create", "ncnn_cuda_event_destroy", "ncnn_cuda_event_record", "ncnn_cuda_event_sync",
     "ncnn_cuda_event_elapsed_ms", "ncnn_cuda_graph_begin_capture", "ncnn_cuda_graph_end_capture", "ncnn_cuda_graph_launch", "ncnn_cuda_graph_destroy",
-    "ncnn_cuda_launch_count", "ncnn_cuda_pack_from_planar", "ncnn_cuda_unpack_to_planar", "ncnn_cuda_reshape", "ncnn_cuda_permute",
+    "ncnn_cuda_launch_count", "ncnn_cuda_tc_launch_count", "ncnn_cuda_pack_from_planar", "ncnn_cuda_unpack_to_planar", "ncnn_cuda_reshape", "ncnn_cuda_permute",
     "ncnn_cuda_conv2d_create", "ncnn_cuda_conv2d_destroy", "ncnn_cuda_conv2d_forward", "ncnn_cuda_conv2d_workspace_size", "ncnn_cuda_conv2d_algo",
     "ncnn_cuda_dwconv2d_create", "ncnn_cuda_dwconv2d_destroy", "ncnn_cuda_dwconv2d_forward", "ncnn_cuda_pool2d_forward",
     "ncnn_cuda_linear_create", "ncnn_cuda_linear_destroy", "ncnn_cuda_linear_forward", "ncnn_cuda_gemm_strided",
