@@ -157,7 +157,8 @@ typedef struct ncnn_cuda_conv2d_desc
 {
     int inch, outch;
     int kernel_w, kernel_h, dilation_w, dilation_h, stride_w, stride_h;
-    int pad_left, pad_right, pad_top, pad_bottom; /* resolved, >= 0 (host resolves -233/-234 per input size) */
+    int pad_left, pad_right, pad_top, pad_bottom; /* the layer's fixed padding, or -1 when it is resolved per call (SAME_UPPER / SAME_LOWER
+                                                    * depend on the input size: the host passes the resolved pads to forward) */
     float pad_value;
     int bias_term;
     ncnn_cuda_activation act;

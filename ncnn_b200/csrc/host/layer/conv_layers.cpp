@@ -128,10 +128,13 @@ int Convolution::create_pipeline(const Option& opt)
     desc.dilation_h = dilation_h;
     desc.stride_w = stride_w;
     desc.stride_h = stride_h;
-    desc.pad_left = pad_left > 0 ? pad_left : 0;
-    desc.pad_right = pad_right > 0 ? pad_right : 0;
-    desc.pad_top = pad_top > 0 ? pad_top : 0;
-    desc.pad_bottom = pad_bottom > 0 ? pad_bottom : 0;
+    // SAME_UPPER / SAME_LOWER (-233 / -234) resolve per input size at forward time: the descriptor carries -1 ("not known yet"),
+    // so the kernel plan does not build the fixed-padding stem variant for a padding the layer will never use
+    const bool pads_known = pad_left >= 0 && pad_right >= 0 && pad_top >= 0 && pad_bottom >= 0;
+    desc.pad_left = pads_known ? pad_left : -1;
+    desc.pad_right = pads_known ? pad_right : -1;
+    desc.pad_top = pads_known ? pad_top : -1;
+    desc.pad_bottom = pads_known ? pad_bottom : -1;
     desc.pad_value = pad_value;
     desc.bias_term = bias_term;
     desc.act = make_activation(activation_type, activation_params);
@@ -252,6 +255,12 @@ int ConvolutionDepthWise::load_param(const ParamDict& pd)
         return -1;
     }
     if (group <= 0 || num_output % group != 0) return -1; // reference: "num_output % group != 0" -> -100
+    // a malformed param must fail here, not divide by zero in create_pipeline (weight_data_size / maxk) or loop forever in a kernel
+    if (num_output <= 0 || kernel_w <= 0 || kernel_h <= 0 || stride_w <= 0 || stride_h <= 0 || dilation_w <= 0 || dilation_h <= 0 || weight_data_size <= 0)
+    {
+        NCNN_LOGE("ConvolutionDepthWise: invalid num_output / kernel / stride / dilation / weight_data_size");
+        return -1;
+    }
     return 0;
 }
 
@@ -540,6 +549,14 @@ int Pooling::load_param(const ParamDict& pd)
     out_w = pd.get(8, 0);
     out_h = pd.get(18, out_w);
     if (pooling_type != 0 && pooling_type != 1) return -1;
+    // windowed pooling needs a real window and step (the output-size formula divides by the stride); global and adaptive
+    // pooling take their geometry from the blob
+    if (!global_pooling && !adaptive_pooling && (kernel_w <= 0 || kernel_h <= 0 || stride_w <= 0 || stride_h <= 0))
+    {
+        NCNN_LOGE("Pooling: invalid kernel / stride");
+        return -1;
+    }
+    if (adaptive_pooling && (out_w < 0 || out_h < 0)) return -1;
     return 0;
 }
 

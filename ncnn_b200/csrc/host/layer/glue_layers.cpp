@@ -428,9 +428,12 @@ static int interp_run(const Interp* self, const CudaMat& bottom, int outw, int o
     }
     top.create(outw, outh, bottom.c, bottom.elemtype, bottom.n, cmd.blob_allocator(opt));
     if (top.empty()) return -100;
-    // interp.cpp:606-607
-    const float hs = explicit_size ? h / (float)outh : 1.f / self->height_scale;
-    const float ws = explicit_size ? w / (float)outw : 1.f / self->width_scale;
+    // interp.cpp:606-607: the nearest-neighbour source step comes from the layer's OWN output_height / output_width members when they
+    // are set and from its scale factors otherwise -- also when the target size was lent by a second bottom (dynamic_target_size),
+    // where the reference therefore steps by 1 / scale (1 by default) and clamps; reproduced as is
+    (void)explicit_size;
+    const float hs = self->output_height ? h / (float)outh : 1.f / self->height_scale;
+    const float ws = self->output_width ? w / (float)outw : 1.f / self->width_scale;
     ncnn_cuda_tensor b = bottom.view(), t = top.view();
     return ncnn_cuda_interp(self->resize_type, self->align_corner, hs, ws, &b, &t, cmd.stream());
 }

@@ -276,14 +276,22 @@ int Net::load_param_text(const std::string& text)
         }
         // top shape hints, id 30 (src/net.cpp:1487-1519)
         Mat shape_hints = pd.get(30, Mat());
-        if (!shape_hints.empty() && top_count > 0)
+        // an int array of top_count records of (dims, extents...): anything else (a float array, too few values) is ignored
+        const int hint_type = pd.type(30);
+        const int psh_step_checked = (!shape_hints.empty() && top_count > 0) ? shape_hints.w / top_count : 0;
+        if ((hint_type == 5 || hint_type == 4) && psh_step_checked >= 2)
         {
-            const int psh_step = shape_hints.w / top_count;
+            const int psh_step = psh_step_checked;
             const int* psh = (const int*)shape_hints.data;
             for (int j = 0; j < top_count; j++)
             {
                 Blob& blob = d->blobs[layer->tops[j]];
                 int dims = psh[0];
+                if (dims < 1 || dims > 4 || dims + 1 > psh_step)
+                {
+                    psh += psh_step;
+                    continue;
+                }
                 if (dims == 1) blob.shape = shape_hint_mat(1, psh[1], 1, 1, 1);
                 if (dims == 2) blob.shape = shape_hint_mat(2, psh[1], psh[2], 1, 1);
                 if (dims == 3) blob.shape = psh_step == 5 ? shape_hint_mat(3, psh[1], psh[2], 1, psh[4]) : shape_hint_mat(3, psh[1], psh[2], 1, psh[3]);
@@ -489,9 +497,29 @@ int Net::load_param_bin(const DataReader& dr)
         READ_VALUE(typeindex)
         READ_VALUE(bottom_count)
         READ_VALUE(top_count)
-        const char* type = layer_index_to_type(typeindex);
+        // typeindex with LayerType::CustomBit (1 << 8, src/layer_type.h) addresses the custom-layer registry by position
+        // (src/net.cpp:1715-1726: create_custom_layer(typeindex & ~CustomBit))
+        const int kCustomBit = 1 << 8;
+        const char* type = 0;
         int custom_index = -1;
-        Layer* layer = type ? create_layer_by_type(type, &custom_index) : 0;
+        Layer* layer = 0;
+        std::string custom_type_name;
+        if (typeindex & kCustomBit)
+        {
+            const int ci = typeindex & ~kCustomBit;
+            if (ci >= 0 && ci < (int)d->custom_layer_registry.size() && d->custom_layer_registry[ci].creator)
+            {
+                layer = d->custom_layer_registry[ci].creator(d->custom_layer_registry[ci].userdata);
+                if (layer) custom_index = ci;
+                custom_type_name = d->custom_layer_registry[ci].name;
+                type = custom_type_name.c_str();
+            }
+        }
+        else
+        {
+            type = layer_index_to_type(typeindex);
+            layer = type ? create_layer_by_type(type, &custom_index) : 0;
+        }
         if (!layer)
         {
             NCNN_LOGE("layer %d not exists or registered (the CUDA backend has no CPU fallback)", typeindex);
@@ -865,6 +893,7 @@ int NetPrivate::fuse_graph(const Option&)
                     blobs[newtop].producer = i;
                     blobs[top].producer = -1;
                     blobs[top].consumer = -1;
+                    blobs[top].folded_into = i;
                     a->bottoms.clear();
                     a->tops.clear();
                     retire(j);
@@ -931,12 +960,14 @@ int NetPrivate::fuse_graph(const Option&)
                         layers[relu_layer]->tops.clear();
                         blobs[etop].producer = -1;
                         blobs[etop].consumer = -1;
+                        blobs[etop].folded_into = best;
                         retire(relu_layer);
                     }
                     c->tops[0] = final_top;
                     blobs[final_top].producer = best;
                     blobs[conv_top].producer = -1;
                     blobs[conv_top].consumer = -1;
+                    blobs[conv_top].folded_into = best;
                     e->bottoms.clear();
                     e->tops.clear();
                     retire(j);
@@ -952,6 +983,7 @@ int NetPrivate::fuse_graph(const Option&)
             blobs[newtop].producer = j;
             blobs[etop].producer = -1;
             blobs[etop].consumer = -1;
+            blobs[etop].folded_into = j;
             layers[relu_layer]->bottoms.clear();
             layers[relu_layer]->tops.clear();
             retire(relu_layer);
@@ -1071,14 +1103,28 @@ class ExtractorPrivate
 {
 public:
     explicit ExtractorPrivate(const Net* _net)
-        : net(_net), h2d(0), d2h(0)
+        : net(_net), h2d(0), d2h(0), ctx(0)
     {
+    }
+    // One stream + device pool for the Extractor's whole life (acquired at the first host extract, handed back by clear() / the
+    // destructor): the device blobs an Extractor keeps between extract() calls belong to this pool and were enqueued on this
+    // stream, so a later extract() must not run on another stream while those blocks are recycled.
+    CudaContext* context()
+    {
+        if (!ctx) ctx = acquire_cuda_context(net->opt.cuda_device_index);
+        return ctx;
+    }
+    void release_context()
+    {
+        if (ctx) reclaim_cuda_context(ctx);
+        ctx = 0;
     }
     const Net* net;
     std::vector<Mat> blob_mats;
     std::vector<CudaMat> blob_mats_gpu;
     Option opt;
     size_t h2d, d2h;
+    CudaContext* ctx;
     // inputs given as raw 8-bit pixels, converted on the device when the walk starts
     struct PixelInput
     {
@@ -1128,7 +1174,8 @@ Extractor& Extractor::operator=(const Extractor& rhs)
 void Extractor::clear()
 {
     d->blob_mats.clear();
-    d->blob_mats_gpu.clear();
+    d->blob_mats_gpu.clear(); // (device blocks go back to the pool of the pinned context before the context itself does)
+    d->release_context();
 }
 
 void Extractor::set_light_mode(bool enable)
@@ -1161,9 +1208,21 @@ int Extractor::input(const char* blob_name, const Mat& in)
     return input(blob_index, in);
 }
 
+// a blob that load-time fusion folded into a layer does not exist at run time (was silently ignored / "no producer")
+static int reject_folded_blob(const Net* net, int blob_index, const char* what)
+{
+    const Blob& b = net->blobs()[blob_index];
+    if (b.folded_into < 0) return 0;
+    NCNN_LOGE("%s: blob %s was folded into layer %s by load-time graph fusion and is never materialised; load the net with "
+              "opt.use_cuda_graph_fusion = false (ncnn_option_set_use_cuda_graph_fusion(opt, 0)) to %s it",
+              what, b.name.c_str(), net->layers()[b.folded_into]->name.c_str(), what);
+    return -1;
+}
+
 int Extractor::input(int blob_index, const Mat& in)
 {
     if (blob_index < 0 || blob_index >= (int)d->blob_mats.size()) return -1;
+    if (reject_folded_blob(d->net, blob_index, "input")) return -1;
     d->blob_mats[blob_index] = in;
     d->blob_mats_gpu[blob_index].release();
     return 0;
@@ -1179,6 +1238,7 @@ int Extractor::input(const char* blob_name, const CudaMat& in)
 int Extractor::input(int blob_index, const CudaMat& in)
 {
     if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
+    if (reject_folded_blob(d->net, blob_index, "input")) return -1;
     d->blob_mats_gpu[blob_index] = in;
     d->blob_mats[blob_index].release();
     return 0;
@@ -1195,6 +1255,7 @@ int Extractor::input_pixels_resize(const char* blob_name, const unsigned char* p
 {
     int blob_index = d->net->find_blob_index_by_name(blob_name);
     if (blob_index == -1 || !pixels) return -1;
+    if (reject_folded_blob(d->net, blob_index, "input")) return -1;
     ExtractorPrivate::PixelInput pi;
     pi.blob_index = blob_index;
     pi.pixels = pixels;
@@ -1249,12 +1310,13 @@ int Extractor::extract(const char* blob_name, Mat& feat, int type)
 int Extractor::extract(int blob_index, Mat& feat, int /*type*/)
 {
     if (blob_index < 0 || blob_index >= (int)d->blob_mats.size()) return -1;
+    if (reject_folded_blob(d->net, blob_index, "extract")) return -1;
     if (!d->blob_mats[blob_index].empty())
     {
         feat = d->blob_mats[blob_index];
         return 0;
     }
-    CudaContext* ctx = acquire_cuda_context(d->net->opt.cuda_device_index);
+    CudaContext* ctx = d->context();
     if (!ctx)
     {
         NCNN_LOGE("no CUDA device available: %s", ncnn_cuda_last_error());
@@ -1274,7 +1336,6 @@ int Extractor::extract(int blob_index, Mat& feat, int /*type*/)
         d->h2d = cmd.h2d_bytes;
         d->d2h = cmd.d2h_bytes;
     }
-    reclaim_cuda_context(ctx);
     if (ret != 0) return ret;
     feat = d->blob_mats[blob_index];
     return 0;
@@ -1291,6 +1352,7 @@ int Extractor::extract(const char* blob_name, CudaMat& feat, CudaCompute& cmd)
 int Extractor::extract(int blob_index, CudaMat& feat, CudaCompute& cmd)
 {
     if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
+    if (reject_folded_blob(d->net, blob_index, "extract")) return -1;
     int ret = 0;
     // pixel inputs first: upload the raw bytes, convert + normalise on the device
     for (size_t i = 0; i < d->pixel_inputs.size(); i++)
@@ -1327,7 +1389,7 @@ int Extractor::extract_yolov8_proposals(const char* blob_name, const int* stride
 {
     int blob_index = d->net->find_blob_index_by_name(blob_name);
     if (blob_index == -1) return -1;
-    CudaContext* ctx = acquire_cuda_context(d->net->opt.cuda_device_index);
+    CudaContext* ctx = d->context();
     if (!ctx)
     {
         NCNN_LOGE("no CUDA device available: %s", ncnn_cuda_last_error());
@@ -1355,7 +1417,6 @@ int Extractor::extract_yolov8_proposals(const char* blob_name, const int* stride
         d->h2d = cmd.h2d_bytes;
         d->d2h = cmd.d2h_bytes;
     }
-    reclaim_cuda_context(ctx);
     return ret;
 }
 

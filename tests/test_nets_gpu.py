@@ -591,3 +591,42 @@ def test_yolov8_device_decode(ref):
         oa, ow = np.argsort(-a[:, 4], kind="stable")[:300], np.argsort(-w_[:, 4], kind="stable")[:300]
         if np.array_equal(oa, ow):  # equal scores can order differently; NMS is only comparable on the same order
             assert oy.nms_sorted_bboxes(a[oa], 0.45) == oy.nms_sorted_bboxes(w_[ow], 0.45)
+
+
+def test_folded_blob_is_rejected_not_silently_ignored(ref):
+    """load-time fusion folds `c1` (a Convolution's pre-activation output) into conv1: extracting or feeding it must fail loudly,
+    and the same graph loaded with opt.use_cuda_graph_fusion = 0 serves it like the reference does"""
+    import ctypes as C
+    from ncnn_b200 import capi
+    L = product()
+    text = ("7767517\n4 4\nInput data 0 1 data 0=8 1=8 2=3\nConvolution conv1 1 1 data c1 0=4 1=3 4=1 5=1 6=108\n"
+            "ReLU relu1 1 1 c1 r1\nConvolution conv2 1 1 r1 output 0=2 1=1 5=1 6=8\n")
+    weights = modelzoo.random_model_bytes(text, seed=11)
+    x = np.random.default_rng(4).uniform(-1, 1, (3, 8, 8)).astype(np.float32)
+    want = run_ref(ref, text, weights, {"data": x}, batched=False, outputs=["c1", "output"])
+    for fusion in (1, 0):
+        opt = L.make_option(1, **MODES["fp32"])
+        L.lib.ncnn_option_set_use_cuda_graph_fusion(opt, fusion)
+        net = capi.Net(L, text, weights, opt)
+        try:
+            ex = L.lib.ncnn_extractor_create(net.net)
+            m = L.mat_from_numpy(x)
+            out = C.c_void_p()
+            assert L.lib.ncnn_extractor_input(ex, b"data", m) == 0
+            r = L.lib.ncnn_extractor_extract(ex, b"c1", C.byref(out))
+            if fusion:
+                assert r != 0, "a folded blob must not be extractable"
+                assert L.lib.ncnn_extractor_input(ex, b"c1", m) != 0, "feeding a folded blob must fail, not be ignored"
+            else:
+                assert r == 0
+                assert nerr(L.mat_to_numpy(out), want["c1"]) <= 1e-5
+                L.lib.ncnn_mat_destroy(out)
+            out = C.c_void_p()
+            assert L.lib.ncnn_extractor_extract(ex, b"output", C.byref(out)) == 0
+            assert nerr(L.mat_to_numpy(out), want["output"]) <= 1e-5
+            L.lib.ncnn_mat_destroy(out)
+            L.lib.ncnn_mat_destroy(m)
+            L.lib.ncnn_extractor_destroy(ex)
+        finally:
+            net.close()
+            L.lib.ncnn_option_destroy(opt)
