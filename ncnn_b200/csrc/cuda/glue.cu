@@ -15,10 +15,29 @@ struct Flat
     int C, cpitch;
 };
 
+// "dense" for the flat (whole-buffer) kernels: samples back to back AND no foreign data between the pixels -- a channel-range
+// view into a wider blob (Slice views, producers writing into their Concat's buffer) has cpitch far beyond its own channels and
+// the lanes in between belong to its neighbours
 static bool is_dense(const ncnn_cuda_tensor* t)
 {
     TView v = make_view(t);
+    if ((long long)(v.cpitch - v.C) * (long long)elem_size(t->elemtype) >= 16) return false;
     return v.n == 1 || v.nstep == (long long)v.P * v.cpitch;
+}
+
+// pixel-dense: element (b, p, q) at (b * P + p) * cpitch + q -- true for compact blobs and for channel-range views alike
+static bool is_pixel_dense(const ncnn_cuda_tensor* t)
+{
+    TView v = make_view(t);
+    return v.n == 1 || v.nstep == (long long)v.P * v.cpitch;
+}
+
+// the pitched vector kernels below: same logical shape, C a whole number of 16-byte vectors, every operand pixel-dense with a
+// 16-byte aligned base and pitch
+static bool pitched_vec_ok(const ncnn_cuda_tensor* t, int vec)
+{
+    TView v = make_view(t);
+    return v.C > 0 && v.C % vec == 0 && t->cpitch % vec == 0 && (((uintptr_t)t->data) & 15) == 0 && is_pixel_dense(t);
 }
 
 // total addressable elements of a dense blob including pad lanes
@@ -80,6 +99,24 @@ __global__ void __launch_bounds__(256) unary_flat_kernel(const T* __restrict__ i
         out[i] = from_f32<T>(unary_apply(op, to_f32(in[i]), p0, p1));
 }
 
+// one thread per (pixel, 16-byte channel vector); in / out may be channel-range views with their own pitches
+template<typename T, int VEC>
+__global__ void __launch_bounds__(256) unary_pitched_kernel(const T* __restrict__ in, T* __restrict__ out, long long npix, int CV, int icp, int ocp, int op, float p0, float p1)
+{
+    NC_PDL_PROLOGUE();
+    const long long total = npix * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const long long pix = i / CV;
+        const int q = (int)(i - pix * CV) * VEC;
+        float v[VEC];
+        load_vec_f32<T, VEC>(in + pix * icp + q, v);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) v[k] = unary_apply(op, v[k], p0, p1);
+        store_vec_f32<T, VEC>(out + pix * ocp + q, v);
+    }
+}
+
 template<typename T>
 __global__ void unary_strided_kernel(const T* __restrict__ in, T* __restrict__ out, int n, int P, int C, int icp, long long ins, int ocp, long long ons, int op, float p0, float p1)
 {
@@ -104,6 +141,14 @@ static int run_unary(int op, float p0, float p1, const ncnn_cuda_tensor* bottom,
         long long count = flat_count(bottom);
         if (count == 0) return 0;
         NC_PDL_LAUNCH((unary_flat_kernel<T, VEC>), grid_for(count / VEC + 1, 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, count, op, p0, p1);
+    }
+    else if (pitched_vec_ok(bottom, VEC) && pitched_vec_ok(top, VEC))
+    {
+        TView b = make_view(bottom);
+        const long long npix = (long long)b.n * b.P;
+        if (npix == 0) return 0;
+        NC_PDL_LAUNCH((unary_pitched_kernel<T, VEC>), grid_for(npix * (b.C / VEC), 256), 256, 0, stream, (const T*)bottom->data, (T*)top->data, npix, b.C / VEC, bottom->cpitch,
+                      top->cpitch, op, p0, p1);
     }
     else
     {
@@ -171,6 +216,46 @@ struct EltStrided
     long long nstep[8];
 };
 
+template<typename T, int VEC>
+__global__ void __launch_bounds__(256) eltwise_pitched_kernel(EltArgs a, EltStrided s, T* __restrict__ out, long long npix, int CV, int ocp)
+{
+    NC_PDL_PROLOGUE();
+    const long long total = npix * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const long long pix = i / CV;
+        const int q = (int)(i - pix * CV) * VEC;
+        float acc[VEC];
+        load_vec_f32<T, VEC>((const T*)a.in[0] + pix * s.cpitch[0] + q, acc);
+        if (a.op == 1 && a.has_coeff)
+        {
+#pragma unroll
+            for (int k = 0; k < VEC; k++) acc[k] *= a.coeff[0];
+        }
+        for (int j = 1; j < a.count; j++)
+        {
+            float v[VEC];
+            load_vec_f32<T, VEC>((const T*)a.in[j] + pix * s.cpitch[j] + q, v);
+#pragma unroll
+            for (int k = 0; k < VEC; k++)
+            {
+                if (a.op == 0)
+                    acc[k] *= v[k];
+                else if (a.op == 1)
+                    acc[k] = a.has_coeff ? acc[k] + v[k] * a.coeff[j] : acc[k] + v[k];
+                else
+                    acc[k] = fmaxf(acc[k], v[k]);
+            }
+        }
+        if (a.relu)
+        {
+#pragma unroll
+            for (int k = 0; k < VEC; k++) acc[k] = fmaxf(acc[k], 0.f);
+        }
+        store_vec_f32<T, VEC>(out + pix * ocp + q, acc);
+    }
+}
+
 template<typename T>
 __global__ void eltwise_strided_kernel(EltArgs a, EltStrided s, T* __restrict__ out, int n, int P, int C, int ocp, long long ons)
 {
@@ -210,6 +295,19 @@ static int run_eltwise(EltArgs& a, const ncnn_cuda_tensor* bottoms, const ncnn_c
         long long count = flat_count(top);
         if (count == 0) return 0;
         NC_PDL_LAUNCH((eltwise_flat_kernel<T, VEC>), grid_for(count / VEC, 256), 256, 0, stream, a, (T*)top->data, count);
+    }
+    else if ([&]() { bool ok = pitched_vec_ok(top, VEC); for (int j = 0; j < a.count && ok; j++) ok = pitched_vec_ok(&bottoms[j], VEC); return ok; }())
+    {
+        EltStrided s;
+        for (int j = 0; j < a.count; j++)
+        {
+            s.cpitch[j] = bottoms[j].cpitch;
+            s.nstep[j] = bottoms[j].nstep;
+        }
+        TView t = make_view(top);
+        const long long npix = (long long)t.n * t.P;
+        if (npix == 0) return 0;
+        NC_PDL_LAUNCH((eltwise_pitched_kernel<T, VEC>), grid_for(npix * (t.C / VEC), 256), 256, 0, stream, a, s, (T*)top->data, npix, t.C / VEC, top->cpitch);
     }
     else
     {
@@ -328,6 +426,31 @@ __global__ void __launch_bounds__(256) binary_flat_kernel(const T* __restrict__ 
     }
 }
 
+template<typename T, int VEC>
+__global__ void __launch_bounds__(256) binary_pitched_kernel(const T* __restrict__ a, const T* __restrict__ b, float scalar, int use_scalar, T* __restrict__ out, long long npix, int CV,
+                                                            int acp, int bcp, int ocp, int op)
+{
+    NC_PDL_PROLOGUE();
+    const long long total = npix * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const long long pix = i / CV;
+        const int q = (int)(i - pix * CV) * VEC;
+        float va[VEC], vb[VEC];
+        load_vec_f32<T, VEC>(a + pix * acp + q, va);
+        if (use_scalar)
+        {
+#pragma unroll
+            for (int k = 0; k < VEC; k++) vb[k] = scalar;
+        }
+        else
+            load_vec_f32<T, VEC>(b + pix * bcp + q, vb);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) va[k] = binary_apply(op, va[k], vb[k]);
+        store_vec_f32<T, VEC>(out + pix * ocp + q, va);
+    }
+}
+
 static BShape bshape(const ncnn_cuda_tensor* t)
 {
     BShape s;
@@ -365,6 +488,17 @@ static int run_binary(int op, const ncnn_cuda_tensor* a, const ncnn_cuda_tensor*
         long long count = flat_count(top);
         if (count == 0) return 0;
         NC_PDL_LAUNCH((binary_flat_kernel<T, VEC>), grid_for(count / VEC, 256), 256, 0, stream, (const T*)a->data, b ? (const T*)b->data : 0, scalar, use_scalar, (T*)top->data, count, op);
+        NC_LAUNCH_CHECK();
+        return 0;
+    }
+    if (same_shape(a, top) && (!b || same_shape(b, top)) && pitched_vec_ok(a, VEC) && pitched_vec_ok(top, VEC) && (!b || pitched_vec_ok(b, VEC)))
+    {
+        // same logical shape, operands may be channel-range views with their own pitches
+        TView t = make_view(top);
+        const long long npix = (long long)t.n * t.P;
+        if (npix == 0) return 0;
+        NC_PDL_LAUNCH((binary_pitched_kernel<T, VEC>), grid_for(npix * (t.C / VEC), 256), 256, 0, stream, (const T*)a->data, b ? (const T*)b->data : 0, scalar, use_scalar,
+                      (T*)top->data, npix, t.C / VEC, a->cpitch, b ? b->cpitch : 0, top->cpitch, op);
         NC_LAUNCH_CHECK();
         return 0;
     }

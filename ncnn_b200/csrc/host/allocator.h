@@ -80,6 +80,18 @@ public:
     virtual void clear();
     virtual void* fastMalloc(size_t size) = 0;
     virtual void fastFree(void* ptr) = 0;
+    // Placement hook of CudaMat::create_dims: an allocator may hand out a VIEW into memory it manages (own pitch, shared
+    // refcount) for the blob being created -- how a producer writes straight into the channel range of its Concat's buffer
+    // (CudaPlacementAllocator, net.cpp).  Default: no placement.
+    virtual bool place(class CudaMat& /*m*/)
+    {
+        return false;
+    }
+    // the allocator a blob allocated through this one must be freed with (a placement allocator lives on the executor's stack)
+    virtual CudaAllocator* real()
+    {
+        return this;
+    }
     int device_index;
 };
 

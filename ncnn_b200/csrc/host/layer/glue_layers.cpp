@@ -370,9 +370,20 @@ int Slice::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat
             if (slice == -233) slice = (int)((extent - q) / (top_blobs.size() - i));
         }
         if (slice <= 0 || q + slice > extent) return -1;
+        CudaMat& top = top_blobs[i];
+        if (opt.use_cuda_graph_fusion && dims == 3 && positive_axis == 0)
+        {
+            // channel ranges of a channel-innermost blob are VIEWS (same pixels, same pitch, data moved by q channels): no copy;
+            // needs a 16-byte aligned start (every consumer addresses blobs through cpitch / nstep)
+            top = bottom.channel_range(q, slice);
+            if (!top.empty())
+            {
+                q += slice;
+                continue;
+            }
+        }
         int w = bottom.w, h = bottom.h, d = bottom.d, c = bottom.c;
         set_axis_extent(dims, positive_axis, slice, w, h, d, c);
-        CudaMat& top = top_blobs[i];
         top.create_dims(dims, w, h, d, c, bottom.elemtype, bottom.n, cmd.blob_allocator(opt));
         if (top.empty()) return -100;
         ncnn_cuda_tensor t = top.view();

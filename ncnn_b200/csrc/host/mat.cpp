@@ -634,12 +634,12 @@ const float* Mat::row(int y) const
 
 // ------------------------------------------------------------------ CudaMat
 CudaMat::CudaMat()
-    : data(0), refcount(0), allocator(0), elemtype(NCNN_CUDA_F32), dims(0), w(0), h(0), d(0), c(0), n(1), cpitch(0), nstep(0)
+    : data(0), base(0), refcount(0), allocator(0), elemtype(NCNN_CUDA_F32), dims(0), w(0), h(0), d(0), c(0), n(1), cpitch(0), nstep(0)
 {
 }
 
 CudaMat::CudaMat(const CudaMat& m)
-    : data(m.data), refcount(m.refcount), allocator(m.allocator), elemtype(m.elemtype), dims(m.dims), w(m.w), h(m.h), d(m.d), c(m.c), n(m.n), cpitch(m.cpitch),
+    : data(m.data), base(m.base), refcount(m.refcount), allocator(m.allocator), elemtype(m.elemtype), dims(m.dims), w(m.w), h(m.h), d(m.d), c(m.c), n(m.n), cpitch(m.cpitch),
       nstep(m.nstep)
 {
     addref();
@@ -656,6 +656,7 @@ CudaMat& CudaMat::operator=(const CudaMat& m)
     if (m.refcount) NCNN_XADD(m.refcount, 1);
     release();
     data = m.data;
+    base = m.base;
     refcount = m.refcount;
     allocator = m.allocator;
     elemtype = m.elemtype;
@@ -679,10 +680,11 @@ void CudaMat::release()
 {
     if (refcount && NCNN_XADD(refcount, -1) == 1)
     {
-        if (allocator && data) allocator->fastFree(data);
+        if (allocator && base) allocator->fastFree(base);
         delete refcount;
     }
     data = 0;
+    base = 0;
     refcount = 0;
     dims = 0;
     w = h = d = c = 0;
@@ -725,12 +727,28 @@ void CudaMat::create_dims(int _dims, int _w, int _h, int _d, int _c, int _elemty
     nstep = (size_t)pixels() * cpitch;
     size_t bytes = nstep * n * elemsize();
     if (bytes == 0 || !allocator) return;
+    // a placement allocator may answer with a view into a buffer it manages (it fills data / base / refcount / cpitch / nstep and
+    // the owning allocator); otherwise the blob is a fresh allocation owned by the real allocator behind it
+    if (allocator->place(*this)) return;
+    allocator = allocator->real();
     data = allocator->fastMalloc(bytes);
+    base = data;
     if (data)
     {
         refcount = new int;
         *refcount = 1;
     }
+}
+
+CudaMat CudaMat::channel_range(int c0, int count) const
+{
+    CudaMat v;
+    if (!data || dims < 3 || c0 < 0 || count <= 0 || c0 + count > c) return v;
+    if (((size_t)c0 * elemsize()) % 16 != 0) return v;
+    v = *this; // shares the refcount and the base allocation
+    v.data = (unsigned char*)data + (size_t)c0 * elemsize();
+    v.c = count;
+    return v;
 }
 
 void CudaMat::create(int _w, int _elemtype, int _n, CudaAllocator* _allocator)

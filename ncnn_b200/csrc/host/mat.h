@@ -169,8 +169,13 @@ public:
     }
     // same storage, other logical shape (only valid when the device layouts coincide; see Reshape layer)
     ncnn_cuda_tensor view() const;
+    // channels [c0, c0 + count) of a 3-D / 4-D blob as a VIEW: same pixels, same cpitch / nstep, data moved by c0 elements; shares
+    // the refcount, so the parent allocation lives as long as any view does (Slice without a copy; Concat in place).
+    // c0 must keep the view 16-byte aligned.  Empty when the request is out of range.
+    CudaMat channel_range(int c0, int count) const;
 
     void* data;
+    void* base;    // the allocation this handle keeps alive (what goes back to the allocator): == data except for views
     int* refcount; // host-side counter
     CudaAllocator* allocator;
     int elemtype;

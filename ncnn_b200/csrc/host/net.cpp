@@ -23,7 +23,7 @@ class NetPrivate
 {
 public:
     NetPrivate()
-        : device_index(-1), fused_layers(0)
+        : device_index(-1), fused_layers(0), planned_concats(0)
     {
     }
     std::vector<Blob> blobs;
@@ -37,11 +37,31 @@ public:
     int device_index;
     int fused_layers;
 
+    // ---- Concat in place (load-time plan): a channel-axis Concat of 3-D blobs whose inputs' channel counts are
+    // known from the graph gets ONE buffer per forward walk; the layer that produces an input (through Split shares and Slice
+    // views) allocates its top blob as a channel-range VIEW of that buffer, so the Concat itself has nothing left to copy.
+    struct ConcatPlan
+    {
+        ConcatPlan()
+            : planned(false), total_c(0)
+        {
+        }
+        bool planned;
+        int total_c;
+        std::vector<int> offset; // channel offset of every bottom in the buffer
+    };
+    std::vector<ConcatPlan> concat_plan; // per layer
+    std::vector<int> placed_concat;      // per blob: Concat layer whose buffer the blob's producer writes into (-1: none)
+    std::vector<int> placed_offset;      // per blob: channel offset there
+    std::vector<int> static_channels;    // per blob: channel count when it is a 3-D blob whose channels the graph fixes, else -1
+    int planned_concats;
+
+    void plan_concat_placement();
     void update_input_output_indexes();
     void update_input_output_names();
     int fuse_graph(const Option& opt);
     int forward_layer(int layer_index, std::vector<Mat>& blob_mats, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const;
-    int do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const;
+    int do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt_in) const;
 };
 
 Net::Net()
@@ -640,7 +660,11 @@ int Net::load_model(const DataReader& dr)
     }
     if (ret != 0) return ret;
 
-    if (opt.use_cuda_graph_fusion) d->fuse_graph(opt);
+    if (opt.use_cuda_graph_fusion)
+    {
+        d->fuse_graph(opt);
+        d->plan_concat_placement();
+    }
 
     for (size_t i = 0; i < d->layers.size(); i++)
     {
@@ -994,6 +1018,278 @@ int NetPrivate::fuse_graph(const Option&)
     return 0;
 }
 
+// ------------------------------------------------------------------ Concat in place: load-time plan
+static bool is_channel_axis_3d(int axis)
+{
+    return axis == 0 || axis == -3;
+}
+
+// per-top channel counts of a channel-axis Slice of a 3-D blob with `extent` channels (slice.cpp:40-72); false when not computable
+static bool slice_channel_counts(const Slice* sl, int extent, size_t ntops, std::vector<int>& out)
+{
+    out.assign(ntops, 0);
+    const int* slices_ptr = (const int*)sl->slices.data;
+    const int* indices_ptr = (const int*)sl->indices.data;
+    int q = 0;
+    for (size_t i = 0; i < ntops; i++)
+    {
+        int slice;
+        if (indices_ptr)
+        {
+            if (i == ntops - 1)
+                slice = extent - q;
+            else
+            {
+                if ((int)i >= sl->indices.w) return false;
+                int indice = indices_ptr[i];
+                int positive_indice = indice < 0 ? extent + indice : indice;
+                slice = positive_indice - q;
+            }
+        }
+        else
+        {
+            if (!slices_ptr || (int)i >= sl->slices.w) return false;
+            slice = slices_ptr[i];
+            if (slice == -233) slice = (int)((extent - q) / (ntops - i));
+        }
+        if (slice <= 0 || q + slice > extent) return false;
+        out[i] = slice;
+        q += slice;
+    }
+    return true;
+}
+
+void NetPrivate::plan_concat_placement()
+{
+    const size_t L = layers.size();
+    concat_plan.assign(L, ConcatPlan());
+    placed_concat.assign(blobs.size(), -1);
+    placed_offset.assign(blobs.size(), 0);
+    static_channels.assign(blobs.size(), -1);
+    planned_concats = 0;
+    std::vector<int>& chan = static_channels;
+
+    // 1. channel counts the graph fixes (3-D blobs only: everything here starts from a 3-D Input hint or a convolution)
+    static const char* same_as_bottom[] = {"ReLU", "Sigmoid", "Swish", "TanH", "Mish", "Clip", "HardSwish", "HardSigmoid", "GELU", "Dropout", "BatchNorm", "Scale",
+                                           "LRN", "Noop", "Pooling", "Interp", "Eltwise", "ShuffleChannel", 0};
+    for (size_t li = 0; li < L; li++)
+    {
+        const Layer* layer = layers[li];
+        if (!layer || layer->tops.empty() || layer_custom_index[li] >= 0) continue;
+        const std::string& t = layer->type;
+        const int b0 = layer->bottoms.empty() ? -1 : chan[layer->bottoms[0]];
+        if (t == "Input")
+        {
+            const Input* in = (const Input*)layer;
+            if (in->w > 0 && in->h > 0 && in->c > 0 && in->d == 0) chan[layer->tops[0]] = in->c;
+            continue;
+        }
+        if (t == "Convolution" || t == "ConvolutionDepthWise" || t == "Deconvolution" || t == "DeconvolutionDepthWise")
+        {
+            if (b0 < 0) continue;
+            int num_output = -1;
+            if (t == "Convolution") num_output = ((const Convolution*)layer)->num_output;
+            if (t == "ConvolutionDepthWise") num_output = ((const ConvolutionDepthWise*)layer)->num_output;
+            if (t == "Deconvolution" || t == "DeconvolutionDepthWise") num_output = ((const Deconvolution*)layer)->num_output;
+            chan[layer->tops[0]] = num_output;
+            continue;
+        }
+        bool same = false;
+        for (int k = 0; same_as_bottom[k]; k++) same = same || t == same_as_bottom[k];
+        if (same)
+        {
+            if (t == "Eltwise")
+                for (size_t j = 1; j < layer->bottoms.size(); j++)
+                    if (chan[layer->bottoms[j]] != b0) same = false;
+            if (t == "Pooling" && ((const Pooling*)layer)->global_pooling) same = false; // (stays 3-D with the same channels, but never feeds a concat buffer of its size)
+            if (same && layer->tops.size() == 1) chan[layer->tops[0]] = b0;
+            continue;
+        }
+        if (t == "BinaryOp")
+        {
+            const BinaryOp* bo = (const BinaryOp*)layer;
+            if (bo->with_scalar || layer->bottoms.size() == 1)
+                chan[layer->tops[0]] = b0;
+            else if (layer->bottoms.size() == 2 && b0 >= 0 && chan[layer->bottoms[1]] == b0)
+                chan[layer->tops[0]] = b0;
+            continue;
+        }
+        if (t == "Split")
+        {
+            for (size_t j = 0; j < layer->tops.size(); j++) chan[layer->tops[j]] = b0;
+            continue;
+        }
+        if (t == "Slice")
+        {
+            const Slice* sl = (const Slice*)layer;
+            std::vector<int> counts;
+            if (b0 >= 0 && is_channel_axis_3d(sl->axis) && slice_channel_counts(sl, b0, layer->tops.size(), counts))
+                for (size_t j = 0; j < layer->tops.size(); j++) chan[layer->tops[j]] = counts[j];
+            continue;
+        }
+        if (t == "Concat")
+        {
+            const Concat* cc = (const Concat*)layer;
+            int sum = 0;
+            bool ok = is_channel_axis_3d(cc->axis);
+            for (size_t j = 0; j < layer->bottoms.size() && ok; j++)
+            {
+                if (chan[layer->bottoms[j]] < 0) ok = false;
+                sum += chan[layer->bottoms[j]];
+            }
+            if (ok) chan[layer->tops[0]] = sum;
+            continue;
+        }
+    }
+
+    // 2. a blob seen through Split shares and channel-axis Slice views: (root blob, first channel inside it)
+    auto resolve = [&](int b, int& root, int& start) {
+        root = b;
+        start = 0;
+        for (;;)
+        {
+            const int p = blobs[root].producer;
+            if (p < 0 || layer_custom_index[p] >= 0) return;
+            const Layer* pl = layers[p];
+            if (pl->type == "Split")
+            {
+                root = pl->bottoms[0];
+                continue;
+            }
+            if (pl->type == "Slice" && is_channel_axis_3d(((const Slice*)pl)->axis) && chan[pl->bottoms[0]] >= 0)
+            {
+                int off = 0;
+                bool found = false;
+                for (size_t j = 0; j < pl->tops.size(); j++)
+                {
+                    if (pl->tops[j] == root)
+                    {
+                        found = true;
+                        break;
+                    }
+                    if (chan[pl->tops[j]] < 0) return;
+                    off += chan[pl->tops[j]];
+                }
+                if (!found) return;
+                start += off;
+                root = pl->bottoms[0];
+                continue;
+            }
+            return;
+        }
+    };
+    static const char* placeable[] = {"Convolution", "ConvolutionDepthWise", "Deconvolution", "DeconvolutionDepthWise", "Pooling", "Interp", "Eltwise", "BinaryOp",
+                                      "ReLU", "Sigmoid", "Swish", "TanH", "Mish", "Clip", "HardSwish", "HardSigmoid", "GELU", 0};
+    const int kVec = 8; // channel offsets / counts in whole 16-byte vectors for 16-bit blobs (and 32 bytes for fp32 ones)
+    for (size_t k = 0; k < L; k++)
+    {
+        const Layer* layer = layers[k];
+        if (!layer || layer->tops.size() != 1 || layer_custom_index[k] >= 0 || layer->type != "Concat") continue;
+        if (!is_channel_axis_3d(((const Concat*)layer)->axis) || layer->bottoms.size() < 2) continue;
+        ConcatPlan plan;
+        bool ok = true;
+        int off = 0;
+        for (size_t j = 0; j < layer->bottoms.size() && ok; j++)
+        {
+            const int c = chan[layer->bottoms[j]];
+            if (c <= 0 || c % kVec != 0) ok = false;
+            plan.offset.push_back(off);
+            off += c;
+        }
+        if (!ok) continue;
+        plan.total_c = off;
+        // groups of consecutive bottoms that are adjacent channel ranges of one root covering it completely
+        int marked = 0;
+        for (size_t i = 0; i < layer->bottoms.size();)
+        {
+            int root, start;
+            resolve(layer->bottoms[i], root, start);
+            int covered = chan[layer->bottoms[i]];
+            size_t j = i + 1;
+            if (start == 0)
+            {
+                for (; j < layer->bottoms.size(); j++)
+                {
+                    int r2, s2;
+                    resolve(layer->bottoms[j], r2, s2);
+                    if (r2 != root || s2 != covered) break;
+                    covered += chan[layer->bottoms[j]];
+                }
+            }
+            const int prod = blobs[root].producer;
+            bool can = start == 0 && covered == chan[root] && prod >= 0 && layer_custom_index[prod] < 0 && placed_concat[root] < 0;
+            if (can)
+            {
+                bool allowed = false;
+                for (int q = 0; placeable[q]; q++) allowed = allowed || layers[prod]->type == placeable[q];
+                if (layers[prod]->type == "BinaryOp" && ((const BinaryOp*)layers[prod])->with_scalar) allowed = false;
+                if (layers[prod]->tops.size() != 1) allowed = false;
+                can = allowed;
+            }
+            if (can)
+            {
+                placed_concat[root] = (int)k;
+                placed_offset[root] = plan.offset[i];
+                marked++;
+            }
+            i = can ? j : i + 1;
+        }
+        if (marked > 0)
+        {
+            plan.planned = true;
+            concat_plan[k] = plan;
+            planned_concats++;
+        }
+    }
+}
+
+// Hands the blob a producer creates for its top a channel-range view of its Concat's buffer (allocating that buffer at the first
+// request of a walk: its pixel grid and batch are only known then).  Lives on the executor's stack for one layer call.
+class CudaPlacementAllocator : public CudaAllocator
+{
+public:
+    CudaPlacementAllocator(CudaAllocator* real_allocator, CudaMat* _slot, int _offset, int _total_c, int _expect_c)
+        : CudaAllocator(real_allocator->device_index), real_(real_allocator), slot(_slot), offset(_offset), total_c(_total_c), expect_c(_expect_c), used(false)
+    {
+    }
+    virtual void* fastMalloc(size_t size)
+    {
+        return real_->fastMalloc(size);
+    }
+    virtual void fastFree(void* ptr)
+    {
+        real_->fastFree(ptr);
+    }
+    virtual CudaAllocator* real()
+    {
+        return real_;
+    }
+    virtual bool place(CudaMat& m)
+    {
+        if (used || m.dims != 3 || m.c != expect_c) return false;
+        const int vec = m.elemtype == NCNN_CUDA_F32 ? 4 : 8;
+        if (expect_c % vec != 0 || offset % vec != 0 || total_c % vec != 0) return false;
+        if (slot->empty())
+        {
+            slot->create(m.w, m.h, total_c, m.elemtype, m.n, real_);
+            if (slot->empty()) return false;
+        }
+        else if (slot->w != m.w || slot->h != m.h || slot->n != m.n || slot->elemtype != m.elemtype || slot->c != total_c)
+            return false; // (an earlier input of this walk had another pixel grid: this one is copied by the Concat instead)
+        CudaMat v = slot->channel_range(offset, expect_c);
+        if (v.empty()) return false;
+        m = v;
+        used = true;
+        return true;
+    }
+
+private:
+    CudaAllocator* real_;
+    CudaMat* slot;
+    int offset, total_c, expect_c;
+    bool used;
+};
+
 // ------------------------------------------------------------------ executor
 // src/net.cpp:192-356 (Vulkan forward_layer): depth-first, lazy
 int NetPrivate::forward_layer(int layer_index, std::vector<Mat>& blob_mats, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const
@@ -1028,8 +1324,74 @@ int NetPrivate::forward_layer(int layer_index, std::vector<Mat>& blob_mats, std:
 }
 
 // src/net.cpp:886-1140 (Vulkan do_forward_layer): lightmode recycling, in-place clone rule; no per-sample batch loop
-int NetPrivate::do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const
+int NetPrivate::do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt_in) const
 {
+    // ---- Concat in place (plan_concat_placement): the walk keeps one buffer per planned Concat in the slots behind the blobs
+    // (blob_mats_gpu[blobs.size() + layer index]); a layer whose top is a planned input creates that top through a placement
+    // allocator, and the Concat itself only copies the inputs that did not end up in place
+    const bool have_slots = planned_concats > 0 && blob_mats_gpu.size() >= blobs.size() + layers.size();
+    Option opt = opt_in;
+    CudaPlacementAllocator* placer = 0;
+    char placer_storage[sizeof(CudaPlacementAllocator)];
+    if (have_slots && layer->tops.size() == 1 && placed_concat[layer->tops[0]] >= 0)
+    {
+        const int t = layer->tops[0];
+        const int k = placed_concat[t];
+        placer = new (placer_storage) CudaPlacementAllocator(cmd.blob_allocator(opt_in), &blob_mats_gpu[blobs.size() + k], placed_offset[t], concat_plan[k].total_c,
+                                                             static_channels[t]);
+        opt.blob_cuda_allocator = placer;
+    }
+    struct PlacerGuard
+    {
+        CudaPlacementAllocator* p;
+        ~PlacerGuard()
+        {
+            if (p) p->~CudaPlacementAllocator();
+        }
+    } placer_guard = {placer};
+
+    if (have_slots && layer->type == "Concat" && layer->tops.size() == 1)
+    {
+        int k = -1;
+        for (size_t i = 0; i < layers.size(); i++)
+            if (layers[i] == layer)
+            {
+                k = (int)i;
+                break;
+            }
+        CudaMat& slot = k >= 0 ? blob_mats_gpu[blobs.size() + k] : blob_mats_gpu[0];
+        if (k >= 0 && concat_plan[k].planned && !slot.empty())
+        {
+            const ConcatPlan& plan = concat_plan[k];
+            bool usable = true;
+            int batch = slot.n;
+            for (size_t i = 0; i < layer->bottoms.size() && usable; i++)
+            {
+                const CudaMat& b = blob_mats_gpu[layer->bottoms[i]];
+                usable = b.dims == 3 && b.w == slot.w && b.h == slot.h && b.elemtype == slot.elemtype && b.c == static_channels[layer->bottoms[i]] && (b.n == batch || b.n <= 1);
+            }
+            if (usable)
+            {
+                ncnn_cuda_tensor t = slot.view();
+                for (size_t i = 0; i < layer->bottoms.size(); i++)
+                {
+                    const CudaMat& b = blob_mats_gpu[layer->bottoms[i]];
+                    const void* expect = (const unsigned char*)slot.data + (size_t)plan.offset[i] * slot.elemsize();
+                    if (b.data == expect && b.base == slot.base && b.cpitch == slot.cpitch && b.nstep == slot.nstep) continue; // already in place
+                    ncnn_cuda_tensor bv = b.view();
+                    int ret = ncnn_cuda_copy_into_axis(&bv, &t, 0, plan.offset[i], cmd.stream());
+                    if (ret != 0) return ret;
+                }
+                blob_mats_gpu[layer->tops[0]] = slot;
+                slot.release();
+                if (opt.lightmode)
+                    for (size_t i = 0; i < layer->bottoms.size(); i++) blob_mats_gpu[layer->bottoms[i]].release();
+                return 0;
+            }
+            slot.release(); // inputs of another shape than planned: the ordinary copying Concat below
+        }
+    }
+
     if (layer->one_blob_only)
     {
         int bottom_blob_index = layer->bottoms[0];
@@ -1143,7 +1505,8 @@ Extractor::Extractor(const Net* _net, size_t blob_count)
     : d(new ExtractorPrivate(_net))
 {
     d->blob_mats.resize(blob_count);
-    d->blob_mats_gpu.resize(blob_count);
+    // device side: the blobs, then one slot per layer for the buffers of planned in-place Concats (NetPrivate::do_forward_layer)
+    d->blob_mats_gpu.resize(blob_count + _net->layers().size());
     d->opt = _net->opt;
 }
 
@@ -1237,7 +1600,7 @@ int Extractor::input(const char* blob_name, const CudaMat& in)
 
 int Extractor::input(int blob_index, const CudaMat& in)
 {
-    if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
+    if (blob_index < 0 || blob_index >= (int)d->blob_mats.size()) return -1;
     if (reject_folded_blob(d->net, blob_index, "input")) return -1;
     d->blob_mats_gpu[blob_index] = in;
     d->blob_mats[blob_index].release();
@@ -1351,7 +1714,7 @@ int Extractor::extract(const char* blob_name, CudaMat& feat, CudaCompute& cmd)
 // src/net.cpp:3083-3116
 int Extractor::extract(int blob_index, CudaMat& feat, CudaCompute& cmd)
 {
-    if (blob_index < 0 || blob_index >= (int)d->blob_mats_gpu.size()) return -1;
+    if (blob_index < 0 || blob_index >= (int)d->blob_mats.size()) return -1;
     if (reject_folded_blob(d->net, blob_index, "extract")) return -1;
     int ret = 0;
     // pixel inputs first: upload the raw bytes, convert + normalise on the device
