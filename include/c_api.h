@@ -279,6 +279,9 @@ NCNN_C_API int ncnn_option_get_use_cuda_compute(const ncnn_option_t opt);
 NCNN_C_API void ncnn_option_set_use_cuda_compute(ncnn_option_t opt, int enable);
 NCNN_C_API void ncnn_option_set_lightmode(ncnn_option_t opt, int enable);
 NCNN_C_API void ncnn_option_set_use_cuda_graph_fusion(ncnn_option_t opt, int enable);
+/* Option::use_mapped_model_loading (src/option.h:125; C++-only in the reference): ncnn_net_load_model(path) mmap's the .bin and
+ * parses it in place (src/net.cpp:2263-2301) */
+NCNN_C_API void ncnn_option_set_use_mapped_model_loading(ncnn_option_t opt, int enable);
 NCNN_C_API int ncnn_get_cuda_device_count(void);
 NCNN_C_API void ncnn_net_set_cuda_device(ncnn_net_t net, int device_index);
 NCNN_C_API int ncnn_net_get_fused_layer_count(const ncnn_net_t net);

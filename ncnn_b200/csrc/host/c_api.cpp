@@ -18,6 +18,49 @@
 
 using namespace ncnn;
 
+// src/c_api.cpp:55-138: the Allocator object behind an ncnn_allocator_t calls back THROUGH the C function table, and the table's
+// default entries call the base class non-virtually -- so a C caller may replace fast_malloc / fast_free on the struct it was
+// handed and every Mat the runtime allocates from it goes through the replacement (that is the allocator plugin contract).
+namespace {
+template<class Base>
+class TableAllocator : public Base
+{
+public:
+    explicit TableAllocator(ncnn_allocator_t t)
+        : table(t)
+    {
+    }
+    virtual void* fastMalloc(size_t size)
+    {
+        return table->fast_malloc(table, size);
+    }
+    virtual void fastFree(void* ptr)
+    {
+        table->fast_free(table, ptr);
+    }
+    ncnn_allocator_t table;
+};
+template<class Base>
+void* table_default_malloc(ncnn_allocator_t a, size_t size)
+{
+    return ((TableAllocator<Base>*)(Allocator*)a->pthis)->Base::fastMalloc(size);
+}
+template<class Base>
+void table_default_free(ncnn_allocator_t a, void* ptr)
+{
+    ((TableAllocator<Base>*)(Allocator*)a->pthis)->Base::fastFree(ptr);
+}
+template<class Base>
+ncnn_allocator_t make_table_allocator()
+{
+    ncnn_allocator_t a = (ncnn_allocator_t)malloc(sizeof(struct __ncnn_allocator_t));
+    a->pthis = (void*)(Allocator*)(new TableAllocator<Base>(a));
+    a->fast_malloc = table_default_malloc<Base>;
+    a->fast_free = table_default_free<Base>;
+    return a;
+}
+} // namespace
+
 extern "C" {
 
 const char* ncnn_version(void)
@@ -31,42 +74,17 @@ int ncnn_version_number(void)
 }
 
 // ------------------------------------------------------------------ allocator
-namespace {
-struct AllocatorHolder
-{
-    Allocator* impl;
-};
-} // namespace
-
-static void* c_fast_malloc(ncnn_allocator_t a, size_t size)
-{
-    return ((Allocator*)a->pthis)->fastMalloc(size);
-}
-static void c_fast_free(ncnn_allocator_t a, void* ptr)
-{
-    ((Allocator*)a->pthis)->fastFree(ptr);
-}
-
-static ncnn_allocator_t wrap_allocator(Allocator* impl)
-{
-    ncnn_allocator_t a = (ncnn_allocator_t)malloc(sizeof(struct __ncnn_allocator_t));
-    a->pthis = impl;
-    a->fast_malloc = c_fast_malloc;
-    a->fast_free = c_fast_free;
-    return a;
-}
-
 ncnn_allocator_t ncnn_allocator_create_pool_allocator(void)
 {
-    return wrap_allocator(new PoolAllocator);
+    return make_table_allocator<PoolAllocator>();
 }
 ncnn_allocator_t ncnn_allocator_create_unlocked_pool_allocator(void)
 {
-    return wrap_allocator(new PoolAllocator);
+    return make_table_allocator<PoolAllocator>();
 }
 ncnn_allocator_t ncnn_allocator_create_cuda_staging_allocator(void)
 {
-    return wrap_allocator(new CudaStagingAllocator);
+    return make_table_allocator<CudaStagingAllocator>();
 }
 void ncnn_allocator_destroy(ncnn_allocator_t a)
 {
@@ -138,6 +156,10 @@ void ncnn_option_set_lightmode(ncnn_option_t opt, int enable)
 void ncnn_option_set_use_cuda_graph_fusion(ncnn_option_t opt, int enable)
 {
     ((Option*)opt)->use_cuda_graph_fusion = enable != 0;
+}
+void ncnn_option_set_use_mapped_model_loading(ncnn_option_t opt, int enable)
+{
+    ((Option*)opt)->use_mapped_model_loading = enable != 0;
 }
 
 // ------------------------------------------------------------------ mat

@@ -115,6 +115,11 @@ Mat ModelBinFromDataReader::load(int w, int type) const
         }
         if (flag.tag == 0x0002C056 || sum == 0)
         {
+            // a reader over memory that outlives the weights (a mapped model file, src/net.cpp:2263-2301) lends the bytes
+            // instead of copying them (src/modelbin.cpp:180-196): the Mat is an external-data view, refcount NULL
+            const void* refbuf = 0;
+            if (dr_.reference(w * sizeof(float), &refbuf) == w * sizeof(float) && refbuf && ((size_t)refbuf & 3) == 0)
+                return Mat(w, (void*)refbuf, (size_t)4u);
             m.create(w);
             if (m.empty()) return m;
             nread = dr_.read(m.data, w * sizeof(float));

@@ -2,14 +2,35 @@
 #include "net.h"
 
 #include <ctype.h>
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "layer/cuda_layers.h"
 #include "modelbin.h"
 #include "paramdict.h"
 
 namespace ncnn {
+
+// a read-only mapping of a model file (the reference's MappedFile, src/net.cpp:55-121)
+struct MappedModelFile
+{
+    MappedModelFile()
+        : ptr(0), size(0)
+    {
+    }
+    ~MappedModelFile()
+    {
+        close();
+    }
+    int open(const char* path);
+    void close();
+    void* ptr;
+    size_t size;
+};
 
 struct custom_layer_registry_entry
 {
@@ -36,6 +57,7 @@ public:
     std::vector<custom_layer_registry_entry> custom_layer_registry;
     int device_index;
     int fused_layers;
+    MappedModelFile mapped_model;
 
     // ---- Concat in place (load-time plan): a channel-axis Concat of 3-D blobs whose inputs' channel counts are
     // known from the graph gets ONE buffer per forward walk; the layer that produces an input (through Split shares and Slice
@@ -63,6 +85,32 @@ public:
     int forward_layer(int layer_index, std::vector<Mat>& blob_mats, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt) const;
     int do_forward_layer(const Layer* layer, std::vector<CudaMat>& blob_mats_gpu, CudaCompute& cmd, const Option& opt_in) const;
 };
+
+int MappedModelFile::open(const char* path)
+{
+    close();
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return -1;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0)
+    {
+        ::close(fd);
+        return -1;
+    }
+    void* p = mmap(0, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd); // the mapping keeps the file
+    if (p == MAP_FAILED) return -1;
+    ptr = p;
+    size = (size_t)st.st_size;
+    return 0;
+}
+
+void MappedModelFile::close()
+{
+    if (ptr) munmap(ptr, size);
+    ptr = 0;
+    size = 0;
+}
 
 Net::Net()
     : d(new NetPrivate)
@@ -687,8 +735,36 @@ int Net::load_model(FILE* fp)
     return load_model(dr);
 }
 
+// opt.use_mapped_model_loading (src/net.cpp:2263-2301): the .bin is mmap'ed read-only and parsed in place -- raw fp32 weight
+// records become views of the mapping (ModelBinFromDataReader::load via DataReader::reference), nothing is copied through the
+// page cache into a second host buffer before create_pipeline re-packs the weights for the device.  The mapping lives until
+// Net::clear().  Falls back to stdio when the file cannot be mapped.
 int Net::load_model(const char* modelpath)
 {
+    if (opt.use_mapped_model_loading)
+    {
+        if (d->mapped_model.open(modelpath) == 0)
+        {
+            const unsigned char* mem = (const unsigned char*)d->mapped_model.ptr;
+            size_t consumed = 0;
+            int ret;
+            {
+                const unsigned char* cur = mem;
+                DataReaderFromMemory dr(cur);
+                ret = load_model(dr);
+                consumed = cur - mem;
+            }
+            if (ret != 0) return ret;
+            if (consumed != d->mapped_model.size)
+            {
+                NCNN_LOGE("mapped_file consumed %zu != %zu", consumed, d->mapped_model.size);
+                d->mapped_model.close();
+                return -1;
+            }
+            return 0;
+        }
+        // fallback to regular file loading
+    }
     FILE* fp = fopen(modelpath, "rb");
     if (!fp)
     {
@@ -733,6 +809,7 @@ void Net::clear()
     d->layers.clear();
     d->layer_custom_index.clear();
     d->blobs.clear();
+    d->mapped_model.close(); // (after the layers: their weight Mats may be views of the mapping)
     d->input_blob_indexes.clear();
     d->output_blob_indexes.clear();
     d->input_blob_names.clear();

@@ -85,7 +85,12 @@ def gen_headers(gen, isa):
     src = re.sub(r"#cmakedefine01 (\w+)", sub01, src)
     src = src.replace('#cmakedefine NCNN_VERSION_STRING "@NCNN_VERSION_STRING@"', '#define NCNN_VERSION_STRING "1.0.oracle"')
     src = src.replace("#cmakedefine NCNN_VERSION_NUMBER @NCNN_VERSION_NUMBER@", "#define NCNN_VERSION_NUMBER 20260101")
-    open(os.path.join(gen, "platform.h"), "w").write(src)
+    # NCNN_SIMPLEOCV stays off for the library proper; the two translation units that need the reference's OpenCV stand-in
+    # (simpleocv.cpp and the YOLOv8 example driver) are compiled with -DNCNN_SIMPLEOCV=1
+    src = src.replace("#define NCNN_SIMPLEOCV 0", "#ifndef NCNN_SIMPLEOCV\n#define NCNN_SIMPLEOCV 0\n#endif")
+    old = open(os.path.join(gen, "platform.h")).read() if os.path.exists(os.path.join(gen, "platform.h")) else None
+    if old != src:
+        open(os.path.join(gen, "platform.h"), "w").write(src)
     open(os.path.join(gen, "ncnn_export.h"), "w").write(
         "#ifndef NCNN_EXPORT_H\n#define NCNN_EXPORT_H\n#define NCNN_EXPORT __attribute__((visibility(\"default\")))\n"
         "#define NCNN_NO_EXPORT\n#define NCNN_DEPRECATED\n#endif\n")
@@ -139,8 +144,19 @@ def build(isa, jobs):
     rules, objs = [], []
     for s in sources():
         o = os.path.join(obj, os.path.relpath(s, os.path.join(REF, "src")).replace("/", "__")[:-4] + ".o")
+        extra = ""
+        if os.path.basename(s) == "simpleocv.cpp":
+            o = o[:-2] + "_on.o"  # (a new object name: the cached one was compiled with NCNN_SIMPLEOCV 0, i.e. empty)
+            extra = " -DNCNN_SIMPLEOCV=1"
         objs.append(o)
-        rules.append("%s: %s\n\t@echo CXX %s\n\t@%s %s -c $< -o $@\n" % (o, s, os.path.basename(s), CXX, cflags))
+        rules.append("%s: %s\n\t@echo CXX %s\n\t@%s %s%s -c $< -o $@\n" % (o, s, os.path.basename(s), CXX, cflags, extra))
+    # the reference's YOLOv8 post-processing (file-static functions of examples/yolov8.cpp), made callable by a driver TU of
+    # OURS that includes the example where it lies (oracle/yolov8_example_driver.cpp)
+    ydrv = os.path.join(HERE, "yolov8_example_driver.cpp")
+    ydrv_o = os.path.join(obj, "yolov8_example_driver.o")
+    objs.append(ydrv_o)
+    rules.append("%s: %s %s\n\t@echo CXX yolov8_example_driver.cpp\n\t@%s %s -DUSE_NCNN_SIMPLEOCV -DNCNN_SIMPLEOCV=1 -DNCNN_REFERENCE_YOLOV8_CPP='\"%s\"' -c $< -o $@\n"
+                 % (ydrv_o, ydrv, os.path.join(REF, "examples/yolov8.cpp"), CXX, cflags, os.path.join(REF, "examples/yolov8.cpp")))
     # the driver is OUR code (oracle/ref_driver.cpp): extra C entry points next to the reference's own c_api
     drv = os.path.join(HERE, "ref_driver.cpp")
     drv_o = os.path.join(obj, "ref_driver.o")

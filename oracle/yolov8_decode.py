@@ -2,10 +2,12 @@
 
 TEST INFRASTRUCTURE ONLY (imported by tests/ as the checker of ncnn_cuda_yolov8_decode; never by the product).
 
-This step lives in the reference's example program, not in its library: it is not part of oracle/_ref (the example needs
-OpenCV) and the reference holds no test, fixture or golden vector for it -- PARITY UNPINNED beyond the line-by-line
-restatement below.  The Softmax it runs over the 4 x 16 box logits is the library layer (src/layer/softmax.cpp: subtract
-the row maximum, exp, divide by the sum), restated here in fp32.
+This step lives in the reference's example program, not in its library, and the reference holds no test, fixture or golden
+vector for it.  PINNED since round 2 against the reference's own code: oracle/build_ref.py compiles examples/yolov8.cpp where it
+lies into oracle/_ref (oracle/yolov8_example_driver.cpp includes it as a translation unit, OpenCV replaced by the reference's
+simpleocv.h through the example's USE_NCNN_SIMPLEOCV switch) and tests/test_oracle_golden.py::test_yolov8_decode_restatement_
+matches_reference_example checks every function below against it on seeded inputs.  The Softmax the example runs over the 4 x 16
+box logits is the library layer (src/layer/softmax.cpp: subtract the row maximum, exp, divide by the sum), restated here in fp32.
 
     generate_proposals  examples/yolov8.cpp:160-254 (one stride) and :256-273 (all strides, rows stride by stride)
     sigmoid             examples/yolov8.cpp:155-158

@@ -681,3 +681,143 @@ def test_folded_blob_is_rejected_not_silently_ignored(ref):
         finally:
             net.close()
             L.lib.ncnn_option_destroy(opt)
+
+
+def test_mapped_model_loading(ref, tmp_path):
+    """Option::use_mapped_model_loading (src/net.cpp:2263-2301): ncnn_net_load_model(path) on an mmap'ed .bin (weights parsed in
+    place, raw fp32 records lent as views of the mapping) must load the same net as the stdio path and as the reference"""
+    import ctypes as C
+    L = product()
+    name = "squeezenet_v1_1"
+    text = netutil.with_input_size(modelzoo.param_text(name), 227)
+    weights = modelzoo.random_model_bytes(text, seed=5)
+    pp, bp = tmp_path / "m.param", tmp_path / "m.bin"
+    pp.write_text(text)
+    bp.write_bytes(weights)
+    x = netutil.random_input(name, 2, 227, seed=6)
+    want = run_ref(ref, text, weights, {"data": x}, batched=True)["output"]
+    L.lib.ncnn_option_set_use_mapped_model_loading.argtypes = [C.c_void_p, C.c_int]
+    L.lib.ncnn_net_load_param.argtypes = [C.c_void_p, C.c_char_p]
+    L.lib.ncnn_net_load_model.argtypes = [C.c_void_p, C.c_char_p]
+    outs = []
+    for mapped in (1, 0):
+        opt = L.make_option(1, **MODES["fp32"])
+        L.lib.ncnn_option_set_use_mapped_model_loading(opt, mapped)
+        net = L.lib.ncnn_net_create()
+        L.lib.ncnn_net_set_option(net, opt)
+        assert L.lib.ncnn_net_load_param(net, str(pp).encode()) == 0
+        assert L.lib.ncnn_net_load_model(net, str(bp).encode()) == 0
+        m = L.mat_from_numpy(x, batched=True)
+        ex = L.lib.ncnn_extractor_create(net)
+        out = C.c_void_p()
+        assert L.lib.ncnn_extractor_input(ex, b"data", m) == 0
+        assert L.lib.ncnn_extractor_extract(ex, b"output", C.byref(out)) == 0
+        outs.append(L.mat_to_numpy(out, force_batch=True))
+        L.lib.ncnn_mat_destroy(out)
+        L.lib.ncnn_extractor_destroy(ex)
+        L.lib.ncnn_mat_destroy(m)
+        L.lib.ncnn_net_destroy(net)
+        L.lib.ncnn_option_destroy(opt)
+    assert np.array_equal(outs[0], outs[1])
+    assert nerr(outs[0], want) <= 1e-5
+    # a truncated file must be refused on the mapped path too ("mapped_file consumed ..."): the parser may not run past the mapping
+    bp.write_bytes(weights + b"\0\0\0\0")
+    opt = L.make_option(1, **MODES["fp32"])
+    L.lib.ncnn_option_set_use_mapped_model_loading(opt, 1)
+    net = L.lib.ncnn_net_create()
+    L.lib.ncnn_net_set_option(net, opt)
+    assert L.lib.ncnn_net_load_param(net, str(pp).encode()) == 0
+    assert L.lib.ncnn_net_load_model(net, str(bp).encode()) != 0, "trailing bytes: consumed != size must fail like the reference"
+    L.lib.ncnn_net_destroy(net)
+    L.lib.ncnn_option_destroy(opt)
+
+
+def test_out_of_memory_paths_return_minus_100_and_recover(ref):
+    """the reference's error contract (tests/testutil.cpp:2111-2156 TestOOMAllocator, src/net.cpp:641-642): an allocation that
+    fails makes forward / extract return -100 -- no crash, no partial result -- and the Net stays usable afterwards.
+      * device side: an Interp whose output (64x upscale of a 1024 x 1024 x 16 blob = 275 TB) cannot be allocated on any GPU;
+      * host side: a user ncnn_allocator_t (the plugin table of src/c_api.h:33-38) that starts failing, installed as the blob
+        allocator the extracted host Mat comes from."""
+    import ctypes as C
+    from ncnn_b200 import capi
+    L = product()
+    text = ("7767517\n3 3\nInput data 0 1 data\nConvolution conv1 1 1 data c1 0=16 1=1 5=1 6=256\n"
+            "Interp up 1 1 c1 output 0=1 1=64.0 2=64.0\n")
+    weights = modelzoo.random_model_bytes(text, seed=2)
+    opt = L.make_option(1, **MODES["fp32"])
+    net = capi.Net(L, text, weights, opt)
+    try:
+        small = np.random.default_rng(0).uniform(-1, 1, (16, 4, 4)).astype(np.float32)
+        want = run_ref(ref, text, weights, {"data": small}, batched=False)["output"]
+        ok = net.run({"data": small})["output"]
+        assert nerr(ok, want) <= 1e-5
+        big = np.zeros((16, 1024, 1024), np.float32)
+        ex = L.lib.ncnn_extractor_create(net.net)
+        m = L.mat_from_numpy(big)
+        out = C.c_void_p()
+        assert L.lib.ncnn_extractor_input(ex, b"data", m) == 0
+        r = L.lib.ncnn_extractor_extract(ex, b"output", C.byref(out))
+        assert r == -100, "device OOM must surface as -100, got %d" % r
+        if out.value:  # (like the reference's c_api.cpp, *mat is always a fresh -- here empty -- Mat)
+            assert L.lib.ncnn_mat_get_dims(out) == 0
+            L.lib.ncnn_mat_destroy(out)
+        L.lib.ncnn_extractor_destroy(ex)
+        L.lib.ncnn_mat_destroy(m)
+        # the runtime recovers: the same Net serves the next request
+        again = net.run({"data": small})["output"]
+        assert np.array_equal(again, ok)
+
+        # host side: a failing user allocator behind the extracted Mat
+        ALLOC = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+        FREE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+        class _Alloc(C.Structure):
+            _fields_ = [("pthis", C.c_void_p), ("fast_malloc", ALLOC), ("fast_free", FREE)]
+        # the plugin contract of src/c_api.cpp:55-138: take the table of a pool allocator and replace its entries; the Allocator
+        # object behind it calls back through the table
+        L.lib.ncnn_allocator_create_pool_allocator.restype = C.c_void_p
+        L.lib.ncnn_allocator_destroy.argtypes = [C.c_void_p]
+        ua_raw = L.lib.ncnn_allocator_create_pool_allocator()
+        ua = C.cast(ua_raw, C.POINTER(_Alloc))
+        base_m, base_f = ua.contents.fast_malloc, ua.contents.fast_free
+        base_m = C.cast(base_m, ALLOC)
+        base_f = C.cast(base_f, FREE)
+        state = {"fail": False, "calls": 0}
+
+        def fm(a, size):
+            state["calls"] += 1
+            return None if state["fail"] else base_m(a, size)
+
+        def ff(a, p):
+            base_f(a, p)
+        cb_m, cb_f = ALLOC(fm), FREE(ff)
+        ua.contents.fast_malloc = cb_m
+        ua.contents.fast_free = cb_f
+        L.lib.ncnn_option_set_blob_allocator.argtypes = [C.c_void_p, C.c_void_p]
+        opt2 = L.make_option(1, **MODES["fp32"])
+        L.lib.ncnn_option_set_blob_allocator(opt2, ua_raw)
+        net2 = capi.Net(L, text, weights, opt2)
+        try:
+            for fail, expect in ((False, 0), (True, -100), (False, 0)):
+                state["fail"] = fail
+                ex = L.lib.ncnn_extractor_create(net2.net)
+                m = L.mat_from_numpy(small)
+                out = C.c_void_p()
+                assert L.lib.ncnn_extractor_input(ex, b"data", m) == 0
+                r = L.lib.ncnn_extractor_extract(ex, b"output", C.byref(out))
+                assert r == expect, (fail, r)
+                if r == 0:
+                    assert nerr(L.mat_to_numpy(out), want) <= 1e-5
+                if out.value:
+                    L.lib.ncnn_mat_destroy(out)
+                L.lib.ncnn_extractor_destroy(ex)
+                L.lib.ncnn_mat_destroy(m)
+            assert state["calls"] >= 3, "the user allocator must have been asked for the extracted Mats"
+        finally:
+            net2.close()
+            L.lib.ncnn_option_destroy(opt2)
+            ua.contents.fast_malloc, ua.contents.fast_free = base_m, base_f
+            L.lib.ncnn_allocator_destroy(ua_raw)
+    finally:
+        net.close()
+        L.lib.ncnn_option_destroy(opt)

@@ -90,3 +90,50 @@ def test_naive_vs_optimised_layers(ref):
     a = ref.layer_forward("Pooling", pp, [], [x], naive=True)[0]
     c = ref.layer_forward("Pooling", pp, [], [x], naive=False)[0]
     assert a.shape == (16, 10, 10) and np.array_equal(a, c)  # ceil mode: (20-3)/2 -> 9.5 -> 10 windows
+
+
+def test_yolov8_decode_restatement_matches_reference_example(ref):
+    """oracle/yolov8_decode.py (the numpy checker of the device decode) against the reference's OWN post-processing:
+    generate_proposals / qsort_descent_inplace / nms_sorted_bboxes of examples/yolov8.cpp:67-273, compiled where they lie into
+    oracle/_ref by oracle/build_ref.py (oracle/yolov8_example_driver.cpp).  Pins SURVEY 8f row f4's oracle."""
+    import ctypes as C
+    from oracle import yolov8_decode as oy
+    L = ref.lib
+    if not hasattr(L, "ref_yolov8_generate_proposals"):
+        pytest.skip("oracle/_ref was built before the YOLOv8 example driver existed: re-run oracle/build_ref.py")
+    L.ref_yolov8_generate_proposals.restype = C.c_int
+    L.ref_yolov8_generate_proposals.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    L.ref_yolov8_sort_nms.restype = C.c_int
+    L.ref_yolov8_sort_nms.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(77)
+    strides = [8, 16, 32]
+    for (in_w, in_h, num_class, thr) in [(96, 64, 80, 0.25), (64, 64, 5, 0.4), (160, 96, 33, 0.25), (32, 32, 1, 0.5)]:
+        rows = sum((in_w // s) * (in_h // s) for s in strides)
+        pred = rng.uniform(-3.0, 0.0, (rows, 64 + num_class)).astype(np.float32)
+        pred[:, :64] = rng.uniform(-2.0, 4.0, (rows, 64)).astype(np.float32)
+        pred[:, 64:] += rng.uniform(-2.0, 1.5, (rows, 1)).astype(np.float32)
+        pred[3, 64:] = 1.0  # a tie between all classes: the first one wins in both
+        pred = np.ascontiguousarray(pred)
+        st = (C.c_int * 3)(*strides)
+        out = np.zeros((rows, 6), np.float32)
+        n = L.ref_yolov8_generate_proposals(pred.ctypes.data, rows, pred.shape[1], st, 3, in_w, in_h, thr, out.ctypes.data, rows)
+        dense = oy.generate_proposals(pred, strides, in_w, in_h, thr)
+        mine = dense[dense[:, 5] >= 0]  # the example pushes only the accepted anchors, in anchor order
+        score = 1.0 / (1.0 + np.exp(-pred[:, 64:].max(-1).astype(np.float64)))
+        assert np.abs(score - thr).min() > 1e-6, "seed puts a score on the threshold: pick another"
+        assert n == mine.shape[0] and 0 < n < rows
+        got = out[:n]
+        assert np.array_equal(got[:, 5], mine[:, 5])
+        assert np.abs(got[:, 4] - mine[:, 4]).max() <= 2e-7
+        assert np.abs(got[:, :4] - mine[:, :4]).max() <= 2e-5 * max(in_w, in_h)
+        # sort + NMS (class-aware and agnostic): same survivors in the same order
+        for agnostic in (0, 1):
+            boxes = got.copy()
+            picked = np.zeros(n, np.int32)
+            k = L.ref_yolov8_sort_nms(boxes.ctypes.data, n, 0.45, agnostic, picked.ctypes.data, n)
+            order = np.argsort(-got[:, 4], kind="stable")
+            srt = got[order]
+            if np.unique(got[:, 4]).size == n:  # (the example's quicksort is not stable: compare orders only without ties)
+                assert np.array_equal(boxes, srt)
+            keep = oy.nms_sorted_bboxes(boxes, 0.45, agnostic=bool(agnostic))
+            assert k == len(keep) and list(picked[:k]) == keep
