@@ -175,6 +175,15 @@ NCNN_CUDA_API int ncnn_cuda_conv2d_destroy(ncnn_cuda_conv2d_t conv);
 NCNN_CUDA_API int ncnn_cuda_conv2d_forward(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top,
                                            int pad_left, int pad_top, const ncnn_cuda_tensor* residual, const ncnn_cuda_activation* act_override,
                                            void* workspace, size_t workspace_size, void* stream);
+/* Projection-shortcut fold (load-time fusion; the offline tool fuses only activations, tools/ncnnoptimize.cpp:1268-1419):
+ * `top = act(conv(bottom) + shortcut(bottom2))` where both are 1x1 / pad 0 / no activation and the shortcut may be strided
+ * (src/layer/convolution.cpp:113-184 twice + src/layer/eltwise.cpp SUM): ONE GEMM whose K axis runs over both inputs.
+ * fuse_shortcut takes the reference-order fp32 weights of both layers; returns -1 when the pair cannot be folded (the caller
+ * keeps two layers), as does forward_shortcut for blobs it cannot address (the caller falls back to conv + residual). */
+NCNN_CUDA_API int ncnn_cuda_conv2d_fuse_shortcut(ncnn_cuda_conv2d_t conv, const float* weight_host, const float* bias_host, const ncnn_cuda_conv2d_desc* shortcut_desc,
+                                                 const float* shortcut_weight_host, const float* shortcut_bias_host, void* stream);
+NCNN_CUDA_API int ncnn_cuda_conv2d_forward_shortcut(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* bottom2, const ncnn_cuda_tensor* top,
+                                                    const ncnn_cuda_activation* act, void* stream);
 /* bytes of scratch `forward` needs for this input shape (0 for the implicit-GEMM paths) */
 NCNN_CUDA_API size_t ncnn_cuda_conv2d_workspace_size(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top);
 /* which kernel family a call would use: 0 SIMT fp32, 1 tcgen05 GEMM (1x1), 2 tcgen05 implicit GEMM (TMA im2col), 3 tcgen05 + explicit im2col */

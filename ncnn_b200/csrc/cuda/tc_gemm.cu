@@ -378,6 +378,16 @@ int tc_conv_supported(const TcPlan* plan, const TcConvCall* c)
     if (((uintptr_t)c->in & 15) || ((uintptr_t)c->out & 15)) return 0;
     if (c->residual && ((c->res_cpitch & 7) || ((uintptr_t)c->residual & 15))) return 0;
     if ((long long)c->n * c->outh * c->outw > 0x7fffff00LL) return 0;
+    if (plan->dual_k1_blocks > 0)
+    {
+        // a dual plan only runs as the two-operand GEMM it was packed for
+        if (!c->tiled || !c->in2 || c->residual || plan->block_k != 64) return 0;
+        if ((c->in2_cpitch & 7) || ((uintptr_t)c->in2 & 15) || c->in2_ch != plan->dual_inch2) return 0;
+        if (c->in2_stride_w < 1 || c->in2_stride_h < 1 || c->in2_stride_w > 8 || c->in2_stride_h > 8) return 0;
+        if ((c->in2_w - 1) / c->in2_stride_w + 1 != c->outw || (c->in2_h - 1) / c->in2_stride_h + 1 != c->outh) return 0;
+        return 1;
+    }
+    if (c->in2) return 0;
     if (c->tiled) return 1;
     // TMA im2col limits for 2 spatial dims: corners in [-128, 127], filter offsets <= 255
     // (cutlass/conv/collective/sm100_implicit_gemm_umma_warpspecialized.hpp can_implement)
@@ -417,7 +427,8 @@ static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid
 }
 
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p, long long tiles, cudaStream_t stream)
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, const CUtensorMap& ta2, tc::Params& p, long long tiles,
+                     cudaStream_t stream)
 {
     using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K, CG>;
     static_assert(Plan::stages_for(true) >= 2, "not enough shared memory for a 2-stage pipeline");
@@ -472,13 +483,13 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     {
         // `tiles` counts pair tiles: one cluster of two CTAs (the two SMs of a TPC) per tile, persistent
         const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, to, p));
+        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, to, ta2, p));
         NC_LAUNCH_CHECK();
         count_tc_launch();
         return 0;
     }
     int grid = (int)(tiles < sms ? tiles : sms);
-    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, to, p));
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, to, ta2, p));
     NC_LAUNCH_CHECK();
     count_tc_launch();
     return 0;
@@ -486,21 +497,21 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 
 // the CTA-pair instances: 64-element k-blocks, 128 / 256-wide tiles, tiled and im2col operands
 template<typename T, int AMODE>
-static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p, long long tiles,
-                            cudaStream_t stream)
+static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, const CUtensorMap& ta2, tc::Params& p,
+                            long long tiles, cudaStream_t stream)
 {
-    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, to, p, tiles, stream);
-    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, to, p, tiles, stream);
+    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, to, ta2, p, tiles, stream);
+    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, to, ta2, p, tiles, stream);
     set_last_error_msg("tc_gemm: no CTA-pair kernel instance for this tile shape");
     return -1;
 }
 
 template<typename T, int AMODE>
-static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p,
-                       long long tiles, cudaStream_t stream)
+static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, const CUtensorMap& ta2,
+                       tc::Params& p, long long tiles, cudaStream_t stream)
 {
 #define NC_TC(BN, BK) \
-    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, to, p, tiles, stream)
+    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, to, ta2, p, tiles, stream)
     NC_TC(256, 64);
     NC_TC(128, 64);
     NC_TC(64, 64);
@@ -642,6 +653,45 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
             if (bytes < 131072) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
         }
     }
+    CUtensorMap ta2 = ta;
+    if (plan->dual_k1_blocks > 0)
+    {
+        p.nk2 = plan->num_k_blocks - plan->dual_k1_blocks;
+        p.a2_stride_w = c->in2_stride_w;
+        p.a2_stride_h = c->in2_stride_h;
+        CUresult r;
+        if (c->in2_stride_w == 1 && c->in2_stride_h == 1)
+        {
+            cuuint64_t gdim[2] = {(cuuint64_t)c->in2_ch, (cuuint64_t)M};
+            cuuint64_t gstride[1] = {(cuuint64_t)c->in2_cpitch * 2};
+            cuuint32_t box[2] = {64u, (cuuint32_t)tc::BLOCK_M};
+            cuuint32_t estride[2] = {1, 1};
+            r = g_encodeTiled(&ta2, dtype_for(plan->elemtype), 2, (void*)c->in2, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        else
+        {
+            // 1x1 window walked with the shortcut's stride: TMA im2col mode, upper corner = the (negative) far-side remainder
+            p.a2_im2col = 1;
+            cuuint64_t gdim[4] = {(cuuint64_t)c->in2_ch, (cuuint64_t)c->in2_w, (cuuint64_t)c->in2_h, (cuuint64_t)c->n};
+            cuuint64_t gstride[3] = {(cuuint64_t)c->in2_cpitch * 2, (cuuint64_t)c->in2_cpitch * 2 * c->in2_w, (cuuint64_t)c->in2_cpitch * 2 * c->in2_w * c->in2_h};
+            int lower[2] = {0, 0};
+            int upper[2] = {(c->outw - 1) * c->in2_stride_w + 1 - c->in2_w, (c->outh - 1) * c->in2_stride_h + 1 - c->in2_h};
+            cuuint32_t estride[4] = {1, (cuuint32_t)c->in2_stride_w, (cuuint32_t)c->in2_stride_h, 1};
+            r = g_encodeIm2col(&ta2, dtype_for(plan->elemtype), 4, (void*)c->in2, gdim, gstride, lower, upper, 64u, (cuuint32_t)tc::BLOCK_M, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS && g_driver_version <= 13010)
+            {
+                size_t bytes = (size_t)c->n * c->in2_h * c->in2_w * c->in2_cpitch * 2;
+                if (bytes < 131072) reinterpret_cast<uint64_t*>(&ta2)[1] &= ~(1ull << 21);
+            }
+        }
+        if (r != CUDA_SUCCESS)
+        {
+            set_last_error_msg("cuTensorMapEncode(second operand) failed");
+            return -1;
+        }
+    }
     if (amode != tc::A_ROWS)
     {
         p.cblocks = plan->cblocks;
@@ -723,10 +773,10 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     {
         const long long pair_tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M + 1) / 2 * ((plan->outch + plan->block_n - 1) / plan->block_n);
         if (plan->elemtype == NCNN_CUDA_BF16)
-            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream)
-                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream);
-        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream)
-                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream);
+            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream)
+                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream);
+        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream)
+                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream);
     }
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row
@@ -734,10 +784,10 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);
 
 #define NC_MODE(T)                                                                                                            \
-    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream);  \
-    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream);  \
-    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream); \
-    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, to, p, tiles, stream)
+    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
+    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
+    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream); \
+    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream)
     if (plan->elemtype == NCNN_CUDA_BF16)
     {
         NC_MODE(__nv_bfloat16);

@@ -89,6 +89,10 @@ struct Params
     int sh_chunks_x, sh_tiles_y;    // column chunks per row, row groups per image
     int sh_stage_bytes, sh_box_bytes;
     FastDiv div_sh_chunks_x, div_sh_tiles_y, div_sh_bw;
+    // A_TILED with a SECOND A operand (a folded projection shortcut: top = act(W1 * x1 + W2 * x2 + b)): the last nk2 k-blocks of
+    // the packed weight matrix multiply 64-channel slabs of tmap_a2 -- a plain [M][C2] matrix (a2_im2col = 0) or a 1x1 strided
+    // window walk over an NHWC blob through TMA im2col mode (a2_im2col = 1) -- over the SAME 128 output pixels
+    int nk2, a2_im2col, a2_stride_w, a2_stride_h;
     // tile decode without integer division
     FastDiv div_n_blocks, div_opix, div_outw, div_chunks, div_outh;
 };
@@ -695,7 +699,7 @@ static __device__ __noinline__ float apply_activation_call(float v, int type, fl
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_res,
-               const __grid_constant__ CUtensorMap tmap_out, const Params p)
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_a2, const Params p)
 {
     static_assert(CG == 1 || AMODE == A_TILED || AMODE == A_IM2COL, "CTA pairs: tiled and im2col operand modes only");
     using Plan = SmemPlan<BLOCK_N, BLOCK_K, CG>;
@@ -761,6 +765,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         prefetch_tmap(&tmap_b);
         if (has_res) prefetch_tmap(&tmap_res);
         if (p.tma_store) prefetch_tmap(&tmap_out);
+        if (AMODE == A_TILED && p.nk2 > 0) prefetch_tmap(&tmap_a2);
     }
     if (warp == 1 && lane == 0)
     {
@@ -934,7 +939,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             else
             {
-                for (int kb = 0, kcoord = 0; kb < p.num_k_blocks; kb++, kcoord += BLOCK_K)
+                const int nk1 = p.num_k_blocks - p.nk2;
+                for (int kb = 0, kcoord = 0; kb < nk1; kb++, kcoord += BLOCK_K)
                 {
                     mbar_wait(empty0 + stage * 8, phase ^ 1);
                     if (elect_one())
@@ -953,6 +959,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                     }
                     advance_stage();
+                }
+                if (p.nk2 > 0)
+                {
+                    // the folded shortcut's operand: same output pixels, its own channels; weights continue at column nk1 * BLOCK_K
+                    int w2 = 0, h2 = 0, n2 = 0;
+                    if (p.a2_im2col)
+                    {
+                        n2 = fast_div(m0, p.div_opix);
+                        const int rem = m0 - n2 * (int)p.div_opix.d;
+                        const int oy = fast_div(rem, p.div_outw);
+                        w2 = (rem - oy * p.outw) * p.a2_stride_w;
+                        h2 = oy * p.a2_stride_h;
+                    }
+                    for (int kb = 0, kc2 = 0, kcoord = nk1 * BLOCK_K; kb < p.nk2; kb++, kc2 += BLOCK_K, kcoord += BLOCK_K)
+                    {
+                        mbar_wait(empty0 + stage * 8, phase ^ 1);
+                        if (elect_one())
+                        {
+                            const uint32_t fb = full0 + stage * 8;
+                            if (CG == 1 || cta_rank == 0) mbar_expect_tx(fb, Plan::stage_bytes * CG);
+                            if (CG == 2)
+                            {
+                                if (p.a2_im2col)
+                                    tma_load_im2col_4d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_a2, full0_leader + stage * 8, kc2, w2, h2, n2, (uint16_t)0, (uint16_t)0);
+                                else
+                                    tma_load_2d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_a2, full0_leader + stage * 8, kc2, m0);
+                                tma_load_2d_cg2(smem_b0 + stage * Plan::b_bytes, &tmap_b, full0_leader + stage * 8, kcoord, n_coord);
+                            }
+                            else
+                            {
+                                if (p.a2_im2col)
+                                    tma_load_im2col_4d(smem_a0 + stage * Plan::a_bytes, &tmap_a2, fb, kc2, w2, h2, n2, (uint16_t)0, (uint16_t)0);
+                                else
+                                    tma_load_2d(smem_a0 + stage * Plan::a_bytes, &tmap_a2, fb, kc2, m0);
+                                tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord, n_coord);
+                            }
+                        }
+                        advance_stage();
+                    }
                 }
             }
             if (has_res)
@@ -1522,6 +1567,9 @@ struct TcPlan
     int rows_Kp;
     void* w_rows;      // device, [outch][kh * wp * cp]
     CUtensorMap tmap_b_rows;
+    // folded-shortcut plan (tc_plan_create_dual): K = [k1_blocks * 64 | second operand's channels]
+    int dual_k1_blocks; // 0: a plain single-operand plan
+    int dual_inch2;
 };
 
 int tc_available(); // 1 when the driver exposes cuTensorMapEncode* and the device is sm_100
@@ -1552,6 +1600,9 @@ struct TcConvCall
     int act_type;
     float act_p0, act_p1;
     int tiled; // 1: A is a plain [M][inch] matrix (1x1 s1 p0 / linear)
+    // second A operand of a dual plan (NULL otherwise): [n][in2_h*in2_w][in2_cpitch], sampled with stride (in2_stride_w, in2_stride_h)
+    const void* in2;
+    int in2_h, in2_w, in2_ch, in2_cpitch, in2_stride_w, in2_stride_h;
     void* workspace;
     size_t workspace_size;
 };

@@ -54,6 +54,8 @@ Convolution::Convolution()
     support_inplace = false;
     fused_residual = false;
     fused_post_activation = -1;
+    shortcut = 0;
+    shortcut_fused = false;
     handle = 0;
     handle_elemtype = -1;
 }
@@ -61,6 +63,7 @@ Convolution::Convolution()
 Convolution::~Convolution()
 {
     if (handle) ncnn_cuda_conv2d_destroy(handle);
+    delete shortcut;
 }
 
 // src/layer/convolution.cpp:18-56
@@ -142,6 +145,26 @@ int Convolution::create_pipeline(const Option& opt)
     handle_elemtype = desc.elemtype;
     int ret = ncnn_cuda_conv2d_create(&handle, &desc, (const float*)weight_data.data, bias_term ? (const float*)bias_data.data : 0, 0);
     if (ret != 0) return ret;
+    shortcut_fused = false;
+    if (shortcut)
+    {
+        ncnn_cuda_conv2d_desc sd;
+        memset(&sd, 0, sizeof(sd));
+        sd.outch = shortcut->num_output;
+        sd.inch = shortcut->weight_data_size / shortcut->num_output;
+        sd.kernel_w = sd.kernel_h = 1;
+        sd.dilation_w = sd.dilation_h = 1;
+        sd.stride_w = shortcut->stride_w;
+        sd.stride_h = shortcut->stride_h;
+        sd.bias_term = shortcut->bias_term;
+        sd.elemtype = desc.elemtype;
+        shortcut_fused = ncnn_cuda_conv2d_fuse_shortcut(handle, (const float*)weight_data.data, bias_term ? (const float*)bias_data.data : 0, &sd,
+                                                        (const float*)shortcut->weight_data.data, shortcut->bias_term ? (const float*)shortcut->bias_data.data : 0, 0) == 0;
+        // the shortcut keeps its own pipeline as well: fp32 storage / small channel counts are not folded at kernel level, and a
+        // blob the two-operand GEMM cannot address (a strided view) falls back to shortcut + residual at forward time
+        ret = shortcut->create_pipeline(opt);
+        if (ret != 0) return ret;
+    }
     if (opt.lightmode)
     {
         weight_data.release();
@@ -150,10 +173,11 @@ int Convolution::create_pipeline(const Option& opt)
     return 0;
 }
 
-int Convolution::destroy_pipeline(const Option&)
+int Convolution::destroy_pipeline(const Option& opt)
 {
     if (handle) ncnn_cuda_conv2d_destroy(handle);
     handle = 0;
+    if (shortcut) shortcut->destroy_pipeline(opt);
     return 0;
 }
 
@@ -206,6 +230,34 @@ int Convolution::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaComp
 
 int Convolution::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat>& top_blobs, CudaCompute& cmd, const Option& opt) const
 {
+    if (bottom_blobs.size() == 2 && shortcut)
+    {
+        const CudaMat& x = bottom_blobs[0];
+        const CudaMat& x2 = bottom_blobs[1];
+        if (shortcut_fused && handle && x.dims == 3 && x2.dims == 3)
+        {
+            CudaMat& top_blob = top_blobs[0];
+            top_blob.create(x.w, x.h, num_output, x.elemtype, x.n, cmd.blob_allocator(opt));
+            if (top_blob.empty()) return -100;
+            ncnn_cuda_tensor b = x.view(), b2 = x2.view(), t = top_blob.view();
+            ncnn_cuda_activation act;
+            act.type = fused_post_activation < 0 ? 0 : fused_post_activation;
+            act.p0 = act.p1 = 0.f;
+            int r = ncnn_cuda_conv2d_forward_shortcut(handle, &b, &b2, &t, &act, cmd.stream());
+            if (r != -1) return r;
+            top_blob.release();
+        }
+        // two launches: the shortcut into a scratch blob, then this layer with that blob as the fused residual
+        if (!shortcut->handle)
+        {
+            NCNN_LOGE("Convolution %s: folded shortcut %s has no pipeline for this blob layout", name.c_str(), shortcut->name.c_str());
+            return -1;
+        }
+        CudaMat sc;
+        int r = shortcut->forward_impl(x2, 0, sc, cmd, opt);
+        if (r != 0) return r;
+        return forward_impl(x, &sc, top_blobs[0], cmd, opt);
+    }
     if (bottom_blobs.size() == 2 && fused_residual) return forward_impl(bottom_blobs[0], &bottom_blobs[1], top_blobs[0], cmd, opt);
     if (bottom_blobs.size() == 1) return forward_impl(bottom_blobs[0], 0, top_blobs[0], cmd, opt);
     return -1;

@@ -43,6 +43,11 @@ public:
     // graph-level fusion state (set by Net before create_pipeline)
     bool fused_residual;
     int fused_post_activation; // activation applied after the residual add (-1: none)
+    // projection shortcut folded into this layer (graph-level Conv1x1(a) + Conv1x1(b) -> Eltwise(SUM)[+ReLU]): the other
+    // Convolution, owned by this one; bottom_blobs[1] is ITS input.  `shortcut_fused` says the kernel-level fold succeeded
+    // (one two-operand GEMM); otherwise forward runs the shortcut layer and adds its output as a residual.
+    Convolution* shortcut;
+    bool shortcut_fused;
     ncnn_cuda_conv2d_t handle;
     int handle_elemtype;
 };

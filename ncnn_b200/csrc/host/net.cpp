@@ -894,14 +894,16 @@ int NetPrivate::fuse_graph(const Option&)
     const int L = (int)layers.size();
     // a blob must not be a net output to be folded away
     auto sole_consumer = [&](int blob) -> int { return blobs[blob].consumer; };
-    auto retire = [&](int li) {
-        // turn layer li into a disconnected no-op
+    auto retire = [&](int li, bool keep_object = false) {
+        // turn layer li into a disconnected no-op (keep_object: the layer object lives on inside the layer it was folded into)
         Layer* old = layers[li];
         RetiredLayer* n = new RetiredLayer;
         n->type = "Noop";
         n->name = old->name;
         int ci = layer_custom_index[li];
-        if (ci >= 0 && custom_layer_registry[ci].destroyer)
+        if (keep_object)
+            ;
+        else if (ci >= 0 && custom_layer_registry[ci].destroyer)
             custom_layer_registry[ci].destroyer(old, custom_layer_registry[ci].userdata);
         else
             delete old;
@@ -1047,10 +1049,40 @@ int NetPrivate::fuse_graph(const Option&)
                 {
                     Convolution* c = (Convolution*)layers[best];
                     int conv_top = c->tops[0];
-                    c->fused_residual = true;
+                    // the other operand is itself a bare 1x1 projection (ResNet's downsample branch) and this layer is a plain 1x1:
+                    // fold it in as extra K of ONE GEMM -- its output blob is never written or re-read
+                    Convolution* sc = 0;
+                    if (other_prod >= 0 && layer_custom_index[other_prod] < 0 && layers[other_prod]->type == "Convolution")
+                    {
+                        Convolution* k = (Convolution*)layers[other_prod];
+                        auto bare1x1 = [](const Convolution* q) {
+                            return q->kernel_w == 1 && q->kernel_h == 1 && q->dilation_w == 1 && q->dilation_h == 1 && q->pad_left == 0 && q->pad_right == 0 &&
+                                   q->pad_top == 0 && q->pad_bottom == 0 && q->activation_type == 0 && !q->fused_residual && !q->shortcut;
+                        };
+                        if (bare1x1(k) && bare1x1(c) && c->stride_w == 1 && c->stride_h == 1 && k->num_output == c->num_output && k->tops.size() == 1 &&
+                                k->bottoms.size() == 1 && c->bottoms.size() == 1 && blobs[other_blob].consumer == j)
+                            sc = k;
+                    }
                     c->one_blob_only = false;
-                    c->bottoms.push_back(other_blob);
-                    blobs[other_blob].consumer = best;
+                    if (sc)
+                    {
+                        int sc_bottom = sc->bottoms[0];
+                        c->shortcut = sc;
+                        c->bottoms.push_back(sc_bottom);
+                        blobs[sc_bottom].consumer = best;
+                        blobs[other_blob].producer = -1;
+                        blobs[other_blob].consumer = -1;
+                        blobs[other_blob].folded_into = best;
+                        sc->bottoms.clear();
+                        sc->tops.clear();
+                        retire(other_prod, true);
+                    }
+                    else
+                    {
+                        c->fused_residual = true;
+                        c->bottoms.push_back(other_blob);
+                        blobs[other_blob].consumer = best;
+                    }
                     int final_top = etop;
                     c->fused_post_activation = -1;
                     if (relu_layer >= 0)

@@ -821,3 +821,53 @@ def test_out_of_memory_paths_return_minus_100_and_recover(ref):
     finally:
         net.close()
         L.lib.ncnn_option_destroy(opt)
+
+
+SHORTCUT_GRID = [
+    # (inch of the block input, mid channels, outch, stride of the projection, input size, batch)
+    (64, 64, 256, 1, 14, 3),     # res2a: both operands plain [M][C] matrices
+    (256, 128, 512, 2, 14, 2),   # res3a: strided projection through TMA im2col mode
+    (96, 40, 136, 2, 15, 2),     # channel counts that are no multiple of the 64-channel slab, odd size (remainder column / row)
+    (72, 200, 320, 1, 9, 5),     # K split 256 | 72, three 128-wide column tiles with a ragged last one
+    (512, 256, 1024, 2, 28, 1),  # res4a at its real width: CTA pairs, 256-wide tiles, several m-blocks
+    (16, 24, 32, 1, 8, 2),       # too narrow for the tensor-core fold (main inch <= 32): shortcut + residual fallback
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("case", SHORTCUT_GRID)
+def test_projection_shortcut_fold(ref, case, mode):
+    """load-time fold of ResNet's projection shortcut: Conv1x1(x, stride s) and Conv1x1(branch) -> Eltwise(SUM) -> ReLU run as ONE
+    two-operand tcgen05 GEMM (include/ncnn_cuda.h ncnn_cuda_conv2d_fuse_shortcut).  Reference: the three layers of
+    src/layer/convolution.cpp:113-184 (twice) and src/layer/eltwise.cpp run one after the other.  The folded graph must match the
+    reference and the unfolded graph in every storage type; fp32 storage (no tensor-core plan) takes the shortcut + residual path."""
+    cin, mid, cout, s, size, n = case
+    text = ("7767517\n8 10\nInput data 0 1 data 0=%d 1=%d 2=%d\n"
+            "Split sp 1 2 data d0 d1\n"
+            "Convolution proj 1 1 d1 proj 0=%d 1=1 3=%d 5=1 6=%d\n"
+            "Convolution a 1 1 d0 a 0=%d 1=3 3=%d 4=1 5=1 6=%d 9=1\n"
+            "Convolution c 1 1 a c 0=%d 1=1 5=1 6=%d\n"
+            "Eltwise sum 2 1 proj c sum 0=1\n"
+            "ReLU relu 1 1 sum relu\n"
+            "Pooling output 1 1 relu output 0=1 4=1\n") % (size, size, cin, cout, s, cin * cout, mid, s, 9 * cin * mid, cout, mid * cout)
+    weights = modelzoo.random_model_bytes(text, seed=11)
+    x = np.random.default_rng(5).uniform(-1, 1, (n, cin, size, size)).astype(np.float32)
+    outs = ["relu", "output"]
+    got = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=outs, fusion=1)
+    plain = run_ours(text, weights, {"data": x}, mode, batched=True, outputs=outs, fusion=0)
+    want = run_ref(ref, text, weights, {"data": x}, batched=True, outputs=outs)
+    tol = {"fp32": 1e-5, "fp16": 2e-3, "bf16": 1e-2}[mode]
+    for k in outs:
+        assert got[k].shape == want[k].shape
+        assert nerr(got[k], want[k]) <= tol, (case, mode, k, nerr(got[k], want[k]))
+        assert nerr(plain[k], want[k]) <= tol, (case, mode, k, nerr(plain[k], want[k]))
+    # the fold really happened: the projection's blob is gone from the folded graph
+    from ncnn_b200 import capi
+    L = product()
+    opt = L.make_option(1, **MODES[mode])
+    net = capi.Net(L, text, weights, opt)
+    try:
+        assert L.lib.ncnn_net_get_fused_layer_count(net.net) >= 3  # Eltwise, ReLU, proj
+    finally:
+        net.close()
+        L.lib.ncnn_option_destroy(opt)
