@@ -184,6 +184,16 @@ NCNN_CUDA_API int ncnn_cuda_conv2d_fuse_shortcut(ncnn_cuda_conv2d_t conv, const 
                                                  const float* shortcut_weight_host, const float* shortcut_bias_host, void* stream);
 NCNN_CUDA_API int ncnn_cuda_conv2d_forward_shortcut(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* bottom2, const ncnn_cuda_tensor* top,
                                                     const ncnn_cuda_activation* act, void* stream);
+/* Stem fold (load-time fusion): Convolution (+bias, ReLU) followed by max Pooling 3x3 stride 2 (src/layer/convolution.cpp:113-184 +
+ * src/layer/pooling.cpp:188-253) in ONE kernel for small-channel stride-2 stems (ResNet conv1 7x7, SqueezeNet conv1 3x3): the
+ * full-resolution conv map never reaches HBM.  `top` is the pooled blob, pool_pad_* the window's leading pads (trailing windows
+ * are clipped to the map, which is what the reference's -FLT_MAX border does); workspace as for `forward`
+ * (ncnn_cuda_conv2d_workspace_size with the conv map's shape).  Returns -1 when the pair cannot be fused (caller runs two layers). */
+NCNN_CUDA_API int ncnn_cuda_conv2d_maxpool3x3s2_supported(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, int conv_outw, int conv_outh, int pad_left, int pad_top,
+                                                          int pw, int ph, int pool_pad_left, int pool_pad_top);
+NCNN_CUDA_API int ncnn_cuda_conv2d_forward_maxpool3x3s2(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, int conv_outw, int conv_outh, int pad_left, int pad_top,
+                                                        const ncnn_cuda_tensor* top, int pool_pad_left, int pool_pad_top, void* workspace, size_t workspace_size,
+                                                        void* stream);
 /* bytes of scratch `forward` needs for this input shape (0 for the implicit-GEMM paths) */
 NCNN_CUDA_API size_t ncnn_cuda_conv2d_workspace_size(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top);
 /* which kernel family a call would use: 0 SIMT fp32, 1 tcgen05 GEMM (1x1), 2 tcgen05 implicit GEMM (TMA im2col), 3 tcgen05 + explicit im2col */

@@ -358,6 +358,58 @@ int ncnn_cuda_conv2d_forward_shortcut(ncnn_cuda_conv2d_t conv, const ncnn_cuda_t
     return tc_conv_forward(&conv->tc_dual, &call, stream);
 }
 
+// Convolution (+bias, ReLU) and the 3x3 stride-2 max pooling behind it in one kernel (stem_pool.cuh): small-channel stride-2 stems
+// whose output row fits one 128-column tile.  `top` is the POOLED blob; the conv map (conv_outw x conv_outh) is never written.
+static int maxpool_fold_call(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, int conv_outw, int conv_outh, int pad_left, int pad_top, int pw, int ph,
+                             int pool_pad_left, int pool_pad_top, TcConvCall* call, TcPoolCall* pc)
+{
+    if (!conv || !bottom || !conv->has_tc || bottom->dims != 3) return -1;
+    if (bottom->elemtype != conv->desc.elemtype || !dense(bottom) || conv->desc.pad_value != 0.f) return -1;
+    // the conv map's shape on a stand-in tensor (never addressed)
+    ncnn_cuda_tensor ct = *bottom;
+    ct.w = conv_outw;
+    ct.h = conv_outh;
+    ct.c = conv->desc.outch;
+    ct.cpitch = (conv->desc.outch + 7) & ~7;
+    Geom2 g;
+    if (geom_of(conv, bottom, &ct, &g) != 0) return -1;
+    fill_call(conv, g, bottom, &ct, pad_left, pad_top, 0, conv->desc.act, call);
+    pc->pad_left = pool_pad_left;
+    pc->pad_top = pool_pad_top;
+    pc->pw = pw;
+    pc->ph = ph;
+    pc->out = bottom->data; // (aligned stand-in for the support check; the caller sets the real blob)
+    pc->out_cpitch = ct.cpitch;
+    call->out = bottom->data;
+    call->out_cpitch = ct.cpitch;
+    return tc_stem_pool_supported(&conv->tc, call, pc) ? 0 : -1;
+}
+
+int ncnn_cuda_conv2d_maxpool3x3s2_supported(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, int conv_outw, int conv_outh, int pad_left, int pad_top, int pw, int ph,
+                                            int pool_pad_left, int pool_pad_top)
+{
+    TcConvCall call;
+    TcPoolCall pc;
+    return maxpool_fold_call(conv, bottom, conv_outw, conv_outh, pad_left, pad_top, pw, ph, pool_pad_left, pool_pad_top, &call, &pc) == 0 ? 1 : 0;
+}
+
+int ncnn_cuda_conv2d_forward_maxpool3x3s2(ncnn_cuda_conv2d_t conv, const ncnn_cuda_tensor* bottom, int conv_outw, int conv_outh, int pad_left, int pad_top,
+                                          const ncnn_cuda_tensor* top, int pool_pad_left, int pool_pad_top, void* workspace, size_t workspace_size, void* stream_)
+{
+    cudaStream_t stream = as_stream(stream_);
+    NC_REQUIRE(conv && bottom && top && bottom->data && top->data, "conv2d_forward_maxpool: null argument");
+    if (top->dims != 3 || top->elemtype != conv->desc.elemtype || !dense(top) || top->c != conv->desc.outch || top->n != bottom->n) return -1;
+    TcConvCall call;
+    TcPoolCall pc;
+    if (maxpool_fold_call(conv, bottom, conv_outw, conv_outh, pad_left, pad_top, top->w, top->h, pool_pad_left, pool_pad_top, &call, &pc) != 0) return -1;
+    call.workspace = workspace;
+    call.workspace_size = workspace_size;
+    pc.out = top->data;
+    pc.out_cpitch = top->cpitch;
+    if (!tc_stem_pool_supported(&conv->tc, &call, &pc)) return -1;
+    return tc_stem_pool_forward(&conv->tc, &call, &pc, stream);
+}
+
 int ncnn_cuda_linear_create(ncnn_cuda_linear_t* fc, const ncnn_cuda_linear_desc* d, const float* weight, const float* bias, void* stream)
 {
     ncnn_cuda_conv2d_desc cd;

@@ -3,6 +3,7 @@
 // encoding (tiled for weights, outputs, residuals and 1x1 convs; im2col mode for general convs; overlapping-stride
 // tiled maps for small-channel stems) and the persistent-kernel launch.
 #include "tc_gemm.cuh"
+#include "stem_pool.cuh"
 
 #include <mutex>
 #include <stdlib.h>
@@ -259,7 +260,9 @@ static bool rows_applicable(const TcPlan* plan, const TcConvCall* c, RowsGeom* g
     g->Lp = c->pad_left + plan->rows_shift;
     int need_w = c->stride_w * (c->outw - 1) + wp;
     int wpitch = g->Lp + c->inw > need_w ? g->Lp + c->inw : need_w;
-    if (cp == 4) wpitch = (wpitch + 1) & ~1; // 16-byte row pitch
+    // rows start on 128-byte lines: a cp.async.bulk row segment whose source is only 16-byte aligned moves at ~14 B/cycle/SM
+    // (measured: the ResNet stem was paced by its seven 2 KB copies per tile, not by the MMAs or the epilogue)
+    wpitch = (wpitch + 64 / cp - 1) / (64 / cp) * (64 / cp);
     int need_h = c->stride_h * (c->outh - 1) + (c->kernel_h - 1) * c->dil_h + 1;
     int hp = c->pad_top + c->inh > need_h ? c->pad_top + c->inh : need_h;
     g->Wpitch = wpitch;
@@ -279,34 +282,77 @@ size_t tc_conv_workspace(const TcPlan* plan, const TcConvCall* c)
     return g.bytes;
 }
 
-// NHWC blob (cpitch channels per pixel) -> zero-padded [n][Hp][Wpitch][CP] copy; one thread per destination pixel
+// NHWC blob (cpitch channels per pixel) -> zero-padded [n][Hp][Wpitch][CP] copy.  One CTA per padded row at a time (one division
+// per row, none per pixel); a thread produces one 16-byte unit of the row -- two 4-channel pixels or one 8-channel pixel -- from
+// 8 / 16-byte loads of the source pixels' leading channels; lanes of the blob beyond `inch` are masked to zero.
 template<int CP>
-__global__ void __launch_bounds__(256) rows_pack_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int inh, int inw, int inch, int in_cpitch,
+__global__ void __launch_bounds__(128) rows_pack_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int n, int inh, int inw, int inch, int in_cpitch,
                                                         int Hp, int Wpitch, int Lp, int pad_top)
 {
-    const long long total = (long long)n * Hp * Wpitch;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    NC_PDL_PROLOGUE();
+    const int rows = n * Hp;
+    const int units = Wpitch * CP / 8; // 16-byte units per padded row
+    const unsigned long long keep = inch >= 4 ? ~0ull : ((1ull << (16 * inch)) - 1ull);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x)
     {
-        const int x = (int)(i % Wpitch);
-        long long r = i / Wpitch;
-        const int y = (int)(r % Hp);
-        const int b = (int)(r / Hp);
-        const int sx = x - Lp, sy = y - pad_top;
-        uint16_t v[CP];
-#pragma unroll
-        for (int k = 0; k < CP; k++) v[k] = 0;
-        if (sx >= 0 && sx < inw && sy >= 0 && sy < inh)
+        const int b = row / Hp;
+        const int sy = row - b * Hp - pad_top;
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * Wpitch * CP);
+        if (sy < 0 || sy >= inh)
         {
-            const uint16_t* src = in + ((long long)b * inh * inw + (long long)sy * inw + sx) * in_cpitch;
-#pragma unroll
-            for (int k = 0; k < CP; k++)
-                if (k < inch) v[k] = src[k];
+            for (int u = threadIdx.x; u < units; u += blockDim.x) dst[u] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
         }
-        if (CP == 4)
-            *reinterpret_cast<uint2*>(out + i * CP) = *reinterpret_cast<const uint2*>(v);
-        else
-            *reinterpret_cast<uint4*>(out + i * CP) = *reinterpret_cast<const uint4*>(v);
+        const uint16_t* srow = in + ((long long)b * inh + sy) * (long long)inw * in_cpitch;
+        for (int u = threadIdx.x; u < units; u += blockDim.x)
+        {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (CP == 4)
+            {
+                const int x0 = 2 * u - Lp, x1 = x0 + 1;
+                unsigned long long p0 = 0ull, p1 = 0ull;
+                if (x0 >= 0 && x0 < inw) p0 = __ldg(reinterpret_cast<const unsigned long long*>(srow + (long long)x0 * in_cpitch)) & keep;
+                if (x1 >= 0 && x1 < inw) p1 = __ldg(reinterpret_cast<const unsigned long long*>(srow + (long long)x1 * in_cpitch)) & keep;
+                v.x = (uint32_t)p0;
+                v.y = (uint32_t)(p0 >> 32);
+                v.z = (uint32_t)p1;
+                v.w = (uint32_t)(p1 >> 32);
+            }
+            else
+            {
+                const int x0 = u - Lp;
+                if (x0 >= 0 && x0 < inw)
+                {
+                    v = __ldg(reinterpret_cast<const uint4*>(srow + (long long)x0 * in_cpitch));
+                    if (inch < 8)
+                    {
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            if (2 * k >= inch) w[k] = 0u;
+                            else if (2 * k + 1 >= inch) w[k] &= 0xFFFFu;
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            dst[u] = v;
+        }
     }
+}
+
+static int launch_rows_pack(int cp, const TcConvCall* c, int Hp, int Wpitch, int Lp, cudaStream_t stream)
+{
+    const int rows = c->n * Hp;
+    const int grid = rows < sm_count() * 16 ? rows : sm_count() * 16;
+    if (cp == 4)
+        NC_PDL_LAUNCH(rows_pack_kernel<4>, grid, 128, 0, stream, (const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, Hp, Wpitch, Lp,
+                      c->pad_top);
+    else
+        NC_PDL_LAUNCH(rows_pack_kernel<8>, grid, 128, 0, stream, (const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, Hp, Wpitch, Lp,
+                      c->pad_top);
+    return 0;
 }
 
 // ---------------------------------------------------------------- A_SHIFT geometry (tc_gemm.cuh)
@@ -589,15 +635,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     {
         const int cp = plan->rows_cp;
         // zero-padded small-channel copy of the input
-        const long long total = (long long)c->n * rg.Hp * rg.Wpitch;
-        int grid = grid_for(total, 256, 16);
-        if (cp == 4)
-            rows_pack_kernel<4><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
-                                                         c->pad_top);
-        else
-            rows_pack_kernel<8><<<grid, 256, 0, stream>>>((const uint16_t*)c->in, (uint16_t*)c->workspace, c->n, c->inh, c->inw, c->inch, c->in_cpitch, rg.Hp, rg.Wpitch, rg.Lp,
-                                                         c->pad_top);
-        NC_LAUNCH_CHECK();
+        if (launch_rows_pack(cp, c, rg.Hp, rg.Wpitch, rg.Lp, stream) != 0) return -100;
         amode = tc::A_ROWS;
         block_k = plan->rows_block_k;
         tb = &plan->tmap_b_rows;
@@ -794,6 +832,130 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     }
     NC_MODE(__half);
 #undef NC_MODE
+}
+
+// ---------------------------------------------------------------- stem convolution + 3x3 s2 max pooling in one kernel (stem_pool.cuh)
+int tc_stem_pool_supported(const TcPlan* plan, const TcConvCall* c, const TcPoolCall* pc)
+{
+    RowsGeom rg;
+    if (!tc_conv_supported(plan, c) || !rows_applicable(plan, c, &rg)) return 0;
+    if (plan->rows_cp != 4 || plan->block_n != 64 || plan->outch > 64 || c->outw > tc::BLOCK_M || c->dil_h != 1) return 0;
+    if (c->act_type != 0 && c->act_type != 1) return 0; // the activation must commute with max: none or ReLU
+    if (pc->pad_left < 0 || pc->pad_left > 2 || pc->pad_top < 0 || pc->pad_top > 2 || pc->pw <= 0 || pc->ph <= 0) return 0;
+    // every pooling window must hold at least one conv element
+    if (2 * (pc->pw - 1) - pc->pad_left >= c->outw || 2 * (pc->ph - 1) - pc->pad_top >= c->outh) return 0;
+    if ((pc->out_cpitch & 7) || ((uintptr_t)pc->out & 15)) return 0;
+    if ((long long)c->n * pc->ph > 0x3fffffffLL) return 0;
+    return 1;
+}
+
+template<typename T, int BLOCK_K>
+static int launch_stem_pool(const CUtensorMap& tb, tc::StemPoolParams& p, cudaStream_t stream)
+{
+    auto kern = tc::stem_pool_kernel<T, BLOCK_K>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        NC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int b_bytes = tc::kStemN * BLOCK_K * 2;
+    const int fixed = ((p.taps_h * b_bytes + 1023) & ~1023) + tc::kStemRowSlots * tc::kStemRowSlotBytes + tc::kStemN * 4 + 512 + 1024;
+    int stages = (227 * 1024 - fixed) / p.rows_stage_bytes;
+    if (stages > 16) stages = 16;
+    if (stages < 2)
+    {
+        set_last_error_msg("stem_pool: the filter rows do not fit in shared memory");
+        return -1;
+    }
+    p.num_stages = stages;
+    const int smem_bytes = stages * p.rows_stage_bytes + fixed;
+    const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, tb, p));
+    NC_LAUNCH_CHECK();
+    count_tc_launch();
+    return 0;
+}
+
+int tc_stem_pool_forward(const TcPlan* plan, const TcConvCall* c, const TcPoolCall* pc, cudaStream_t stream)
+{
+    RowsGeom rg;
+    if (!tc_stem_pool_supported(plan, c, pc) || !rows_applicable(plan, c, &rg)) return -1;
+    if (!c->workspace || c->workspace_size < rg.bytes) return -1;
+    if (launch_rows_pack(plan->rows_cp, c, rg.Hp, rg.Wpitch, rg.Lp, stream) != 0) return -100;
+    tc::StemPoolParams p;
+    memset(&p, 0, sizeof(p));
+    const int cp = plan->rows_cp;
+    p.rows_src = (const unsigned char*)c->workspace;
+    p.rows_row_bytes = rg.Wpitch * cp * 2;
+    p.rows_img_bytes = (long long)rg.Hp * rg.Wpitch * cp * 2;
+    p.rows_seg_bytes = rg.seg_bytes;
+    // one contiguous copy per tile: filter row ky of a conv row is padded row r * stride_h + ky, the shared-memory pitch is the
+    // global row pitch, and the overhang of the last row's 128-window segment comes along (the workspace has the slack)
+    p.rows_seg_pitch = p.rows_row_bytes;
+    {
+        int over = rg.seg_bytes - p.rows_row_bytes;
+        if (over < 0) over = 0;
+        p.rows_copy_bytes = c->kernel_h * p.rows_row_bytes + (over + 15) / 16 * 16;
+    }
+    p.rows_stage_bytes = ((p.rows_copy_bytes + 1023) / 1024) * 1024;
+    p.taps_h = c->kernel_h;
+    p.stride_h = c->stride_h;
+    p.outw = c->outw;
+    p.outh = c->outh;
+    p.N = plan->outch;
+    p.bias = plan->bias_pad;
+    p.relu = c->act_type == 1;
+    p.pad_left = pc->pad_left;
+    p.pad_top = pc->pad_top;
+    p.pw = pc->pw;
+    p.ph = pc->ph;
+    p.out = pc->out;
+    p.out_cpitch = pc->out_cpitch;
+    // bands of pooled rows: one conv row per band is computed twice, fewer bands waste fewer rows but quantise worse over the
+    // SMs -- pick the band height with the fewest conv-row tiles on the busiest CTA
+    {
+        const int sms = sm_count();
+        long long best_cost = -1;
+        int best_rows = pc->ph;
+        for (int bands = 1; bands <= pc->ph && bands <= 64; bands++)
+        {
+            const int br = (pc->ph + bands - 1) / bands;
+            const int nb = (pc->ph + br - 1) / br;
+            const long long items = (long long)c->n * nb;
+            const long long rounds = (items + sms - 1) / sms;
+            const long long cost = rounds * (2 * br + 1);
+            if (best_cost < 0 || cost < best_cost)
+            {
+                best_cost = cost;
+                best_rows = br;
+            }
+        }
+        p.band_rows = best_rows;
+        p.bands = (pc->ph + best_rows - 1) / best_rows;
+        p.num_items = c->n * p.bands;
+        p.div_bands = make_fastdiv((unsigned int)p.bands);
+    }
+    {
+        static int dbg = -1;
+        if (dbg < 0)
+        {
+            const char* e = getenv("NCNN_B200_STEM_DBG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.dbg = dbg;
+    }
+    const int bk = plan->rows_block_k;
+#define NC_STEM(T)                                                                      \
+    if (bk == 16) return launch_stem_pool<T, 16>(plan->tmap_b_rows, p, stream);         \
+    if (bk == 32) return launch_stem_pool<T, 32>(plan->tmap_b_rows, p, stream);         \
+    return launch_stem_pool<T, 64>(plan->tmap_b_rows, p, stream)
+    if (plan->elemtype == NCNN_CUDA_BF16)
+    {
+        NC_STEM(__nv_bfloat16);
+    }
+    NC_STEM(__half);
+#undef NC_STEM
 }
 
 } // namespace ncnn_cuda

@@ -1057,22 +1057,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
             if (AMODE == A_ROWS)
             {
-                // the whole tile sits in one stage: kh filter rows x (BLOCK_K / 16) MMAs, one commit
+                // the whole tile sits in one stage: kh filter rows x (BLOCK_K / 16) MMAs, one commit.  As in the shifted-window
+                // mode only the 14-bit address field of the descriptors moves: low words computed warp-uniformly outside the
+                // elected branch, filter rows unrolled for the common heights (measured on the ResNet stem: ~20 instructions per
+                // MMA made the issuing lane, not the tensor pipe, pace the kernel at 1.8 k cycles per tile)
                 mbar_wait(full0 + stage * 8, phase);
                 tc_fence_after();
-                if (elect_one())
-                {
-                    const uint32_t a_base = smem_a0 + stage * p.rows_stage_bytes;
-                    const uint32_t b_base = smem_u32(smem_res);
-                    for (int ky = 0; ky < p.taps_h; ky++)
-                    {
-                        const uint64_t adesc = make_smem_desc_overlap16(a_base + ky * p.rows_seg_pitch);
-                        const uint64_t bdesc = make_smem_desc<BLOCK_K>(b_base + ky * Plan::b_bytes);
+                const uint64_t a_hi = make_smem_desc_overlap16(0) & 0xFFFFFFFF00000000ull;
+                const uint32_t a_flags = (uint32_t)(make_smem_desc_overlap16(0) & 0xFFFFC000ull);
+                const uint64_t b_hi = make_smem_desc<BLOCK_K>(0) & 0xFFFFFFFF00000000ull;
+                const uint32_t b_flags = (uint32_t)(make_smem_desc<BLOCK_K>(0) & 0xFFFFC000ull);
+                const uint32_t a_lo0 = (((smem_a0 + (uint32_t)(stage * p.rows_stage_bytes)) & 0x3FFFF) >> 4) | a_flags;
+                const uint32_t b_lo0 = ((smem_u32(smem_res) & 0x3FFFF) >> 4) | b_flags;
+                const uint32_t a_step = (uint32_t)p.rows_seg_pitch >> 4;
+                constexpr uint32_t b_step = (uint32_t)Plan::b_bytes >> 4;
+                const uint32_t commit_a = empty0 + stage * 8, commit_d = smem_u32(&tmem_full_bar[acc]);
+                auto mma_row = [&](int ky) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; k++) umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((ky | k) != 0));
+                    for (int k = 0; k < BLOCK_K / 16; k++)
+                        umma_f16(tmem_d, a_hi | (uint64_t)(a_lo0 + (uint32_t)ky * a_step + (uint32_t)(k * 2)), b_hi | (uint64_t)(b_lo0 + (uint32_t)ky * b_step + (uint32_t)(k * 2)),
+                                 idesc, (uint32_t)((ky | k) != 0));
+                };
+                if (p.taps_h == 3)
+                {
+                    if (elect_one())
+                    {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ky++) mma_row(ky);
+                        umma_commit(commit_a);
+                        umma_commit(commit_d);
                     }
-                    umma_commit(empty0 + stage * 8);
-                    umma_commit(smem_u32(&tmem_full_bar[acc]));
+                }
+                else if (p.taps_h == 7)
+                {
+                    if (elect_one())
+                    {
+#pragma unroll
+                        for (int ky = 0; ky < 7; ky++) mma_row(ky);
+                        umma_commit(commit_a);
+                        umma_commit(commit_d);
+                    }
+                }
+                else
+                {
+                    if (elect_one())
+                    {
+                        for (int ky = 0; ky < p.taps_h; ky++) mma_row(ky);
+                        umma_commit(commit_a);
+                        umma_commit(commit_d);
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages)
@@ -1606,6 +1639,18 @@ struct TcConvCall
     void* workspace;
     size_t workspace_size;
 };
+
+// 3x3 stride-2 max pooling fused behind a stem convolution (stem_pool.cuh): leading pads and pooled output
+struct TcPoolCall
+{
+    int pad_left, pad_top; // rows / columns before the conv map that the first window covers (trailing ones are implied by pw / ph)
+    int pw, ph;
+    void* out; // [n][ph][pw][out_cpitch]
+    int out_cpitch;
+};
+int tc_stem_pool_supported(const TcPlan* plan, const TcConvCall* call, const TcPoolCall* pool);
+// the call's `out` is unused (the conv map is never written); workspace as for the A_ROWS variant.  0 ok, -1 unsupported
+int tc_stem_pool_forward(const TcPlan* plan, const TcConvCall* call, const TcPoolCall* pool, cudaStream_t stream);
 
 // returns 0 ok, -1 if the geometry cannot be expressed as a TMA descriptor (caller falls back)
 int tc_conv_forward(const TcPlan* plan, const TcConvCall* call, cudaStream_t stream);

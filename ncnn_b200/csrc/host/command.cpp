@@ -301,6 +301,13 @@ int CudaCompute::record_clone(const CudaMat& src, CudaMat& dst, const Option& op
     if (src.empty()) return -100;
     dst.create_like(src, blob_allocator(opt));
     if (dst.empty()) return -100;
+    // a channel-range view (Slice as a view, a Concat input written in place) has its parent's pitch: the clone is dense, so
+    // the copy is a pitched gather, not one flat memcpy
+    if (src.dims == 3 && (dst.cpitch != src.cpitch || dst.nstep != src.nstep))
+    {
+        ncnn_cuda_tensor s = src.view(), d = dst.view();
+        return ncnn_cuda_copy_from_axis(&s, &d, 0, 0, stream());
+    }
     return ncnn_cuda_memcpy_d2d_async(dst.data, src.data, src.total_elems() * src.elemsize(), stream());
 }
 

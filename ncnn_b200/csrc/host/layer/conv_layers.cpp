@@ -56,6 +56,7 @@ Convolution::Convolution()
     fused_post_activation = -1;
     shortcut = 0;
     shortcut_fused = false;
+    fused_pool = 0;
     handle = 0;
     handle_elemtype = -1;
 }
@@ -64,6 +65,7 @@ Convolution::~Convolution()
 {
     if (handle) ncnn_cuda_conv2d_destroy(handle);
     delete shortcut;
+    delete fused_pool;
 }
 
 // src/layer/convolution.cpp:18-56
@@ -225,7 +227,41 @@ int Convolution::forward_impl(const CudaMat& bottom_blob, const CudaMat* residua
 
 int Convolution::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const
 {
-    return forward_impl(bottom_blob, 0, top_blob, cmd, opt);
+    if (!fused_pool) return forward_impl(bottom_blob, 0, top_blob, cmd, opt);
+    // stem fold: conv (+ReLU) + max pooling 3x3 s2 in one kernel when the geometry allows
+    if (handle && bottom_blob.dims == 3)
+    {
+        const int w = bottom_blob.w, h = bottom_blob.h;
+        int pads[4];
+        resolve_conv_pads(w, h, kernel_w, kernel_h, dilation_w, dilation_h, stride_w, stride_h, pad_left, pad_right, pad_top, pad_bottom, pads);
+        const int cw = (w + pads[0] + pads[1] - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+        const int ch = (h + pads[2] + pads[3] - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+        int al, at, pw, ph;
+        ncnn_cuda_tensor b = bottom_blob.view();
+        if (cw > 0 && ch > 0 && fused_pool->window_geometry(cw, ch, al, at, pw, ph) &&
+                ncnn_cuda_conv2d_maxpool3x3s2_supported(handle, &b, cw, ch, pads[0], pads[2], pw, ph, al, at))
+        {
+            top_blob.create(pw, ph, num_output, bottom_blob.elemtype, bottom_blob.n, cmd.blob_allocator(opt));
+            if (top_blob.empty()) return -100;
+            ncnn_cuda_tensor t = top_blob.view();
+            ncnn_cuda_tensor ct = t;
+            ct.w = cw;
+            ct.h = ch;
+            CudaMat workspace;
+            size_t wsize = ncnn_cuda_conv2d_workspace_size(handle, &b, &ct);
+            if (wsize > 0) workspace.create((int)((wsize + 3) / 4), NCNN_CUDA_F32, 1, cmd.workspace_allocator(opt));
+            if (workspace.empty()) return -100;
+            return ncnn_cuda_conv2d_forward_maxpool3x3s2(handle, &b, cw, ch, pads[0], pads[2], &t, al, at, workspace.data, wsize, cmd.stream());
+        }
+    }
+    // two launches; the conv map is a scratch blob of THIS layer: never placed into a Concat buffer (opt may carry a placement
+    // allocator meant for the pooled top)
+    Option opt_scratch = opt;
+    if (opt.blob_cuda_allocator) opt_scratch.blob_cuda_allocator = opt.blob_cuda_allocator->real();
+    CudaMat conv_top;
+    int r = forward_impl(bottom_blob, 0, conv_top, cmd, opt_scratch);
+    if (r != 0) return r;
+    return fused_pool->forward(conv_top, top_blob, cmd, opt);
 }
 
 int Convolution::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<CudaMat>& top_blobs, CudaCompute& cmd, const Option& opt) const
@@ -253,8 +289,10 @@ int Convolution::forward(const std::vector<CudaMat>& bottom_blobs, std::vector<C
             NCNN_LOGE("Convolution %s: folded shortcut %s has no pipeline for this blob layout", name.c_str(), shortcut->name.c_str());
             return -1;
         }
+        Option opt_scratch = opt;
+        if (opt.blob_cuda_allocator) opt_scratch.blob_cuda_allocator = opt.blob_cuda_allocator->real();
         CudaMat sc;
-        int r = shortcut->forward_impl(x2, 0, sc, cmd, opt);
+        int r = shortcut->forward_impl(x2, 0, sc, cmd, opt_scratch);
         if (r != 0) return r;
         return forward_impl(x, &sc, top_blobs[0], cmd, opt);
     }
@@ -612,6 +650,63 @@ int Pooling::load_param(const ParamDict& pd)
     return 0;
 }
 
+// make_padding, pooling.cpp:350-412: the effective pads of a windowed pooling over a (w, h) map (no padded copy is made)
+void Pooling::resolve_pads(int w, int h, int& al, int& ar, int& at, int& ab, int& wtail, int& htail) const
+{
+    al = ar = at = ab = wtail = htail = 0;
+    if (pad_mode == 0)
+    {
+        int wt = (w + pad_left + pad_right - kernel_w) % stride_w;
+        int ht = (h + pad_top + pad_bottom - kernel_h) % stride_h;
+        if (wt != 0) wtail = stride_w - wt;
+        if (ht != 0) htail = stride_h - ht;
+        al = pad_left;
+        ar = pad_right + wtail;
+        at = pad_top;
+        ab = pad_bottom + htail;
+    }
+    else if (pad_mode == 1)
+    {
+        al = pad_left;
+        ar = pad_right;
+        at = pad_top;
+        ab = pad_bottom;
+    }
+    else if (pad_mode == 2 || pad_mode == 3)
+    {
+        int wpad = kernel_w + (w - 1) / stride_w * stride_w - w;
+        int hpad = kernel_h + (h - 1) / stride_h * stride_h - h;
+        if (wpad > 0 || hpad > 0)
+        {
+            if (pad_mode == 2)
+            {
+                at = hpad / 2;
+                ab = hpad - hpad / 2;
+                al = wpad / 2;
+                ar = wpad - wpad / 2;
+            }
+            else
+            {
+                at = hpad - hpad / 2;
+                ab = hpad / 2;
+                al = wpad - wpad / 2;
+                ar = wpad / 2;
+            }
+        }
+    }
+}
+
+// output size and leading pads of the window walk (pooling.cpp:197-198); false for global / adaptive pooling
+bool Pooling::window_geometry(int w, int h, int& al, int& at, int& outw, int& outh) const
+{
+    if (global_pooling || adaptive_pooling) return false;
+    int ar, ab, wtail, htail;
+    resolve_pads(w, h, al, ar, at, ab, wtail, htail);
+    outw = (w + al + ar - kernel_w) / stride_w + 1;
+    outh = (h + at + ab - kernel_h) / stride_h + 1;
+    return outw > 0 && outh > 0;
+}
+
 int Pooling::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const
 {
     if (bottom_blob.dims != 3) return -1;
@@ -648,48 +743,8 @@ int Pooling::forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute&
     }
     else
     {
-        // make_padding, pooling.cpp:350-412 (no padded copy is made: the kernel predicates)
-        int al = 0, ar = 0, at = 0, ab = 0, wtail = 0, htail = 0;
-        if (pad_mode == 0)
-        {
-            int wt = (w + pad_left + pad_right - kernel_w) % stride_w;
-            int ht = (h + pad_top + pad_bottom - kernel_h) % stride_h;
-            if (wt != 0) wtail = stride_w - wt;
-            if (ht != 0) htail = stride_h - ht;
-            al = pad_left;
-            ar = pad_right + wtail;
-            at = pad_top;
-            ab = pad_bottom + htail;
-        }
-        else if (pad_mode == 1)
-        {
-            al = pad_left;
-            ar = pad_right;
-            at = pad_top;
-            ab = pad_bottom;
-        }
-        else if (pad_mode == 2 || pad_mode == 3)
-        {
-            int wpad = kernel_w + (w - 1) / stride_w * stride_w - w;
-            int hpad = kernel_h + (h - 1) / stride_h * stride_h - h;
-            if (wpad > 0 || hpad > 0)
-            {
-                if (pad_mode == 2)
-                {
-                    at = hpad / 2;
-                    ab = hpad - hpad / 2;
-                    al = wpad / 2;
-                    ar = wpad - wpad / 2;
-                }
-                else
-                {
-                    at = hpad - hpad / 2;
-                    ab = hpad / 2;
-                    al = wpad - wpad / 2;
-                    ar = wpad / 2;
-                }
-            }
-        }
+        int al, ar, at, ab, wtail, htail;
+        resolve_pads(w, h, al, ar, at, ab, wtail, htail);
         const int bw = w + al + ar, bh = h + at + ab;
         const int outw = (bw - kernel_w) / stride_w + 1; // pooling.cpp:197-198
         const int outh = (bh - kernel_h) / stride_h + 1;

@@ -48,6 +48,9 @@ public:
     // (one two-operand GEMM); otherwise forward runs the shortcut layer and adds its output as a residual.
     Convolution* shortcut;
     bool shortcut_fused;
+    // max Pooling 3x3 s2 folded behind this (stem) convolution: owned here; forward produces the POOLED blob in one kernel when
+    // the geometry allows, else runs the two layers one after the other
+    class Pooling* fused_pool;
     ncnn_cuda_conv2d_t handle;
     int handle_elemtype;
 };
@@ -143,6 +146,8 @@ public:
     Pooling();
     virtual int load_param(const ParamDict& pd);
     virtual int forward(const CudaMat& bottom_blob, CudaMat& top_blob, CudaCompute& cmd, const Option& opt) const;
+    void resolve_pads(int w, int h, int& al, int& ar, int& at, int& ab, int& wtail, int& htail) const;
+    bool window_geometry(int w, int h, int& al, int& at, int& outw, int& outh) const;
 
 public:
     int pooling_type, kernel_w, kernel_h, stride_w, stride_h, pad_left, pad_right, pad_top, pad_bottom;

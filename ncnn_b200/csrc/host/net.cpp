@@ -1006,6 +1006,35 @@ int NetPrivate::fuse_graph(const Option&)
         }
     }
 
+    // ---- stem Convolution (<= 4 input channels, stride 2, none / ReLU) -> max Pooling 3x3 s2: one kernel, the full-resolution map
+    // never reaches HBM (include/ncnn_cuda.h ncnn_cuda_conv2d_forward_maxpool3x3s2; other geometries run the two layers in turn)
+    for (int i = 0; i < L; i++)
+    {
+        if (layer_custom_index[i] >= 0 || layers[i]->type != "Convolution") continue;
+        Convolution* c = (Convolution*)layers[i];
+        if (c->tops.size() != 1 || c->bottoms.size() != 1 || c->fused_residual || c->shortcut || c->fused_pool) continue;
+        if (c->activation_type != 0 && c->activation_type != 1) continue;
+        const int inch = c->weight_data_size / (c->num_output * c->kernel_w * c->kernel_h);
+        if (inch > 4 || c->stride_w != 2 || c->stride_h != 2 || c->num_output > 64 || c->kernel_w * c->kernel_h < 2) continue;
+        int top = c->tops[0];
+        int j = sole_consumer(top);
+        if (j <= i || layer_custom_index[j] >= 0 || layers[j]->type != "Pooling") continue;
+        Pooling* pl = (Pooling*)layers[j];
+        if (pl->pooling_type != 0 || pl->global_pooling || pl->adaptive_pooling || pl->kernel_w != 3 || pl->kernel_h != 3 || pl->stride_w != 2 || pl->stride_h != 2)
+            continue;
+        if (pl->bottoms.size() != 1 || pl->tops.size() != 1) continue;
+        int newtop = pl->tops[0];
+        c->fused_pool = pl;
+        c->tops[0] = newtop;
+        blobs[newtop].producer = i;
+        blobs[top].producer = -1;
+        blobs[top].consumer = -1;
+        blobs[top].folded_into = i;
+        pl->bottoms.clear();
+        pl->tops.clear();
+        retire(j, true);
+    }
+
     // ---- Convolution -> Eltwise(SUM) [-> ReLU]
     for (int j = 0; j < L; j++)
     {

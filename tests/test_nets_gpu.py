@@ -871,3 +871,37 @@ def test_projection_shortcut_fold(ref, case, mode):
     finally:
         net.close()
         L.lib.ncnn_option_destroy(opt)
+
+
+STEM_POOL_GRID = [
+    # (input size, batch, outch, conv kernel, conv pad, conv act (9=), pooling params)
+    (224, 2, 64, 7, 3, 1, "1=3 2=2"),            # ResNet-50 conv1 + pool1 (ceil tail: the last window hangs over the map)
+    (227, 2, 64, 3, 0, 1, "1=3 2=2"),            # SqueezeNet v1.1 conv1 + pool1
+    (96, 40, 64, 7, 3, 1, "1=3 2=2"),            # many (image, band) items: several per CTA, carry rows across bands
+    (75, 3, 24, 5, 2, 0, "1=3 2=2 3=1 5=1"),     # odd map, explicit pooling pad 1 (valid mode), no activation, 24 channels
+    (64, 5, 48, 3, 1, 1, "1=3 2=2 5=1"),         # valid mode without padding: the tail row / column is dropped
+    (130, 2, 64, 7, 3, 1, "1=3 2=2 3=1 13=0"),   # pad on the left only
+    (258, 2, 64, 3, 0, 1, "1=3 2=2"),            # conv row wider than one 128-column tile: not fused, the two layers run in turn
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("case", STEM_POOL_GRID)
+def test_stem_conv_maxpool_fold(ref, case, mode):
+    """load-time fold of a stride-2 small-channel stem Convolution (+ReLU) and the max Pooling 3x3 s2 behind it into ONE kernel
+    (include/ncnn_cuda.h ncnn_cuda_conv2d_forward_maxpool3x3s2).  Reference: src/layer/convolution.cpp:113-184 then
+    src/layer/pooling.cpp:188-253 (make_padding :350-412 for the tail).  Rounding to the storage type is monotonic and ReLU
+    commutes with max, so the folded graph must equal the unfolded one BIT FOR BIT; both are held to the reference."""
+    size, n, outch, k, pad, act, pool = case
+    text = ("7767517\n3 3\nInput data 0 1 data 0=%d 1=%d 2=3\n"
+            "Convolution conv1 1 1 data conv1 0=%d 1=%d 3=2 4=%d 5=1 6=%d 9=%d\n"
+            "Pooling output 1 1 conv1 output 0=0 %s\n") % (size, size, outch, k, pad, 3 * outch * k * k, act, pool)
+    weights = modelzoo.random_model_bytes(text, seed=21)
+    x = np.random.default_rng(9).uniform(-1, 1, (n, 3, size, size)).astype(np.float32)
+    got = run_ours(text, weights, {"data": x}, mode, batched=True, fusion=1)["output"]
+    plain = run_ours(text, weights, {"data": x}, mode, batched=True, fusion=0)["output"]
+    want = run_ref(ref, text, weights, {"data": x}, batched=True)["output"]
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.array_equal(got, plain), (case, mode, nerr(got, plain))
+    tol = {"fp32": 1e-5, "fp16": 2e-3, "bf16": 1e-2}[mode]
+    assert nerr(got, want) <= tol, (case, mode, nerr(got, want))
