@@ -121,10 +121,73 @@ __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* 
     }
 }
 
+// The window IS the map (global pooling, or ResNet's 7x7 average over a 7x7 map): one output pixel per image.  pool_kernel walks
+// the P taps serially in one thread per channel vector -- 64 K threads with 49 dependent steps each for ResNet-50 pool5 (38 us for
+// 51 MB).  Here a CTA owns (image, 256-channel chunk): 32 channel vectors x 8 pixel groups, every thread sums its strided share of
+// the pixels with all loads in flight, the eight partial sums meet in shared memory.
+template<typename T, int VEC>
+__global__ void __launch_bounds__(256) pool_whole_map_kernel(const T* __restrict__ in, T* __restrict__ out, int P, int C, int in_cpitch, int out_cpitch, long long in_nstep,
+                                                             long long out_nstep, int chunks, int type, float divisor)
+{
+    NC_PDL_PROLOGUE();
+    __shared__ float part[8][32][VEC + 1];
+    const int b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - b * chunks;
+    const int cv = threadIdx.x & 31, pg = threadIdx.x >> 5;
+    const int c0 = (chunk * 32 + cv) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = type == 0 ? -FLT_MAX : 0.f;
+    if (c0 < C)
+    {
+        const T* src = in + (long long)b * in_nstep + c0;
+#pragma unroll 4
+        for (int p = pg; p < P; p += 8)
+        {
+            float xv[VEC];
+            load_vec_f32<T, VEC>(src + (long long)p * in_cpitch, xv);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = type == 0 ? fmaxf(acc[v], xv[v]) : acc[v] + xv[v];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; v++) part[pg][cv][v] = acc[v];
+    __syncthreads();
+    if (pg == 0 && c0 < C)
+    {
+#pragma unroll
+        for (int k = 1; k < 8; k++)
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = type == 0 ? fmaxf(acc[v], part[k][cv][v]) : acc[v] + part[k][cv][v];
+        if (type == 1)
+        {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = acc[v] / divisor;
+        }
+        store_vec_f32<T, VEC>(out + (long long)b * out_nstep + c0, acc);
+    }
+}
+
 template<typename T>
 static int run_pool(const ncnn_cuda_tensor* bottom, const ncnn_cuda_tensor* top, const PoolGeom& g, cudaStream_t stream)
 {
     constexpr int VEC = 16 / sizeof(T);
+    {
+        const int cround0 = ((g.C + VEC - 1) / VEC) * VEC;
+        const bool aligned = (g.in_cpitch % VEC == 0) && (g.out_cpitch % VEC == 0) && (g.in_nstep % VEC == 0) && (g.out_nstep % VEC == 0) &&
+                             (((uintptr_t)bottom->data & 15) == 0) && (((uintptr_t)top->data & 15) == 0) && cround0 <= g.in_cpitch && cround0 <= g.out_cpitch;
+        // the window covers exactly the map: global pooling, or an unpadded kernel of the map's size with every tap counted
+        const bool whole = g.global || (!g.adaptive && g.outw == 1 && g.outh == 1 && g.kw == g.inw && g.kh == g.inh && g.pad_left == 0 && g.pad_top == 0 && g.ax0 <= 0 &&
+                                        g.ay0 <= 0 && g.ax1 >= g.inw && g.ay1 >= g.inh);
+        if (aligned && whole && g.inw * g.inh >= 16 && g.n > 0)
+        {
+            const int chunks = (cround0 / VEC + 31) / 32;
+            NC_PDL_LAUNCH((pool_whole_map_kernel<T, VEC>), g.n * chunks, 256, 0, stream, (const T*)bottom->data, (T*)top->data, g.inw * g.inh, g.C, g.in_cpitch, g.out_cpitch,
+                          g.in_nstep, g.out_nstep, chunks, g.type, (float)(g.inw * g.inh));
+            NC_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (g.type == 0 && !g.global && !g.adaptive && g.kw == g.kh && g.sw == g.sh && g.n > 0)
     {
         // the bandwidth path: TMA-staged tiles with NaN out-of-bounds fill (pool_tma.cuh); what it declines runs below

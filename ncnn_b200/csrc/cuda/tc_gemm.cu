@@ -219,6 +219,9 @@ int tc_plan_create(TcPlan* plan, int elemtype, int inch, int outch, int kernel_w
     if (plan->block_k == 64 && plan->block_n >= 128 &&
             encode_weights(&plan->tmap_b_half, elemtype, plan->w_packed, plan->Kp, outch, plan->block_k, plan->block_n / 2) == 0)
         plan->pair_ok = 1;
+    // 64-wide tiles for calls with few output pixels (InnerProduct on a batch of a few hundred rows): more CTAs share the weight stream
+    plan->narrow_ok = 0;
+    if (plan->block_k == 64 && plan->block_n > 64 && encode_weights(&plan->tmap_b_64, elemtype, plan->w_packed, plan->Kp, outch, plan->block_k, 64) == 0) plan->narrow_ok = 1;
     if (plan->rows_ok && encode_weights(&plan->tmap_b_rows, elemtype, plan->w_rows, plan->rows_Kp, outch, plan->rows_block_k, plan->block_n) != 0)
     {
         cudaFree(plan->w_rows);
@@ -596,13 +599,28 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     CUtensorMap ta, tr;
     const long long M = (long long)c->n * c->outh * c->outw;
     if (M == 0) return 0;
-    const int epi_n = plan->block_n < 64 ? plan->block_n : 64;
+    // few output pixels and wide tiles leave most SMs idle (ResNet-50 fc1000 on 256 rows: 8 tiles of 128 x 256 for 148 SMs, each
+    // streaming 1/4 of the weights): 64-wide tiles give four times the CTAs for the same bytes
+    int plan_block_n = plan->block_n;
+    const CUtensorMap* tb_plain = &plan->tmap_b;
+    bool allow_pair = true;
+    if (plan->narrow_ok && c->tiled && !c->residual && plan->dual_k1_blocks == 0)
+    {
+        const long long wide_tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((plan->outch + plan->block_n - 1) / plan->block_n);
+        if (wide_tiles * 2 <= sm_count())
+        {
+            plan_block_n = 64;
+            tb_plain = &plan->tmap_b_64;
+            allow_pair = false;
+        }
+    }
+    const int epi_n = plan_block_n < 64 ? plan_block_n : 64;
 
     RowsGeom rg;
     const bool use_rows = rows_applicable(plan, c, &rg) && c->workspace && c->workspace_size >= rg.bytes;
     int amode = c->tiled ? tc::A_TILED : tc::A_IM2COL;
     int block_k = plan->block_k;
-    const CUtensorMap* tb = &plan->tmap_b;
+    const CUtensorMap* tb = tb_plain;
 
     tc::Params p;
     memset(&p, 0, sizeof(p));
@@ -792,7 +810,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     p.act_p1 = c->act_p1;
     p.v8_ok = (c->out_cpitch % 16 == 0) && (((uintptr_t)c->out & 31) == 0);
     p.taps_h = c->tiled ? 1 : c->kernel_h;
-    p.div_n_blocks = make_fastdiv((unsigned int)((plan->outch + plan->block_n - 1) / plan->block_n));
+    p.div_n_blocks = make_fastdiv((unsigned int)((plan->outch + plan_block_n - 1) / plan_block_n));
     p.div_opix = make_fastdiv((unsigned int)(c->outw * c->outh > 0 ? c->outw * c->outh : 1));
     p.div_outw = make_fastdiv((unsigned int)(c->outw > 0 ? c->outw : 1));
     p.div_chunks = make_fastdiv((unsigned int)p.chunks_per_row);
@@ -806,7 +824,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
         const char* e = getenv("NCNN_B200_TC_PAIR");
         pair_mode = e ? atoi(e) : 1;
     }
-    const bool use_pair = pair_mode != 0 && plan->pair_ok && (amode == tc::A_TILED || amode == tc::A_IM2COL) && block_k == 64 && M > tc::BLOCK_M;
+    const bool use_pair = allow_pair && pair_mode != 0 && plan->pair_ok && (amode == tc::A_TILED || amode == tc::A_IM2COL) && block_k == 64 && M > tc::BLOCK_M;
     if (use_pair)
     {
         const long long pair_tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M + 1) / 2 * ((plan->outch + plan->block_n - 1) / plan->block_n);
@@ -819,13 +837,13 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row
                                : (amode == tc::A_SHIFT ? (long long)c->n * p.sh_tiles_y * p.sh_chunks_x : (M + tc::BLOCK_M - 1) / tc::BLOCK_M);
-    const long long tiles = m_blocks * ((plan->outch + plan->block_n - 1) / plan->block_n);
+    const long long tiles = m_blocks * ((plan->outch + plan_block_n - 1) / plan_block_n);
 
 #define NC_MODE(T)                                                                                                            \
-    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
-    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
-    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream); \
-    return dispatch_tc<T, tc::A_ROWS>(plan->block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream)
+    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
+    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
+    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream); \
+    return dispatch_tc<T, tc::A_ROWS>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream)
     if (plan->elemtype == NCNN_CUDA_BF16)
     {
         NC_MODE(__nv_bfloat16);

@@ -1593,6 +1593,8 @@ struct TcPlan
     CUtensorMap tmap_b;
     CUtensorMap tmap_b_half; // box of block_n / 2 rows: what one CTA of a cta_group::2 pair stages (valid when pair_ok)
     int pair_ok;
+    CUtensorMap tmap_b_64; // box of 64 rows: narrow tiles for calls with few output pixels (valid when narrow_ok)
+    int narrow_ok;
     // A_ROWS variant (small-channel stems), valid when rows_ok
     int rows_ok;
     int rows_cp, rows_wp, rows_shift; // channels per pixel of the padded copy, window width in pixels, zero taps on the left
