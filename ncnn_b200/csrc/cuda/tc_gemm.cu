@@ -476,8 +476,7 @@ static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid
 }
 
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, const CUtensorMap& ta2, tc::Params& p, long long tiles,
-                     cudaStream_t stream)
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p, long long tiles, cudaStream_t stream)
 {
     using Plan = tc::SmemPlan<BLOCK_N, BLOCK_K, CG>;
     static_assert(Plan::stages_for(true) >= 2, "not enough shared memory for a 2-stage pipeline");
@@ -532,13 +531,13 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     {
         // `tiles` counts pair tiles: one cluster of two CTAs (the two SMs of a TPC) per tile, persistent
         const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
-        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, to, ta2, p));
+        NC_CHECK(launch_pdl_cluster(kern, dim3(2 * clusters), dim3(tc::kNumThreads), (size_t)smem_bytes, 2, stream, ta, tb, tr, to, p));
         NC_LAUNCH_CHECK();
         count_tc_launch();
         return 0;
     }
     int grid = (int)(tiles < sms ? tiles : sms);
-    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, to, ta2, p));
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, ta, tb, tr, to, p));
     NC_LAUNCH_CHECK();
     count_tc_launch();
     return 0;
@@ -546,21 +545,21 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 
 // the CTA-pair instances: 64-element k-blocks, 128 / 256-wide tiles, tiled and im2col operands
 template<typename T, int AMODE>
-static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, const CUtensorMap& ta2, tc::Params& p,
-                            long long tiles, cudaStream_t stream)
+static int dispatch_tc_pair(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p, long long tiles,
+                            cudaStream_t stream)
 {
-    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, to, ta2, p, tiles, stream);
-    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, to, ta2, p, tiles, stream);
+    if (block_n == 256) return launch_tc<T, 256, 64, AMODE, 2>(ta, tb, tr, to, p, tiles, stream);
+    if (block_n == 128) return launch_tc<T, 128, 64, AMODE, 2>(ta, tb, tr, to, p, tiles, stream);
     set_last_error_msg("tc_gemm: no CTA-pair kernel instance for this tile shape");
     return -1;
 }
 
 template<typename T, int AMODE>
-static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, const CUtensorMap& ta2,
-                       tc::Params& p, long long tiles, cudaStream_t stream)
+static int dispatch_tc(int block_n, int block_k, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to, tc::Params& p,
+                       long long tiles, cudaStream_t stream)
 {
 #define NC_TC(BN, BK) \
-    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, to, ta2, p, tiles, stream)
+    if (block_n == BN && block_k == BK) return launch_tc<T, BN, BK, AMODE>(ta, tb, tr, to, p, tiles, stream)
     NC_TC(256, 64);
     NC_TC(128, 64);
     NC_TC(64, 64);
@@ -709,6 +708,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
             if (bytes < 131072) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
         }
     }
+    // (the second operand's map travels in the residual slot of the kernel's parameters: a dual plan never has a fused residual)
     CUtensorMap ta2 = ta;
     if (plan->dual_k1_blocks > 0)
     {
@@ -767,7 +767,7 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
         }
     }
     else
-        tr = ta;
+        tr = plan->dual_k1_blocks > 0 ? ta2 : ta;
     // output map of the TMA-store epilogue: per-warp boxes of 32 rows x epi_n channels; the channel extent is the blob's padded
     // run (padding lanes up to the next 16-byte unit may be written, as by the per-lane stores)
     CUtensorMap to;
@@ -829,10 +829,10 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     {
         const long long pair_tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M + 1) / 2 * ((plan->outch + plan->block_n - 1) / plan->block_n);
         if (plan->elemtype == NCNN_CUDA_BF16)
-            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream)
-                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream);
-        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream)
-                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, ta2, p, pair_tiles, stream);
+            return amode == tc::A_TILED ? dispatch_tc_pair<__nv_bfloat16, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream)
+                                        : dispatch_tc_pair<__nv_bfloat16, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream);
+        return amode == tc::A_TILED ? dispatch_tc_pair<__half, tc::A_TILED>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream)
+                                    : dispatch_tc_pair<__half, tc::A_IM2COL>(plan->block_n, ta, plan->tmap_b_half, tr, to, p, pair_tiles, stream);
     }
 
     const long long m_blocks = amode == tc::A_ROWS ? rows * p.chunks_per_row
@@ -840,10 +840,10 @@ int tc_conv_forward(const TcPlan* plan, const TcConvCall* c, cudaStream_t stream
     const long long tiles = m_blocks * ((plan->outch + plan_block_n - 1) / plan_block_n);
 
 #define NC_MODE(T)                                                                                                            \
-    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
-    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream);  \
-    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream); \
-    return dispatch_tc<T, tc::A_ROWS>(plan_block_n, block_k, ta, *tb, tr, to, ta2, p, tiles, stream)
+    if (amode == tc::A_SHIFT) return dispatch_tc<T, tc::A_SHIFT>(plan_block_n, block_k, ta, *tb, tr, to, p, tiles, stream);  \
+    if (amode == tc::A_TILED) return dispatch_tc<T, tc::A_TILED>(plan_block_n, block_k, ta, *tb, tr, to, p, tiles, stream);  \
+    if (amode == tc::A_IM2COL) return dispatch_tc<T, tc::A_IM2COL>(plan_block_n, block_k, ta, *tb, tr, to, p, tiles, stream); \
+    return dispatch_tc<T, tc::A_ROWS>(plan_block_n, block_k, ta, *tb, tr, to, p, tiles, stream)
     if (plan->elemtype == NCNN_CUDA_BF16)
     {
         NC_MODE(__nv_bfloat16);

@@ -90,7 +90,8 @@ struct Params
     int sh_stage_bytes, sh_box_bytes;
     FastDiv div_sh_chunks_x, div_sh_tiles_y, div_sh_bw;
     // A_TILED with a SECOND A operand (a folded projection shortcut: top = act(W1 * x1 + W2 * x2 + b)): the last nk2 k-blocks of
-    // the packed weight matrix multiply 64-channel slabs of tmap_a2 -- a plain [M][C2] matrix (a2_im2col = 0) or a 1x1 strided
+    // the packed weight matrix multiply 64-channel slabs of a second operand map (passed in the tmap_res slot: a dual plan has no
+    // fused residual, and a fifth 128-byte descriptor in the kernel's parameter block costs every instance 7-30 %, measured) -- a plain [M][C2] matrix (a2_im2col = 0) or a 1x1 strided
     // window walk over an NHWC blob through TMA im2col mode (a2_im2col = 1) -- over the SAME 128 output pixels
     int nk2, a2_im2col, a2_stride_w, a2_stride_h;
     // tile decode without integer division
@@ -699,7 +700,7 @@ static __device__ __noinline__ float apply_activation_call(float v, int type, fl
 template<typename T, int BLOCK_N, int BLOCK_K, int AMODE, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_res,
-               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_a2, const Params p)
+               const __grid_constant__ CUtensorMap tmap_out, const Params p)
 {
     static_assert(CG == 1 || AMODE == A_TILED || AMODE == A_IM2COL, "CTA pairs: tiled and im2col operand modes only");
     using Plan = SmemPlan<BLOCK_N, BLOCK_K, CG>;
@@ -763,9 +764,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
-        if (has_res) prefetch_tmap(&tmap_res);
+        if (has_res || (AMODE == A_TILED && p.nk2 > 0)) prefetch_tmap(&tmap_res);
         if (p.tma_store) prefetch_tmap(&tmap_out);
-        if (AMODE == A_TILED && p.nk2 > 0) prefetch_tmap(&tmap_a2);
     }
     if (warp == 1 && lane == 0)
     {
@@ -982,17 +982,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             if (CG == 2)
                             {
                                 if (p.a2_im2col)
-                                    tma_load_im2col_4d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_a2, full0_leader + stage * 8, kc2, w2, h2, n2, (uint16_t)0, (uint16_t)0);
+                                    tma_load_im2col_4d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_res, full0_leader + stage * 8, kc2, w2, h2, n2, (uint16_t)0, (uint16_t)0);
                                 else
-                                    tma_load_2d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_a2, full0_leader + stage * 8, kc2, m0);
+                                    tma_load_2d_cg2(smem_a0 + stage * Plan::a_bytes, &tmap_res, full0_leader + stage * 8, kc2, m0);
                                 tma_load_2d_cg2(smem_b0 + stage * Plan::b_bytes, &tmap_b, full0_leader + stage * 8, kcoord, n_coord);
                             }
                             else
                             {
                                 if (p.a2_im2col)
-                                    tma_load_im2col_4d(smem_a0 + stage * Plan::a_bytes, &tmap_a2, fb, kc2, w2, h2, n2, (uint16_t)0, (uint16_t)0);
+                                    tma_load_im2col_4d(smem_a0 + stage * Plan::a_bytes, &tmap_res, fb, kc2, w2, h2, n2, (uint16_t)0, (uint16_t)0);
                                 else
-                                    tma_load_2d(smem_a0 + stage * Plan::a_bytes, &tmap_a2, fb, kc2, m0);
+                                    tma_load_2d(smem_a0 + stage * Plan::a_bytes, &tmap_res, fb, kc2, m0);
                                 tma_load_2d(smem_b0 + stage * Plan::b_bytes, &tmap_b, fb, kcoord, n_coord);
                             }
                         }

@@ -108,6 +108,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--rotate", type=int, default=0, help="number of rotating buffer sets (default: enough to exceed the L2; 1 = the same L2-resident buffers every launch)")
     ap.add_argument("--json", default="")
     args = ap.parse_args()
     import torch
@@ -139,6 +140,8 @@ def main():
         out_bytes = n * outh * outw * ocp * 2
         per = in_bytes + out_bytes * (2 if res else 1)
         R = max(2, min(8, int(300e6 // per) + 1))
+        if args.rotate > 0:
+            R = args.rotate
         wt = (torch.rand((outch, inch, k, k), generator=g, device="cuda") * 2 - 1) * float(np.sqrt(3.0 / (inch * k * k)))
         wt = wt.to(dt).float()
         bias = torch.rand((outch,), generator=g, device="cuda") * 2 - 1
