@@ -207,6 +207,25 @@ def layer_shares(sess, text, dev_in, storage, repeats):
     return rows, acc
 
 
+def algorithmic_conv_flop(text, weights, storage, device, size, batch):
+    """2 x MACs of every Convolution of the graph AS WRITTEN (load-time fusion off, one image, scaled by the batch): the roofline's
+    numerator must not shrink when a projection shortcut is folded into its neighbour or a stem swallows its pooling layer -- the
+    folded layers' arithmetic is still executed"""
+    from ncnn_b200 import runner
+    s = runner.Session(text, weights, storage=storage, device=device, fusion=False)
+    try:
+        h = s.pinned_input(np.zeros((1, 3, size, size), np.float32))
+        d = s.upload(h)
+        prof = s.profile(d, repeats=1)
+        work = runner.layer_work(text, prof)
+        flop = sum(2.0 * work[li]["macs"] for li, t, name, lms, shape in prof if t == "Convolution" and li in work)
+        s.L.lib.ncnn_cuda_mat_destroy(d)
+        s.L.lib.ncnn_mat_destroy(h)
+    finally:
+        s.close()
+    return flop * batch
+
+
 def timed_steps(sess, lib, dev_in, steps, barrier=None):
     """`steps` forward walks with the input resident in HBM, CUDA events on the recorder's own stream -> ms"""
     e0, e1 = sess.event(), sess.event()
@@ -455,6 +474,11 @@ def main():
     # family's SHARE of that sum is applied to the un-profiled ms_per_step.
     peaks = load_peaks()
     rows, acc = layer_shares(sess, text, dev_in, args.storage, repeats=max(3, min(args.steps, 10)))
+    if sess.fused_layers and acc["conv_flop"] > 0:
+        try:
+            acc["conv_flop"] = algorithmic_conv_flop(text, weights, args.storage, local_rank, size, batch)
+        except Exception as e:
+            sys.stderr.write("algorithmic FLOP count from the unfused graph failed (%s): the fused layers' own count is used\n" % e)
     if args.layers and rank == 0:
         for r in rows:
             sys.stderr.write("%-28s %-22s %8.4f ms %s\n" % (r["layer"][:28], r["type"], r["ms"],

@@ -21,7 +21,7 @@ CXX = os.environ.get("NCNN_B200_CXX", "/usr/bin/g++" if os.path.exists("/usr/bin
 
 INCLUDES = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc", "host"), "-I" + os.path.join(HERE, "csrc", "cuda")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--ftz=true", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-              "-ccbin", CXX, "--expt-relaxed-constexpr", "-split-compile", "0", "-Xcudafe", "--diag_suppress=177"]
+              "-ccbin", CXX, "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function", "-pthread", "-I/usr/local/cuda/include"]
 
 
