@@ -1,4 +1,2 @@
 #!/bin/bash
-python bench.py --workload yolov8s --no-extra-legs --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench yolo', d['ms_per_step'])"
-python bench.py --no-extra-legs --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench resnet', d['ms_per_step'])"
-python bench.py --workload mobilenet_v2 --no-extra-legs --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench mbv2', d['ms_per_step'])"
+python bench.py --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "^conv1\|res2a_branch2c\|res2b\|res3b\|res4b\|res5b\|pool5\|fc1000\|layers total"
