@@ -1,2 +1,3 @@
 #!/bin/bash
-python bench.py --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "^conv1\|res2a_branch2c\|res2b\|res3b\|res4b\|res5b\|pool5\|fc1000\|layers total"
+timeout 900 python -m pytest tests/test_nets_gpu.py tests/test_kernels_gpu.py -x -q --timeout 600 --tb=short -k "model_parity or squeezenet_golden or mat_batch or stem_conv or preprocessing" 2>&1 | tail -3
+python tools/e2e_probe.py
