@@ -1,3 +1,3 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_nets_gpu.py tests/test_kernels_gpu.py -x -q --timeout 600 --tb=short -k "model_parity or squeezenet_golden or mat_batch or stem_conv or preprocessing" 2>&1 | tail -3
-python tools/e2e_probe.py
+timeout 600 python -m pytest tests/test_nets_gpu.py -x -q --timeout 600 --tb=short -k "stem_conv" 2>&1 | tail -3
+for i in 1 2; do python bench.py --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "^conv1\|layers total"; done
