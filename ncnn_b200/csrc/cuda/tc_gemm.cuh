@@ -777,7 +777,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < kAccStages; i++)
         {
             mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[i]), kEpilogueWarps * CG); // the leader's barrier counts the epilogue warps of both CTAs
+            // the leader's barrier counts the epilogue warps of both CTAs; 32-wide tiles are read by ONE half (see the epilogue)
+            mbar_init(smem_u32(&tmem_empty_bar[i]), (BLOCK_N == 32 ? kEpilogueWarps / 2 : kEpilogueWarps) * CG);
         }
         mbar_init(smem_u32(bres_bar), 1);
         for (int i = 0; i < kResSlots; i++)
@@ -1275,8 +1276,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_arrive(tmem_empty_leader + a * 8);
         };
 
+        // A 32-wide tile is a single 32-column group: with the usual split one half of the warps would have nothing to read on
+        // every tile, and layers with <= 32 output channels (stems, MobileNetV2 linear bottlenecks, YOLOv8 C2f halves) are bound by
+        // exactly this walk.  The halves take ALTERNATE tiles instead: each accumulator stage is read -- and handed back -- by the
+        // four warps of its owner only (tmem_empty counts four arrivals), the other half skips the tile without touching a barrier.
+        constexpr bool kAltTiles = BLOCK_N == 32;
+        int tile_seq = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step)
         {
+            if (kAltTiles && ((tile_seq++ & 1) != half))
+            {
+                slots_seen += 1u; // (one residual slot per tile at this width)
+                if (++acc == kAccStages)
+                {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             const int m_grp = fast_div(tile, p.div_n_blocks);
             const int n_blk = tile - m_grp * num_n_blocks;
             const int m_blk = CG == 2 ? 2 * m_grp + (int)cta_rank : m_grp;
@@ -1343,8 +1360,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int g_begin, g_last; // first / last owned group (g_last < g_begin: none)
             if (NCHUNK == 1)
             {
-                g_begin = g_last = half;
-                if (half >= ngroups) g_last = -1;
+                g_begin = g_last = kAltTiles ? 0 : half;
+                if (g_begin >= ngroups) g_last = -1;
             }
             else
             {

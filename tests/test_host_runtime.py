@@ -98,13 +98,13 @@ def test_load_param_matches_reference(ours, ref, name):
 def _extra_graphs():
     import glob
     import os
-    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "benchmark_graphs")
     return sorted(glob.glob(os.path.join(d, "*.param")))
 
 
 @pytest.mark.parametrize("path", _extra_graphs(), ids=lambda p: p.split("/")[-1][:-6])
 def test_load_param_benchmark_set_matches_reference(ours, ref, path):
-    """every fp32 graph of the reference's benchmark set kept under models/extra/ parses in the product runtime to the same input /
+    """every fp32 graph of the reference's benchmark set kept under tests/golden/benchmark_graphs/ parses in the product runtime to the same input /
     output blob names as in the reference; graphs that end in host-side detection post-processing are refused by the product
     (no creator for PriorBox / DetectionOutput / Yolo*DetectionOutput: a graph never falls back to the CPU silently)"""
     text = open(path).read()

@@ -380,7 +380,7 @@ def test_multiheadattention_graph(ref, mode):
         assert nerr(got[o], want[o]) <= TOL[mode], (o, nerr(got[o], want[o]))
 
 
-EXTRA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "models", "extra")
+EXTRA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "benchmark_graphs")
 EXTRA_MODELS = ["mobilenet", "mobilenet_v3", "shufflenet", "shufflenet_v2", "mnasnet", "proxylessnasnet", "efficientnet_b0", "regnety_400m", "resnet18",
                 "squeezenet", "blazeface", "FastestDet", "alexnet", "googlenet", "nanodet_m", "yolo-fastestv2", "efficientnetv2_b0", "vision_transformer"]
 EXTRA_INPUT = {"vision_transformer": 384, "blazeface": 128, "FastestDet": 352, "squeezenet": 227, "alexnet": 227, "nanodet_m": 320, "yolo-fastestv2": 352}
@@ -393,7 +393,7 @@ EXTRA_TOL16 = {"FastestDet": 4e-3, "yolo-fastestv2": 4e-3, "nanodet_m": 1e-2}  #
 @pytest.mark.parametrize("mode", ["fp32", "fp16"])
 def test_reference_benchmark_graphs(ref, name, mode):
     """widening: the other graphs of the reference's benchmark set whose operators this backend has
-    (benchmark/models/*.param, committed as model descriptions under models/extra/), with seeded random weights, against
+    (benchmark/models/*.param, committed as model descriptions under tests/golden/benchmark_graphs/), with seeded random weights, against
     the reference CPU path through the same Net API: depthwise/grouped convolutions, squeeze-excite blocks (global pooling
     + broadcasting BinaryOp), HardSwish/HardSigmoid, ShuffleChannel + Slice, multi-output detection heads"""
     text = open(os.path.join(EXTRA, name + ".param")).read()
