@@ -78,9 +78,15 @@ constexpr int kStemN = 64;
 constexpr int kStemAccStages = 8;               // 8 x 64 = all 512 TMEM columns
 constexpr int kStemRowSlotBytes = 128 * 128;    // 128 conv columns x 64 channels x 2 bytes
 constexpr int kStemRowSlots = 2;
+// warp 0 producer, warp 1 MMA issuer of the even conv rows, warps 2..9 epilogue, warp 10 MMA issuer of the odd conv rows.  One
+// issuing warp spends ~750 cycles per tile on barrier waits, fences and descriptor bookkeeping, and the tensor pipe only queues a
+// few MMAs: the 14 MMAs of a conv row (~640 cycles) and that overhead ran back to back.  Two warps on alternate tiles overlap them.
+constexpr int kStemMma2Warp = kEpilogueWarp0 + kEpilogueWarps;
+constexpr int kStemMmaWarps = 3; // issuing warps: warp 1 and the warps behind the epilogue warps
+constexpr int kStemThreads = (kStemMma2Warp + kStemMmaWarps - 1) * 32;
 
 template<typename T, int BLOCK_K>
-__global__ void __launch_bounds__(kNumThreads, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_b, const StemPoolParams p)
+__global__ void __launch_bounds__(kStemThreads, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap tmap_b, const StemPoolParams p)
 {
     constexpr int b_bytes = kStemN * BLOCK_K * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -178,9 +184,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) stem_pool_kernel(const __grid_
             }
         }
     }
-    else if (warp == 1)
+    else if (warp == 1 || warp >= kStemMma2Warp)
     {
-        // ===================== MMA issuer: taps_h x (BLOCK_K / 16) MMAs per conv row, one commit =====================
+        // ===================== MMA issuers: taps_h x (BLOCK_K / 16) MMAs per conv row, one commit =====================
+        // both warps walk every tile (stage / accumulator counters stay in step); each issues the tiles of its parity
+        const int my_parity = warp == 1 ? 0 : warp - kStemMma2Warp + 1;
+        int tile_seq = 0;
         constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M, kStemN);
         int stage = 0;
         uint32_t phase = 0;
@@ -211,6 +220,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) stem_pool_kernel(const __grid_
             item_rows(item, img, py0, py1, r0, r1);
             for (int r = r0; r <= r1; r++)
             {
+                if ((tile_seq++ % kStemMmaWarps) == my_parity)
+                {
                 mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kStemN);
@@ -253,6 +264,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) stem_pool_kernel(const __grid_
                     }
                 }
                 __syncwarp();
+                }
+                else
+                    mbar_wait(full0 + stage * 8, phase); // observe the other issuers' stages in ring order (see tc_gemm.cuh)
                 a_lo0 += stage_step;
                 if (++stage == kStages)
                 {

@@ -889,7 +889,7 @@ static int launch_stem_pool(const CUtensorMap& tb, tc::StemPoolParams& p, cudaSt
     p.num_stages = stages;
     const int smem_bytes = stages * p.rows_stage_bytes + fixed;
     const int grid = p.num_items < sm_count() ? p.num_items : sm_count();
-    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kNumThreads), (size_t)smem_bytes, stream, tb, p));
+    NC_CHECK(launch_pdl(kern, dim3(grid), dim3(tc::kStemThreads), (size_t)smem_bytes, stream, tb, p));
     NC_LAUNCH_CHECK();
     count_tc_launch();
     return 0;

@@ -49,7 +49,12 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int kEpilogueWarp0 = 2;
 constexpr int kEpilogueWarps = 8; // two per TMEM lane quarter
-constexpr int kNumThreads = (kEpilogueWarp0 + kEpilogueWarps) * 32;
+// warp 0 TMA producer, warp 1 MMA issuer of the even tiles, warps 2..9 epilogue, warp 10 MMA issuer of the odd tiles.  An issuing
+// warp spends ~750 cycles per tile on barrier waits, fences, election and descriptor bookkeeping while the tensor pipe, which only
+// queues a few MMAs, drains: on tiles with little K (stems, 1x1 layers with <= 128 input channels, MobileNetV2) that overhead and
+// the tile's MMAs ran back to back.  Two issuers on alternate tiles overlap one's bookkeeping with the other's MMAs.
+constexpr int kMma2Warp = kEpilogueWarp0 + kEpilogueWarps;
+constexpr int kNumThreads = (kMma2Warp + 1) * 32;
 constexpr int kBiasSmemFloats = 4096; // layers up to this many (padded) output channels keep their bias in shared memory
 
 struct Params
@@ -1036,11 +1041,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     }
-    else if (warp == 1)
+    else if (warp == 1 || warp == kMma2Warp)
     {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuers =====================
         // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform registers); one elected
-        // lane issues tcgen05.mma / tcgen05.commit.
+        // lane issues tcgen05.mma / tcgen05.commit.  Both issuing warps walk EVERY tile so that their stage / accumulator counters
+        // stay in step; each issues the tiles of its parity (independent accumulator stages; a commit tracks the MMAs of its own
+        // thread).
         // pair: one 256 x BLOCK_N MMA per K step, issued by the leader only (the peer's MMA warp idles)
         constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M * CG, BLOCK_N);
         int stage = 0;
@@ -1051,8 +1058,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
         const uint64_t adesc0 = make_smem_desc<BLOCK_K>(smem_a0), bdesc0 = make_smem_desc<BLOCK_K>(smem_b0);
         if (AMODE == A_ROWS || AMODE == A_SHIFT) mbar_wait(smem_u32(bres_bar), 0);
+        const int my_parity = warp == 1 ? 0 : 1;
+        int tile_seq = 0;
+        const int stages_per_tile = AMODE == A_ROWS ? 1 : (AMODE == A_SHIFT ? p.cblocks : p.num_k_blocks);
+        // Two issuers only when consecutive tiles sit in DISJOINT ring stages (2 x stages per tile <= ring depth).  A parity wait
+        // tells "phase n complete" from "phase n - 1 complete" only for a waiter at most one phase ahead of its barrier: an issuer
+        // that skipped a tile which wraps the ring could be two uses ahead of a stage's barrier and would sail through the wait.
+        // Tiles with many k-blocks do not need the second issuer anyway (their MMAs outlast the bookkeeping): warp 1 takes them all.
+        const bool dual_issue = 2 * stages_per_tile <= kStages;
         for (int tile = tile_first; tile < (CG == 2 && cta_rank != 0 ? 0 : num_tiles); tile += tile_step)
         {
+            if (dual_issue ? ((tile_seq++ & 1) != my_parity) : (my_parity != 0))
+            {
+                // the other issuer's tile: step over its ring stages and its accumulator stage.  With two issuers the stages are
+                // OBSERVED on the way (a wait does not consume a phase): TMA loads land out of order, and an issuer that has not
+                // seen use n - 1 of a stage land could find its barrier still one phase back -- where the parity test for use n
+                // passes at once, on stale data (this deadlocked MobileNetV2's 144 -> 24 + residual layer at full batch).
+                if (dual_issue)
+                {
+                    for (int i = 0; i < stages_per_tile; i++)
+                    {
+                        mbar_wait(full0 + stage * 8, phase);
+                        if (++stage == kStages)
+                        {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                else
+                {
+                    stage += stages_per_tile;
+                    while (stage >= kStages)
+                    {
+                        stage -= kStages;
+                        phase ^= 1;
+                    }
+                }
+                if (++acc == kAccStages)
+                {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -1576,7 +1625,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     }
 
-    if (warp >= kEpilogueWarp0 && lane == 0 && p.tma_store) tma_store_wait<0>(); // bulk stores issued by this lane have completed
+    if (warp >= kEpilogueWarp0 && warp < kMma2Warp && lane == 0 && p.tma_store) tma_store_wait<0>(); // bulk stores issued by this lane have completed
     tc_fence_before();
     __syncwarp(); // (warp 0 / warp 1: the single working lane rejoins its warp before the aligned barrier)
     if (CG == 2)

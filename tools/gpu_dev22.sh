@@ -1,5 +1,5 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_nets_gpu.py -x -q --timeout 600 --tb=short -k "convolution or model_parity or stem" 2>&1 | tail -3
-python bench.py --workload mobilenet_v2 --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "^conv1\|block1/linear\|block3/linear\|layers total"
-python bench.py --workload yolov8s --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "^conv_1 \|^conv_2 \|layers total"
-python bench.py --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "layers total"
+timeout 600 python -m pytest tests -q -m gpu --timeout 300 --tb=short -x 2>&1 | tail -4
+for wl in resnet50 mobilenet_v2 yolov8s vgg16 squeezenet_v1_1; do
+  timeout 90 python bench.py --workload $wl --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "layers total" | sed "s/^/$wl /"
+done
