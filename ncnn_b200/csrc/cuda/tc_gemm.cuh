@@ -1333,7 +1333,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int tile_seq = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step)
         {
-            if (kAltTiles && ((tile_seq++ & 1) != half))
+            const int tseq = tile_seq++;
+            if (kAltTiles && ((tseq & 1) != half))
             {
                 slots_seen += 1u; // (one residual slot per tile at this width)
                 if (++acc == kAccStages)
@@ -1414,13 +1415,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             else
             {
+                // chunk parity selects the half, and the parity flips from tile to tile: a tile with an odd number of 32-column
+                // groups (96, 144, 160 ... output channels; the short last n-block of 320 or 576) would otherwise give the same
+                // half the extra group every time (MobileNetV2 16 -> 96: 2 groups against 1 on every tile)
                 const int nchunks = (ngroups + SUBS - 1) / SUBS;
-                g_begin = half * SUBS;
-                if (half >= nchunks)
+                const int hsel = half ^ (tseq & 1);
+                g_begin = hsel * SUBS;
+                if (hsel >= nchunks)
                     g_last = -1;
                 else
                 {
-                    const int last_cc = half + ((nchunks - 1 - half) & ~1);
+                    const int last_cc = hsel + ((nchunks - 1 - hsel) & ~1);
                     const int e = last_cc * SUBS + SUBS - 1;
                     g_last = e < ngroups ? e : ngroups - 1;
                 }
