@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pool_kernel(const __grid
         // ===================== MMA issuers: taps_h x (BLOCK_K / 16) MMAs per conv row, one commit =====================
         // both warps walk every tile (stage / accumulator counters stay in step); each issues the tiles of its parity
         const int my_parity = warp == 1 ? 0 : warp - kStemMma2Warp + 1;
+        // several issuers only when a ring stage is reused no sooner than kStemAccStages tiles later: then a tile's own accumulator
+        // wait guarantees that the stage's previous use has landed (see the dual-issue rule in tc_gemm.cuh); else warp 1 issues all
+        const bool multi_issue = kStages >= kStemAccStages;
         int tile_seq = 0;
         constexpr uint32_t idesc = make_idesc(Pack8<T>::ab_format, BLOCK_M, kStemN);
         int stage = 0;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pool_kernel(const __grid
             item_rows(item, img, py0, py1, r0, r1);
             for (int r = r0; r <= r1; r++)
             {
-                if ((tile_seq++ % kStemMmaWarps) == my_parity)
+                if (multi_issue ? ((tile_seq++ % kStemMmaWarps) == my_parity) : (my_parity == 0))
                 {
                 mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
                 tc_fence_after();
@@ -265,8 +268,6 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pool_kernel(const __grid
                 }
                 __syncwarp();
                 }
-                else
-                    mbar_wait(full0 + stage * 8, phase); // observe the other issuers' stages in ring order (see tc_gemm.cuh)
                 a_lo0 += stage_step;
                 if (++stage == kStages)
                 {

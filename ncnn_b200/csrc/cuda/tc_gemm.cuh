@@ -1061,39 +1061,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int my_parity = warp == 1 ? 0 : 1;
         int tile_seq = 0;
         const int stages_per_tile = AMODE == A_ROWS ? 1 : (AMODE == A_SHIFT ? p.cblocks : p.num_k_blocks);
-        // Two issuers only when consecutive tiles sit in DISJOINT ring stages (2 x stages per tile <= ring depth).  A parity wait
-        // tells "phase n complete" from "phase n - 1 complete" only for a waiter at most one phase ahead of its barrier: an issuer
-        // that skipped a tile which wraps the ring could be two uses ahead of a stage's barrier and would sail through the wait.
-        // Tiles with many k-blocks do not need the second issuer anyway (their MMAs outlast the bookkeeping): warp 1 takes them all.
-        const bool dual_issue = 2 * stages_per_tile <= kStages;
+        // Two issuers only when a ring stage is reused no sooner than kAccStages tiles later.  A parity wait separates "use n has
+        // landed" from "use n - 1 has landed" only for a waiter at most one phase ahead of its barrier, and TMA loads land out of
+        // order: an issuer that skips the other's tiles could otherwise reach the barrier of a stage whose previous use has not
+        // landed yet and sail through on stale data (this deadlocked MobileNetV2's 144 -> 24 + residual layer at full batch with the
+        // looser rule "consecutive tiles in disjoint stages").  With reuse distance >= kAccStages the tile's OWN accumulator wait
+        // is the guarantee: tmem_empty of tile t completes after the in-order epilogue has finished tile t - kAccStages, hence
+        // after every tile up to there -- including the stage's previous user -- was issued, i.e. had landed.  (No issuer waits on
+        // another issuer's stage: a late observer aliases the other way, onto a phase that can only complete after its own work.)
+        // Tiles with many k-blocks do not need a second issuer anyway (their MMAs outlast the bookkeeping): warp 1 takes them all.
+        // (32-wide tiles are read by alternate epilogue halves that do not wait for each other, so "in order" holds per parity only:
+        //  there the stage's previous user must be a tile of the SAME parity -- an even, exact reuse distance)
+        const bool dual_issue = kStages >= kAccStages * stages_per_tile && (BLOCK_N != 32 || kStages % (2 * stages_per_tile) == 0);
         for (int tile = tile_first; tile < (CG == 2 && cta_rank != 0 ? 0 : num_tiles); tile += tile_step)
         {
             if (dual_issue ? ((tile_seq++ & 1) != my_parity) : (my_parity != 0))
             {
-                // the other issuer's tile: step over its ring stages and its accumulator stage.  With two issuers the stages are
-                // OBSERVED on the way (a wait does not consume a phase): TMA loads land out of order, and an issuer that has not
-                // seen use n - 1 of a stage land could find its barrier still one phase back -- where the parity test for use n
-                // passes at once, on stale data (this deadlocked MobileNetV2's 144 -> 24 + residual layer at full batch).
-                if (dual_issue)
+                // the other issuer's tile: step over its ring stages and its accumulator stage
+                stage += stages_per_tile;
+                while (stage >= kStages)
                 {
-                    for (int i = 0; i < stages_per_tile; i++)
-                    {
-                        mbar_wait(full0 + stage * 8, phase);
-                        if (++stage == kStages)
-                        {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-                else
-                {
-                    stage += stages_per_tile;
-                    while (stage >= kStages)
-                    {
-                        stage -= kStages;
-                        phase ^= 1;
-                    }
+                    stage -= kStages;
+                    phase ^= 1;
                 }
                 if (++acc == kAccStages)
                 {

@@ -1,5 +1,7 @@
 #!/bin/bash
-timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_gemm_gpu.py tests/test_nets_gpu.py -q --timeout 300 --tb=short -x -k "convolution or gemm or innerproduct or model_parity or shortcut" 2>&1 | tail -3
-for wl in resnet50 mobilenet_v2 yolov8s vgg16; do
-  timeout 90 python bench.py --workload $wl --layers --no-extra-legs --no-cpu-baseline 2>&1 >/dev/null | grep "layers total" | sed "s/^/$wl /"
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests -q -m gpu --timeout 300 --tb=short -x 2>&1 | tail -3
+timeout 300 python bench.py --layers > gpurun_out/bench_resnet50.json 2> gpurun_out/bench_resnet50.layers; tail -c 300 gpurun_out/bench_resnet50.json; tail -2 gpurun_out/bench_resnet50.layers
+for wl in mobilenet_v2 yolov8s vgg16 squeezenet_v1_1; do
+  timeout 120 python bench.py --workload $wl --layers --no-cpu-baseline --no-extra-legs > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.layers; tail -1 gpurun_out/bench_$wl.layers
 done
