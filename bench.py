@@ -558,6 +558,16 @@ def main():
             line["roofline"]["depthwise"] = d
         except Exception as e:
             line["roofline"]["depthwise"] = {"error": str(e)[:120]}
+    # ---- launch-bound networks: one CUDA graph per walk.  On the batch-1 workload itself, and -- in the default invocation -- as a
+    # secondary leg on BASELINE.json configs[0] (SqueezeNet v1.1 227x227 batch 1)
+    if not args.no_extra_legs and rank == 0 and args.storage != "fp32":
+        try:
+            if batch == 1:
+                line["graph"] = graph_leg(sess, host_in, dev_in, batch, max(args.steps, 200))
+            elif args.workload == "resnet50":
+                line["launch_bound"] = launch_bound_leg(local_rank, args.storage)
+        except Exception as e:
+            line["graph" if batch == 1 else "launch_bound"] = {"error": str(e)[:160]}
     if rank == 0:
         sampler.stop()
 
@@ -600,6 +610,74 @@ def parity_check(sess, model, text, weights, x, storage):
         out["top1_identical"] = bool((np.argmax(ours, axis=1) == np.argmax(want, axis=1)).all())
     out["within_bound"] = bool(err <= out["bound"])
     return out
+
+
+def graph_leg(sess, host_in, dev_in, batch, steps):
+    """the same walk eager (one launch per kernel through the recorder) and as ONE cudaGraphLaunch per step (runner.Session.capture:
+    ncnn_cuda_graph_begin_capture / _end_capture around the ordinary recorder + Extractor calls), input resident in HBM, CUDA events
+    on the recorder's stream; and the whole reference-facing extract (pinned host Mat in -> pinned host Mat out, one stream sync per
+    step) eager vs as one graph, wall clock"""
+    lib = sess.L.lib
+    for _ in range(5):
+        lib.ncnn_cuda_mat_destroy(sess.enqueue_device(dev_in))
+    sess.sync()
+    eager_ms = timed_steps(sess, lib, dev_in, steps) / steps
+    g = sess.capture(dev_in=dev_in)
+    for _ in range(5):
+        g.replay()
+    sess.sync()
+    e0, e1 = sess.event(), sess.event()
+    sess.record(e0)
+    for _ in range(steps):
+        g.replay()
+    sess.record(e1)
+    graph_ms = sess.elapsed_ms(e0, e1) / steps
+    kernels = g.kernels
+    g.close()
+    # whole extract, strictly serial (what a batch-1 caller sees): eager Extractor vs one graph + one sync
+    for _ in range(3):
+        lib.ncnn_mat_destroy(sess.extract_host(host_in))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.ncnn_mat_destroy(sess.extract_host(host_in))
+    eager_e2e_ms = (time.perf_counter() - t0) * 1000.0 / steps
+    gh = sess.capture(host_mat=host_in)
+    for _ in range(3):
+        gh.replay()
+        sess.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gh.replay()
+        sess.sync()
+    graph_e2e_ms = (time.perf_counter() - t0) * 1000.0 / steps
+    gh.close()
+    return {"steps": steps, "kernels_per_walk": int(kernels), "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
+            "eager_images_per_s": batch * 1000.0 / eager_ms, "graph_images_per_s": batch * 1000.0 / graph_ms,
+            "e2e_eager_ms_per_step": eager_e2e_ms, "e2e_graph_ms_per_step": graph_e2e_ms,
+            "e2e_eager_images_per_s": batch * 1000.0 / eager_e2e_ms, "e2e_graph_images_per_s": batch * 1000.0 / graph_e2e_ms,
+            "how": "resident: CUDA events around `steps` walks on the recorder's stream; e2e: wall clock, pinned host Mat in -> pinned host Mat out, "
+                   "one stream sync per step, strictly serial"}
+
+
+def launch_bound_leg(local_rank, storage):
+    """BASELINE.json configs[0]: SqueezeNet v1.1 227x227 batch 1 (the reference's own CPU-runnable case), eager and graph replay"""
+    from ncnn_b200 import runner
+    model, batch, size = WORKLOADS["squeezenet_v1_1"]
+    text = with_input_size(modelzoo.param_text(model), size)
+    weights = modelzoo.random_model_bytes(text, seed=WEIGHT_SEED)
+    s3 = runner.Session(text, weights, storage=storage, device=local_rank)
+    del weights
+    try:
+        x = np.random.default_rng(13).uniform(-1, 1, (batch, 3, size, size)).astype(np.float32)
+        hin = s3.pinned_input(x)
+        din = s3.upload(hin)
+        d = graph_leg(s3, hin, din, batch, 300)
+        d["workload"] = "squeezenet_v1_1 %dx%d batch %d, %s storage" % (size, size, batch, storage)
+        s3.L.lib.ncnn_cuda_mat_destroy(din)
+        s3.L.lib.ncnn_mat_destroy(hin)
+        return d
+    finally:
+        s3.close()
 
 
 def depthwise_leg(local_rank, storage, group, max_over_ranks, steps, peaks):

@@ -235,7 +235,9 @@ int ncnn_cuda_event_elapsed_ms(void* start, void* stop, float* ms)
 
 int ncnn_cuda_graph_begin_capture(void* stream)
 {
-    NC_CHECK(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+    // relaxed mode: the recorder may still query pointer attributes, and the device pool may still fall back to cudaMalloc for a
+    // block the warm-up walk did not leave behind, without invalidating the capture (other threads' streams are unaffected)
+    NC_CHECK(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed));
     return 0;
 }
 

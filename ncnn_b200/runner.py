@@ -56,6 +56,10 @@ def _bind_extras(L):
     lib.ncnn_cuda_event_sync.argtypes = [vp]
     lib.ncnn_cuda_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     lib.ncnn_cuda_device_sync.argtypes = []
+    lib.ncnn_cuda_graph_begin_capture.argtypes = [vp]
+    lib.ncnn_cuda_graph_end_capture.argtypes = [vp, C.POINTER(vp)]
+    lib.ncnn_cuda_graph_launch.argtypes = [vp, vp]
+    lib.ncnn_cuda_graph_destroy.argtypes = [vp]
     lib._b200_extras_bound = True
 
 
@@ -215,6 +219,58 @@ class Session(object):
     def sync(self):
         return self.L.lib.ncnn_cuda_compute_submit_and_wait(self.cmd)
 
+    # ---------------------------------------------------------------- CUDA-graph replay of a recorded walk
+    def capture(self, host_mat=None, dev_in=None):
+        """Record ONE forward walk on the session's stream into a CUDA graph (ncnn_cuda_graph_begin_capture / _end_capture of
+        include/ncnn_cuda.h around the ordinary recorder + Extractor calls -- the analogue of re-submitting a recorded VkCompute
+        command buffer) and return a Graph whose replay() is a single cudaGraphLaunch.
+        host_mat: a PINNED host Mat -> the graph holds H2D copy + layout kernel + walk + layout kernel + D2H copy into a pinned
+                  output Mat of fixed address (Graph.host_out): the whole reference-facing extract, replayable after the caller
+                  has overwritten host_mat's bytes in place.
+        dev_in:   a device blob -> the graph holds the walk only (Graph.dev_out stays resident).
+        The walk is run once un-captured first: plans, weight packs and the device pool are built there, so the captured walk
+        allocates nothing new (the pool hands back the same blocks; they stay reserved for as long as the Session lives)."""
+        lib = self.L.lib
+        assert (host_mat is None) != (dev_in is None)
+        # warm-up: the same sequence of recorder calls on the same stream / device pool, un-captured
+        wd = self.upload(host_mat) if host_mat is not None else None
+        out = self.enqueue_device(dev_in if dev_in is not None else wd)
+        if host_mat is not None:
+            self.download(out)
+        self.sync()
+        lib.ncnn_cuda_mat_destroy(out)
+        if wd is not None:
+            lib.ncnn_cuda_mat_destroy(wd)
+        g = Graph(self)
+        n0 = self.launch_count()
+        if lib.ncnn_cuda_graph_begin_capture(self.stream) != 0:
+            raise RuntimeError("begin_capture failed: %s" % lib.ncnn_cuda_last_error().decode())
+        err = None
+        try:
+            if host_mat is not None:
+                dm = C.c_void_p()
+                if lib.ncnn_cuda_compute_record_upload(self.cmd, host_mat, C.byref(dm), self.opt) != 0:
+                    raise RuntimeError("record_upload failed under capture")
+                g.dev_in = dm
+                g.dev_out = self.enqueue_device(dm)
+                m = C.c_void_p()
+                if lib.ncnn_cuda_compute_record_download(self.cmd, g.dev_out, C.byref(m), self.opt) != 0:
+                    raise RuntimeError("record_download failed under capture")
+                g.host_out = m
+            else:
+                g.dev_out = self.enqueue_device(dev_in)
+        except Exception as e:  # the stream must leave capture mode whatever happened
+            err = e
+        ge = C.c_void_p()
+        r = lib.ncnn_cuda_graph_end_capture(self.stream, C.byref(ge))
+        g.kernels = self.launch_count() - n0
+        self.sync()  # nothing was enqueued (capture only records); hands the recorder's scratch blobs back to the pool
+        if err is not None or r != 0 or not ge.value:
+            g.close()
+            raise RuntimeError("graph capture failed: %s" % (err if err is not None else lib.ncnn_cuda_last_error().decode()))
+        g.exec = ge
+        return g
+
     # ---------------------------------------------------------------- timing helpers
     def event(self):
         e = C.c_void_p()
@@ -264,6 +320,42 @@ class Session(object):
         if self.net:
             lib.ncnn_net_destroy(self.net)
             self.net = None
+
+
+class Graph(object):
+    """an instantiated CUDA graph of one recorded walk (Session.capture); replay() enqueues it on the session's stream"""
+
+    def __init__(self, sess):
+        self.sess = sess
+        self.exec = None
+        self.dev_in = None    # owned only in the host_mat form
+        self.dev_out = None
+        self.host_out = None  # pinned output Mat (host_mat form): valid after replay() + Session.sync()
+        self.kernels = 0      # kernels recorded into the graph
+
+    def replay(self):
+        if self.sess.L.lib.ncnn_cuda_graph_launch(self.exec, self.sess.stream) != 0:
+            raise RuntimeError("graph launch failed: %s" % self.sess.L.lib.ncnn_cuda_last_error().decode())
+
+    def result(self):
+        """host_mat form: wait for the stream and read the pinned output Mat"""
+        self.sess.sync()
+        return self.sess.L.mat_to_numpy(self.host_out, force_batch=True).copy()
+
+    def close(self):
+        lib = self.sess.L.lib
+        if self.exec:
+            lib.ncnn_cuda_graph_destroy(self.exec)
+            self.exec = None
+        if self.host_out:
+            lib.ncnn_mat_destroy(self.host_out)
+            self.host_out = None
+        if self.dev_out:
+            lib.ncnn_cuda_mat_destroy(self.dev_out)
+            self.dev_out = None
+        if self.dev_in:
+            lib.ncnn_cuda_mat_destroy(self.dev_in)
+            self.dev_in = None
 
 
 def layer_work(param_text, profile):
