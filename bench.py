@@ -491,7 +491,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", tdir, "traffic.json")
         if traffic is None and os.path.exists(tpath) and batch == WORKLOADS[args.workload][1]:
             t = json.load(open(tpath)).get(args.workload)
-            if t and t.get("storage") == args.storage:
+            if t and t.get("storage") == args.storage and all(isinstance(t.get(k), (int, float)) and t[k] == t[k] for k in ("dram_read_bytes", "dram_write_bytes")):
                 # DRAM bytes of the dominant kernel family over one step, from the committed ncu --set full capture of this command
                 traffic = {"dram_bytes_per_step": t["dram_read_bytes"] + t["dram_write_bytes"], "launches": t["launches"], "source": "profiles/%s/traffic.json (ncu)" % tdir}
 
@@ -533,8 +533,9 @@ def main():
                     "h2d_gbs_per_gpu": h2d * args.steps / e2e_s / 1e9, "numa": numa,
                     "pixels_value": e2e_pixels_value, "pixels_h2d_bytes_per_step": h2d_pixels,
                     "pixels_decoded_value": e2e_decoded_value, "pixels_decoded_d2h_bytes_per_step": d2h_decoded,
-                    "mode": "each step = extractor.input(pinned host Mat) + extract(host Mat); steps dealt to %d host thread(s), one Extractor/stream per step; "
-                            "process, feeder threads and pinned buffers bound to the GPU's NUMA node" % nthreads},
+                    "mode": "each step = extractor.input(pinned host Mat) + extract(host Mat); steps dealt to %d host thread(s), one Extractor/stream per step; %s"
+                            % (nthreads, "process, feeder threads and pinned buffers bound to the GPU's NUMA node" if numa.get("node") is not None
+                               else "no NUMA binding (this box reports numa_node -1 for the GPU)")},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "fused_layers": sess.fused_layers}
     if sustained:
         line["sustained_value"] = sustained["value"]
@@ -581,10 +582,25 @@ def main():
         except Exception as e:  # the oracle library is test infrastructure: report, do not fail the product bench
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(_finite(line)))
     sess.close()
     group.close()
     return 0
+
+
+def _finite(o):
+    """NaN / inf are not JSON: a strict parser on the driver side must be able to read the line"""
+    if isinstance(o, float):
+        return o if o == o and o not in (float("inf"), float("-inf")) else None
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    if isinstance(o, np.floating):
+        return _finite(float(o))
+    if isinstance(o, np.integer):
+        return int(o)
+    return o
 
 
 def parity_check(sess, model, text, weights, x, storage):

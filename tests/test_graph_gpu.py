@@ -60,7 +60,7 @@ def test_graph_replay_whole_extract_squeezenet(storage):
         sess.close()
 
 
-@pytest.mark.parametrize("model,batch,size", [("resnet50", 4, 64), ("mobilenet_v2", 4, 64), ("yolov8s", 2, 96)])
+@pytest.mark.parametrize("model,batch,size", [("resnet50", 2, 224), ("mobilenet_v2", 4, 64), ("yolov8s", 2, 96)])
 def test_graph_replay_device_walk(model, batch, size):
     """device form: the walk only, input resident; replay == eager.  An eager walk recorded on the same recorder between two
     replays shares the graph's pool blocks (the stream orders them): its result is read before the next replay, which may
