@@ -149,6 +149,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+// Monotonic "tiles observed" word of an MMA-issuing warp (see the issuers in tc_gemm_kernel): unlike a parity wait, a comparison
+// against a counter cannot alias onto an earlier or later phase.
+__device__ __forceinline__ void obs_publish(uint32_t addr, int seq)
+{
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(addr), "r"(seq) : "memory");
+}
+
+__device__ __forceinline__ void obs_wait(uint32_t addr, int want)
+{
+    uint32_t spins = 0;
+    while (true)
+    {
+        int v;
+        asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= want) break;
+        if (++spins > (1u << 26))
+        {
+            printf("[ncnn_cuda tc_gemm] issuer wait timed out: block %d thread %d word 0x%x want %d have %d\n", blockIdx.x, threadIdx.x, addr, want, v);
+            __trap();
+        }
+    }
+}
+
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
 // its predecessor in the stream is still draining; everything before pdl_wait() (barrier / TMEM set-up, constant loads)
 // overlaps that tail, pdl_wait() returns once the predecessor has completed and its writes are visible.
@@ -746,6 +769,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* res_empty_bar = bars + 52;        // [kResSlots]
     uint64_t* bres_bar = bars + 56;             // A_ROWS: resident weights landed
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 57);
+    int* issuer_obs = reinterpret_cast<int*>(bars + 58); // [2]: last tile (per-CTA sequence number) whose operand stages each MMA issuer has seen land
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -786,6 +810,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(smem_u32(&tmem_empty_bar[i]), (BLOCK_N == 32 ? kEpilogueWarps / 2 : kEpilogueWarps) * CG);
         }
         mbar_init(smem_u32(bres_bar), 1);
+        issuer_obs[0] = -1;
+        issuer_obs[1] = -1;
         for (int i = 0; i < kResSlots; i++)
         {
             mbar_init(smem_u32(&res_full_bar[i]), 1);
@@ -1061,21 +1087,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int my_parity = warp == 1 ? 0 : 1;
         int tile_seq = 0;
         const int stages_per_tile = AMODE == A_ROWS ? 1 : (AMODE == A_SHIFT ? p.cblocks : p.num_k_blocks);
-        // Two issuers only when a ring stage is reused no sooner than kAccStages tiles later.  A parity wait separates "use n has
-        // landed" from "use n - 1 has landed" only for a waiter at most one phase ahead of its barrier, and TMA loads land out of
-        // order: an issuer that skips the other's tiles could otherwise reach the barrier of a stage whose previous use has not
-        // landed yet and sail through on stale data (this deadlocked MobileNetV2's 144 -> 24 + residual layer at full batch with the
-        // looser rule "consecutive tiles in disjoint stages").  With reuse distance >= kAccStages the tile's OWN accumulator wait
-        // is the guarantee: tmem_empty of tile t completes after the in-order epilogue has finished tile t - kAccStages, hence
-        // after every tile up to there -- including the stage's previous user -- was issued, i.e. had landed.  (No issuer waits on
-        // another issuer's stage: a late observer aliases the other way, onto a phase that can only complete after its own work.)
-        // Tiles with many k-blocks do not need a second issuer anyway (their MMAs outlast the bookkeeping): warp 1 takes them all.
-        // (32-wide tiles are read by alternate epilogue halves that do not wait for each other, so "in order" holds per parity only:
-        //  there the stage's previous user must be a tile of the SAME parity -- an even, exact reuse distance)
-        const bool dual_issue = kStages >= kAccStages * stages_per_tile && (BLOCK_N != 32 || kStages % (2 * stages_per_tile) == 0);
+        // Two issuers on alternate tiles when a tile takes at most half of the ring (tiles with many k-blocks do not need a second
+        // issuer: their MMAs outlast the bookkeeping, warp 1 takes them all).  What makes it safe: a parity wait separates "use n of a
+        // stage has landed" from "use n - 1 has landed" only for a waiter at most one phase ahead of its barrier, and TMA loads land out
+        // of order, so an issuer that skips the other's tiles could reach the barrier of a stage whose previous use has not landed yet
+        // and sail through on stale data (this deadlocked MobileNetV2's 144 -> 24 + residual layer at full batch); observing the other
+        // issuer's stages with more parity waits aliases the other way when the observer is late (that deadlocked the default bench).
+        // So the issuers tell each other through a MONOTONIC word: after the last `full` wait of its tile number q an issuer publishes
+        // q (release); before the first `full` wait of tile q the other issuer waits until it reads >= q - 1 (acquire).  Then every
+        // tile before q has been seen to land by one of the two (each walks its own tiles in order), in particular the previous use
+        // of every stage tile q touches, so each parity wait of tile q is at most one phase ahead.  No cycle: tile q - 1 never waits
+        // for anything tile q does.  The accumulator barriers are untouched by this: kAccStages is even, so a TMEM stage's previous
+        // use belongs to the same issuer (and, for 32-wide tiles, to the same epilogue half).
+        static_assert(kAccStages % 2 == 0, "two issuers: an accumulator stage must come back to the issuer that used it last");
+        const bool dual_issue = 2 * stages_per_tile <= kStages;
+        const uint32_t obs_mine = smem_u32(issuer_obs + my_parity), obs_other = smem_u32(issuer_obs + (my_parity ^ 1));
         for (int tile = tile_first; tile < (CG == 2 && cta_rank != 0 ? 0 : num_tiles); tile += tile_step)
         {
-            if (dual_issue ? ((tile_seq++ & 1) != my_parity) : (my_parity != 0))
+            const int seq = tile_seq++;
+            if (dual_issue ? ((seq & 1) != my_parity) : (my_parity != 0))
             {
                 // the other issuer's tile: step over its ring stages and its accumulator stage
                 stage += stages_per_tile;
@@ -1093,6 +1123,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
             tc_fence_after();
+            if (dual_issue && seq > 0) obs_wait(obs_other, seq - 1);
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
             if (AMODE == A_ROWS)
             {
@@ -1101,6 +1132,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // elected branch, filter rows unrolled for the common heights (measured on the ResNet stem: ~20 instructions per
                 // MMA made the issuing lane, not the tensor pipe, pace the kernel at 1.8 k cycles per tile)
                 mbar_wait(full0 + stage * 8, phase);
+                if (dual_issue) obs_publish(obs_mine, seq);
                 tc_fence_after();
                 const uint64_t a_hi = make_smem_desc_overlap16(0) & 0xFFFFFFFF00000000ull;
                 const uint32_t a_flags = (uint32_t)(make_smem_desc_overlap16(0) & 0xFFFFC000ull);
@@ -1175,12 +1207,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 };
                 for (int cb = 0; cb < p.cblocks; cb++)
                 {
+                    const bool last_cb = cb == p.cblocks - 1;
                     mbar_wait(full0 + stage * 8, phase);
+                    if (dual_issue && last_cb) obs_publish(obs_mine, seq);
                     tc_fence_after();
                     const uint32_t a_lo0 = (((smem_a0 + (uint32_t)(stage * p.sh_stage_bytes)) & 0x3FFFF) >> 4) | desc_lo_flags;
                     const uint32_t b_lo_cb = b_lo0 + (uint32_t)(cb * (Plan::b_bytes >> 4));
                     const uint32_t commit_bar = empty0 + stage * 8;
-                    const bool last_cb = cb == p.cblocks - 1;
                     if (p.taps_h == 3 && p.taps_w == 3)
                     {
                         if (elect_one())
@@ -1218,6 +1251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int kb = 0; kb < p.num_k_blocks; kb++)
                 {
                     mbar_wait(full0 + stage * 8, phase);
+                    if (dual_issue && kb == p.num_k_blocks - 1) obs_publish(obs_mine, seq);
                     tc_fence_after();
                     if (elect_one())
                     {
