@@ -10,9 +10,9 @@
 // W = weights re-packed once at create_pipeline time to [outch][taps * cblocks * BLOCK_K] K-major.
 //
 // Structure (one CTA per SM, persistent over output tiles, warp-specialised):
-//   warp 0 lane 0 : TMA producer      -- cp.async.bulk.tensor -> kStages-deep smem ring (128B-swizzled)
-//   warp 1 lane 0 : MMA issuer        -- tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM,
-//                                        2 accumulator stages so the epilogue of tile i overlaps tile i+1
+//   warp 0        : TMA producer      -- cp.async.bulk.tensor -> kStages-deep smem ring (128B-swizzled), one elected lane issues
+//   warps 1, 10   : MMA issuers       -- tcgen05.mma.cta_group::1/2.kind::f16 on alternate tiles, fp32 accumulators in TMEM,
+//                                        up to 8 accumulator stages (all 512 columns) so epilogues overlap the next tiles
 //   warps 2..9    : epilogue          -- tcgen05.ld TMEM->registers, +bias, +residual, activation, 32-byte stores;
 //                                        two warps per TMEM lane quarter, alternating 64-column chunks, no CTA-wide sync
 //   full/empty mbarriers between producer and MMA, tmem_full/tmem_empty between MMA and epilogue.
