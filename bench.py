@@ -16,6 +16,8 @@ seeded random-init weights; BASELINE.json: ResNet-50 224x224 batch 256).  Prints
              and frac_sustained next to `sustained` = the same step repeated for >= 2 s with its own clock record.
              roofline.depthwise: the MobileNetV2 batch-128 leg (the bandwidth configuration of BASELINE.json) run in the
              same invocation: depthwise layers' algorithmic bytes / their share of that step, as a fraction of HBM copy peak
+  launch_bound / graph  BASELINE.json configs[0] (SqueezeNet v1.1 batch 1): the walk eager and replayed as ONE CUDA graph per step
+             (runner.Session.capture), resident and through the whole extract
   parity     max|ours - reference| / max|reference| on samples picked from the benched batch, against oracle/_ref (the
              reference's own CPU fp32 path), for the dtype the line reports
   cpu_baseline  the reference's own CPU implementation (oracle/_ref, built from /root/reference) on this box's host
