@@ -36,7 +36,7 @@ class Bar(object):
         return (self.c & 1) != parity
 
 
-def simulate(variant, S, A, spt, tiles, halves, seed, max_steps=200000):
+def simulate(variant, S, A, spt, tiles, halves, seed, max_steps=200000, issuers=2):
     rng = random.Random(seed)
     full = [Bar() for _ in range(S)]
     empty = [Bar() for _ in range(S)]
@@ -44,7 +44,7 @@ def simulate(variant, S, A, spt, tiles, halves, seed, max_steps=200000):
     tempty = [Bar() for _ in range(A)]
     loads_in_flight = []   # stage indices; any of them may land next (TMA completes out of order across stages)
     mma_fifo = []          # commit lists in issue order: the tensor pipe retires MMAs in the order they were queued
-    obs = [-1, -1]         # the monotonic words of the `words` variant
+    obs = [-1] * issuers   # the monotonic words of the `words` variant
 
     if variant == "single":
         dual = False
@@ -71,7 +71,7 @@ def simulate(variant, S, A, spt, tiles, halves, seed, max_steps=200000):
     def issuer(me):
         stage, phase, acc, acc_phase = 0, 0, 0, 0
         for t in range(tiles):
-            mine = ((t & 1) == me) if dual else (me == 0)
+            mine = ((t % issuers) == me) if dual else (me == 0)
             if not mine:
                 for j in range(spt):
                     if variant == "observe" and dual:
@@ -88,9 +88,11 @@ def simulate(variant, S, A, spt, tiles, halves, seed, max_steps=200000):
                 yield
             if tempty[acc].c < t // A:
                 raise Stale("issuer %d reused accumulator stage %d of tile %d before the epilogue released it" % (me, acc, t))
-            if variant == "words" and dual and t > 0:
-                while obs[me ^ 1] < t - 1:
-                    yield
+            if variant == "words" and dual:
+                for other in range(issuers):  # each other issuer's last tile before t
+                    last = t - 1 - ((t - 1 - other) % issuers) if t > 0 else -1
+                    while other != me and last >= 0 and obs[other] < last:
+                        yield
             commits = []
             for j in range(spt):
                 g = t * spt + j
@@ -129,7 +131,7 @@ def simulate(variant, S, A, spt, tiles, halves, seed, max_steps=200000):
             if acc == A:
                 acc, acc_phase = 0, acc_phase ^ 1
 
-    agents = [producer(), issuer(0), issuer(1), epilogue(0)] + ([epilogue(1)] if halves else [])
+    agents = [producer()] + [issuer(i) for i in range(issuers)] + [epilogue(0)] + ([epilogue(1)] if halves else [])
     live = list(agents)
     idle = 0
     for _ in range(max_steps):
@@ -190,6 +192,15 @@ def test_checker_catches_the_variants_that_failed_on_the_gpu():
     observe = outcomes("observe", range(60))
     assert observe, observe                                                    # the default-bench failure (deadlock or stale pass)
     assert any(r == "deadlock" for r in observe.values()) or any(r.startswith("stale") for r in observe.values())
+
+
+@pytest.mark.parametrize("variant", ["strict", "words"])
+def test_three_issuers_of_the_fused_stem(variant):
+    """stem_pool_kernel: three issuers, 8 accumulator stages (an accumulator stage comes back to a DIFFERENT issuer: 8 % 3 != 0),
+    one ring stage per conv row, ring of 8 or more"""
+    for S in (8, 10, 16):
+        for seed in range(40):
+            assert simulate(variant, S, 8, 1, tiles=50, halves=False, seed=seed, issuers=3) == "ok", (S, seed)
 
 
 def test_words_protocol_uses_two_issuers_where_strict_cannot():
